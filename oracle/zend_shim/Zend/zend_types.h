@@ -1,0 +1,2 @@
+/* TEST INFRASTRUCTURE — Zend shim. */
+#include "zend.h"
