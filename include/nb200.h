@@ -1,0 +1,180 @@
+/*
+ * nb200.h — C-ABI of the B200-native device backend for NumPower's NDArray.
+ *
+ * This is the drop-in boundary (SURVEY.md §8 b).  In the reference the device
+ * backend is a link-time interface: two objects (`cuda_math.o`, `gpu_alloc.o`)
+ * exporting the `extern "C"` symbols of src/ndmath/cuda/cuda_math.h:14-79 and
+ * src/gpu_alloc.h:8-15, selected by `#ifdef HAVE_CUBLAS` at the call sites in
+ * src/ndmath/arithmetics.c, src/ndarray.c, src/ndmath/linalg.c.  libnb200.so
+ * exports
+ *   (1) the 64-bit entry points below (`nb200_*`): plain pointers and sizes,
+ *       int status returns, no torch / C++ types; and
+ *   (2) the exact legacy symbols (include/nb200_legacy.h) implemented on top of
+ *       (1), so the reference's unmodified host objects link against it.
+ *
+ * Conventions
+ *   - every function returns 0 (NB200_OK) or a negative NB200_E* code;
+ *     nb200_last_error() returns the message for the calling thread's last
+ *     failure (the host maps it to zend_throw_error).
+ *   - all array arguments are DEVICE pointers to fp32 unless the name says host.
+ *   - compute entry points are ASYNCHRONOUS on the context stream
+ *     (nb200_stream()); entry points that return a value to the host
+ *     (`*_host`) synchronise that stream before returning.
+ *   - ownership: the host allocates inputs and outputs through nb200_alloc;
+ *     the backend never frees host-visible arrays (same as vmalloc/vfree).
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails
+ *     with NB200_ENODEV.
+ */
+#ifndef NB200_H
+#define NB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_OK 0
+#define NB200_EINVAL (-1)  /* bad argument (shape, op id, alignment that cannot be served) */
+#define NB200_ECUDA (-2)   /* CUDA runtime / driver error, see nb200_last_error() */
+#define NB200_ENOMEM (-3)  /* device allocation failed ("device memory allocation failed", gpu_alloc.c:14-16) */
+#define NB200_ENODEV (-4)  /* no usable sm_100 device */
+#define NB200_EDOMAIN (-5) /* math domain error seen by a unary op (double_math.c:145-148 exit(1) in the reference) */
+
+#define NB200_MAX_DIMS 8
+
+/* Binary ops — replace cuda_{add,subtract,multiply,divide,mod,pow}_float
+ * (cuda_math.h:25-29,33) and the CPU-only NDArray_Maximum/Minimum
+ * (ndarray.c:852-931) and float_arctan2 (double_math.c:259).
+ * Semantics are the reference's CPU ones. */
+enum nb200_binary_op {
+    NB200_ADD = 0, NB200_SUB = 1, NB200_MUL = 2, NB200_DIV = 3,
+    NB200_MOD = 4,      /* a - floor(a/b)*b, fused multiply-subtract (arithmetics.c:787-806 AVX body) */
+    NB200_POW = 5, NB200_MAXIMUM = 6, NB200_MINIMUM = 7, NB200_ARCTAN2 = 8,
+    NB200_MOD_TRUNC = 9, /* fmodf: the reference's scalar tail / ref-GPU semantics (arithmetics.c:801) */
+    /* comparisons -> 1.0f / 0.0f masks, all ORDERED (any NaN operand -> 0, including != : _CMP_NEQ_OQ), as the
+     * _mm256_cmp_ps predicates of src/logic.c:121-660; replace cuda_float_compare_* (cuda_math.h:63,69-73) */
+    NB200_CMP_EQ = 10, NB200_CMP_NE = 11, NB200_CMP_GT = 12, NB200_CMP_GE = 13, NB200_CMP_LT = 14, NB200_CMP_LE = 15,
+    NB200_BIN_COUNT = 16
+};
+
+/* Unary ops — replace cuda_float_<op> (cuda_math.h:16-24,38-61,67,78-79) and
+ * NDArrayMathGPU_ElementWise* (:14-15,75-76).  Semantics follow the CPU functors
+ * of src/ndmath/double_math.c (line given), not the old .cu ones. */
+enum nb200_unary_op {
+    NB200_UN_ABS = 0,      /* :10  */ NB200_UN_SQRT = 1,     /* :19  */ NB200_UN_EXP = 2,      /* :28  */
+    NB200_UN_EXP2 = 3,     /* :37  */ NB200_UN_EXPM1 = 4,    /* :46  */ NB200_UN_LOG = 5,      /* :55  */
+    NB200_UN_LOG2 = 6,     /* :91  */ NB200_UN_LOG10 = 7,    /* :64  */ NB200_UN_LOG1P = 8,    /* :73  */
+    NB200_UN_LOGB = 9,     /* :82  */ NB200_UN_SIN = 10,     /* :99  */ NB200_UN_COS = 11,     /* :107 */
+    NB200_UN_TAN = 12,     /* :132 */ NB200_UN_ARCSIN = 13,  /* :140 */ NB200_UN_ARCCOS = 14,  /* :144 */
+    NB200_UN_ARCTAN = 15,  /* :152 */ NB200_UN_SINH = 16,    /* :164 */ NB200_UN_COSH = 17,    /* :168 */
+    NB200_UN_TANH = 18,    /* :172 */ NB200_UN_ARCSINH = 19, /* :176 */ NB200_UN_ARCCOSH = 20, /* :180 */
+    NB200_UN_ARCTANH = 21, /* :188 */ NB200_UN_DEGREES = 22, /* :156 */ NB200_UN_RADIANS = 23, /* :160 */
+    NB200_UN_RINT = 24,    /* :200 */ NB200_UN_FIX = 25,     /* :212 */ NB200_UN_TRUNC = 26,   /* :224 */
+    NB200_UN_FLOOR = 27,   /* :216 */ NB200_UN_CEIL = 28,    /* :220 */ NB200_UN_SINC = 29,    /* :228 */
+    NB200_UN_NEGATIVE = 30,/* :237 */ NB200_UN_POSITIVE = 31,/* :241 (== abs) */ NB200_UN_SIGN = 32, /* :246 */
+    NB200_UN_RECIPROCAL = 33, /* :263 */ NB200_UN_RSQRT = 34,/* :111 fast inverse sqrt, bit-exact */
+    NB200_UN_CLIP = 35,    /* :250 p0=min p1=max */
+    NB200_UN_ROUND = 36,   /* :254 p0=decimals */
+    NB200_UN_SQUARE = 37,  /* numpower.c:3093 Multiply(a,a) */
+    NB200_UN_COUNT = 38
+};
+
+enum nb200_reduce_op { NB200_SUM = 0, NB200_PROD = 1, NB200_MIN = 2, NB200_MAX = 3 };
+
+/* Axis-reduction order.  TREE: deterministic split of the axis (fast, HBM-bound);
+ * SEQUENTIAL: ((x0 op x1) op x2)... along the axis, the exact order of the
+ * reference's reduce()/_reduce() slice loop (ndarray.c:394-429) => bit-identical. */
+enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
+
+/* nd::matmul precision.  TF32X3 (default): error-compensated 3-pass TF32 on the
+ * tcgen05 tensor pipe, meets 1e-5 vs cblas_sgemm; TF32X1: single pass, fast mode. */
+enum nb200_gemm_precision { NB200_GEMM_TF32X3 = 0, NB200_GEMM_TF32X1 = 1 };
+
+/* ---- context / device -------------------------------------------------------- */
+/* Replaces the process-global cudaSetDevice of NDArray::setDevice (numpower.c:615-635). */
+int nb200_init(int device);
+int nb200_shutdown(void);
+int nb200_device_count(int *count);
+int nb200_set_device(int device);
+int nb200_get_device(int *device);
+int nb200_synchronize(void);
+const char *nb200_last_error(void);
+/* The CUDA stream (cudaStream_t) compute is enqueued on; nb200_set_stream lets a
+ * harness (e.g. torch.cuda.current_stream().cuda_stream) time with its own events. */
+void *nb200_stream(void);
+int nb200_set_stream(void *cuda_stream);
+/* Number of kernels this library has launched since init (bench.py "gpu_launches"). */
+int64_t nb200_launch_count(void);
+/* Returns and clears the sticky math-domain flag set by arccos/arccosh/arctanh
+ * (synchronises). 0 = none. */
+int nb200_poll_domain_error(int *flag);
+
+/* ---- memory: replaces vmalloc/vfree/vmemcpyd2d/vmemcpyh2d/NDArray_VFLOAT/vmemcheck
+ * (gpu_alloc.h:8-15) with 64-bit sizes. -------------------------------- */
+int nb200_alloc(void **dev_ptr, int64_t bytes);
+int nb200_free(void *dev_ptr);
+int nb200_copy_h2d(void *dev_dst, const void *host_src, int64_t bytes);
+int nb200_copy_d2h(void *host_dst, const void *dev_src, int64_t bytes);
+int nb200_copy_d2d(void *dev_dst, const void *dev_src, int64_t bytes);
+int nb200_memset_zero(void *dev_ptr, int64_t bytes);
+int nb200_mem_stats(int64_t *live_allocations, int64_t *live_bytes);
+/* pinned host staging (NDArray_ToGPU / ToCPU, ndarray.c:1037-1093, use pageable memcpy) */
+int nb200_host_alloc(void **host_ptr, int64_t bytes);
+int nb200_host_free(void *host_ptr);
+
+/* ---- elementwise --------------------------------------------------------------- */
+/* out[idx] = a[idx·a_strides] op b[idx·b_strides] over `out_shape` (C order, out
+ * contiguous).  Strides are in ELEMENTS; 0 = broadcast along that dim.  Replaces
+ * cuda_<op>_float + the NDArray_Broadcast materialisation (ndarray.c:1172-1294). */
+int nb200_ew_binary(int op, float *out, const float *a, const float *b, int ndim,
+                    const int64_t *out_shape, const int64_t *a_strides, const int64_t *b_strides);
+/* scalar operand passed by value: replaces the NDArray_Fill temp (arithmetics.c:169-181). */
+int nb200_ew_binary_scalar(int op, float *out, const float *a, float scalar, int scalar_is_lhs, int64_t n);
+/* out = a*b + c with two roundings (mul then add, no FMA): one pass instead of the
+ * two nd:: calls PHP makes for `$a * $b + $c` (numpower.c:193-229). */
+int nb200_ew_mul_add(float *out, const float *a, const float *b, const float *c, int ndim,
+                     const int64_t *out_shape, const int64_t *a_strides, const int64_t *b_strides,
+                     const int64_t *c_strides);
+/* out[i] = f(in[i]); out may alias in (the legacy cuda_float_<op> are in-place). */
+int nb200_ew_unary(int op, float *out, const float *in, int64_t n, float p0, float p1);
+int nb200_fill(float *out, float value, int64_t n);   /* cuda_fill_float, cuda_math.h:36 */
+
+/* ---- reductions ----------------------------------------------------------------- */
+/* Full reduction to a device scalar (async) / to the host (sync).  Replaces
+ * cuda_sum_float/cuda_prod_float/cuda_max_float/cuda_min_float (cuda_math.h:31-32,35,66).
+ * min/max follow the CPU NaN rule of NDArray_Min/Max (ndarray.c:752-772,939-959):
+ * NaN at index 0 sticks, NaN elsewhere is skipped.  Deterministic (fixed 2-stage tree). */
+int nb200_reduce_full(int op, float *dev_out, const float *in, int64_t n);
+int nb200_reduce_full_host(int op, float *host_out, const float *in, int64_t n);
+/* Input viewed as (outer, len, inner) contiguous; out (outer, inner).  Replaces the
+ * reduce()/_reduce() slice loop (ndarray.c:394-429,523-578) and NDArray_MaxAxis (:781-844). */
+int nb200_reduce_axis(int op, float *out, const float *in, int64_t outer, int64_t len, int64_t inner, int order);
+/* argmax/argmin along the middle dim of (outer, len, inner); out (outer, inner) holds the
+ * index as float32.  Semantics of float_argmax/float_argmin (calculation.c:9-59): first
+ * occurrence; argmax skips NaN unless it is element 0, argmin returns the first NaN.
+ * The reference has no GPU path ("GPU not supported.", calculation.c:75-78). */
+int nb200_argminmax(int is_max, float *out, const float *in, int64_t outer, int64_t len, int64_t inner);
+int nb200_argminmax_host(int is_max, float *host_out, const float *in, int64_t n);
+
+/* ---- matmul --------------------------------------------------------------------- */
+/* Row-major C[M,N] = A[M,K]·B[K,N] (alpha=1, beta=0).  Replaces the cublasSgemm call in
+ * NDArray_FMatmul (linalg.c:54-72).  tcgen05 TF32 tensor cores, fp32 accumulate in TMEM. */
+int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, int64_t N, int64_t K,
+                int64_t lda, int64_t ldb, int64_t ldc, int precision);
+/* batch of independent products; stride* in elements (0 = shared operand). */
+int nb200_sgemm_batched(float *C, const float *A, const float *B, int64_t batch, int64_t M, int64_t N, int64_t K,
+                        int64_t strideA, int64_t strideB, int64_t strideC, int precision);
+/* scratch the 3xTF32 split needs for an (M,N,K,batch) problem; allocated lazily from the
+ * context and reused (bytes reported for capacity planning). */
+int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes);
+/* y[rows] = A[rows,cols]·x[cols] — replaces cuda_float_multiply_matrix_vector (cuda_math.h:62). */
+int nb200_gemv(float *y, const float *A, const float *x, int64_t rows, int64_t cols);
+/* out[cols,rows] = in[rows,cols]^T, out != in — replaces cuda_float_transpose (cuda_math.h:77). */
+int nb200_transpose2d(float *out, const float *in, int64_t rows, int64_t cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NB200_H */

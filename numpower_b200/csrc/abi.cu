@@ -1,0 +1,262 @@
+// Context, error and memory entry points of the C-ABI (include/nb200.h).
+// Replaces src/gpu_alloc.c (vmalloc/vfree/vmemcpy*/NDArray_VFLOAT/vmemcheck, :11-54 in
+// /root/reference) with 64-bit sizes, status returns and an allocation ledger, and the
+// process-global cudaSetDevice of NDArray::setDevice (numpower.c:615-635).
+#include "common.cuh"
+#include <unordered_map>
+
+namespace nb200 {
+
+static Ctx g_ctx;
+static std::unordered_map<void *, int64_t> g_ledger;  // live device blocks handed to the host (vmalloc leak counter, gpu_alloc.c:12,31)
+static thread_local char g_err[512] = "";
+
+Ctx &ctx() { return g_ctx; }
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int init_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return set_error(NB200_ENODEV, "no CUDA device available (%s); libnb200 has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return set_error(NB200_EINVAL, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    NB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error(NB200_ENODEV, "device %d is sm_%d%d; libnb200 is built for sm_100a only", device, prop.major,
+                         prop.minor);
+    NB_CUDA(cudaSetDevice(device));
+    Ctx &c = g_ctx;
+    c.device = device;
+    c.num_sms = prop.multiProcessorCount;
+    NB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.own_stream = true;
+    NB_CUDA(cudaMalloc(&c.ticket, 4096 * sizeof(unsigned int)));
+    NB_CUDA(cudaMemset(c.ticket, 0, 4096 * sizeof(unsigned int)));
+    NB_CUDA(cudaMalloc(&c.domain_flag, sizeof(int)));
+    NB_CUDA(cudaMemset(c.domain_flag, 0, sizeof(int)));
+    NB_CUDA(cudaMalloc(&c.dev_result, 64));
+    NB_CUDA(cudaMallocHost(&c.host_result, 64));
+    c.scratch = nullptr;
+    c.scratch_bytes = 0;
+    c.gemm_ws = nullptr;
+    c.gemm_ws_bytes = 0;
+    c.ready = true;
+    return NB200_OK;
+}
+
+int ensure_ready() {
+    if (g_ctx.ready) return NB200_OK;
+    return init_device(0);
+}
+
+int ensure_scratch(int64_t bytes) {
+    Ctx &c = g_ctx;
+    if (bytes <= c.scratch_bytes) return NB200_OK;
+    if (c.scratch) {
+        NB_CUDA(cudaStreamSynchronize(c.stream));
+        NB_CUDA(cudaFree(c.scratch));
+        c.scratch = nullptr;
+        c.scratch_bytes = 0;
+    }
+    int64_t want = bytes < (int64_t)(1 << 20) ? (int64_t)(1 << 20) : bytes;
+    if (cudaMalloc(&c.scratch, (size_t)want) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(NB200_ENOMEM, "device memory allocation failed (scratch %lld bytes)", (long long)want);
+    }
+    c.scratch_bytes = want;
+    return NB200_OK;
+}
+
+int ensure_gemm_ws(int64_t bytes) {
+    Ctx &c = g_ctx;
+    if (bytes <= c.gemm_ws_bytes) return NB200_OK;
+    if (c.gemm_ws) {
+        NB_CUDA(cudaStreamSynchronize(c.stream));
+        NB_CUDA(cudaFree(c.gemm_ws));
+        c.gemm_ws = nullptr;
+        c.gemm_ws_bytes = 0;
+    }
+    if (cudaMalloc(&c.gemm_ws, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(NB200_ENOMEM, "device memory allocation failed (gemm workspace %lld bytes)", (long long)bytes);
+    }
+    c.gemm_ws_bytes = bytes;
+    return NB200_OK;
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+extern "C" int nb200_init(int device) {
+    if (ctx().ready) {
+        if (ctx().device == device) return NB200_OK;
+        int rc = nb200_shutdown();
+        if (rc != NB200_OK) return rc;
+    }
+    return init_device(device);
+}
+
+extern "C" int nb200_shutdown(void) {
+    Ctx &c = ctx();
+    if (!c.ready) return NB200_OK;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+    if (c.scratch) cudaFree(c.scratch);
+    if (c.gemm_ws) cudaFree(c.gemm_ws);
+    if (c.ticket) cudaFree(c.ticket);
+    if (c.domain_flag) cudaFree(c.domain_flag);
+    if (c.dev_result) cudaFree(c.dev_result);
+    if (c.host_result) cudaFreeHost(c.host_result);
+    int64_t launches = c.launches;
+    c = Ctx();
+    c.launches = launches;
+    return NB200_OK;
+}
+
+extern "C" int nb200_device_count(int *count) {
+    if (!count) return set_error(NB200_EINVAL, "null argument");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return set_error(NB200_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return NB200_OK;
+}
+
+extern "C" int nb200_set_device(int device) { return nb200_init(device); }
+
+extern "C" int nb200_get_device(int *device) {
+    NB_READY();
+    if (!device) return set_error(NB200_EINVAL, "null argument");
+    *device = ctx().device;
+    return NB200_OK;
+}
+
+extern "C" int nb200_synchronize(void) {
+    NB_READY();
+    NB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return NB200_OK;
+}
+
+extern "C" const char *nb200_last_error(void) { return g_err; }
+
+extern "C" void *nb200_stream(void) { return ctx().ready ? (void *)ctx().stream : nullptr; }
+
+extern "C" int nb200_set_stream(void *cuda_stream) {
+    NB_READY();
+    Ctx &c = ctx();
+    NB_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+    c.stream = static_cast<cudaStream_t>(cuda_stream);
+    c.own_stream = false;
+    return NB200_OK;
+}
+
+extern "C" int64_t nb200_launch_count(void) { return ctx().launches; }
+
+extern "C" int nb200_poll_domain_error(int *flag) {
+    NB_READY();
+    if (!flag) return set_error(NB200_EINVAL, "null argument");
+    Ctx &c = ctx();
+    int h = 0;
+    NB_CUDA(cudaMemcpyAsync(&h, c.domain_flag, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    NB_CUDA(cudaStreamSynchronize(c.stream));
+    if (h) NB_CUDA(cudaMemsetAsync(c.domain_flag, 0, sizeof(int), c.stream));
+    *flag = h;
+    return NB200_OK;
+}
+
+// ---- memory ------------------------------------------------------------------------
+extern "C" int nb200_alloc(void **dev_ptr, int64_t bytes) {
+    NB_READY();
+    if (!dev_ptr || bytes < 0) return set_error(NB200_EINVAL, "nb200_alloc: bad argument");
+    *dev_ptr = nullptr;
+    size_t sz = bytes == 0 ? 16 : (size_t)bytes;
+    if (cudaMalloc(dev_ptr, sz) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(NB200_ENOMEM, "device memory allocation failed");  // gpu_alloc.c:15 message
+    }
+    ctx().live_allocs++;
+    ctx().live_bytes += bytes;
+    g_ledger[*dev_ptr] = bytes;
+    return NB200_OK;
+}
+
+extern "C" int nb200_free(void *dev_ptr) {
+    NB_READY();
+    if (!dev_ptr) return NB200_OK;
+    // cudaFree synchronises the device, so no kernel on the context stream can still use the block
+    auto it = g_ledger.find(dev_ptr);
+    if (it == g_ledger.end()) return set_error(NB200_EINVAL, "nb200_free: pointer %p was not allocated by nb200_alloc", dev_ptr);
+    NB_CUDA(cudaFree(dev_ptr));
+    ctx().live_allocs--;
+    ctx().live_bytes -= it->second;
+    g_ledger.erase(it);
+    return NB200_OK;
+}
+
+extern "C" int nb200_copy_h2d(void *dev_dst, const void *host_src, int64_t bytes) {
+    NB_READY();
+    if (bytes < 0 || (bytes > 0 && (!dev_dst || !host_src))) return set_error(NB200_EINVAL, "nb200_copy_h2d: bad argument");
+    NB_CUDA(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx().stream));
+    NB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return NB200_OK;
+}
+
+extern "C" int nb200_copy_d2h(void *host_dst, const void *dev_src, int64_t bytes) {
+    NB_READY();
+    if (bytes < 0 || (bytes > 0 && (!host_dst || !dev_src))) return set_error(NB200_EINVAL, "nb200_copy_d2h: bad argument");
+    NB_CUDA(cudaMemcpyAsync(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    NB_CUDA(cudaStreamSynchronize(ctx().stream));
+    return NB200_OK;
+}
+
+extern "C" int nb200_copy_d2d(void *dev_dst, const void *dev_src, int64_t bytes) {
+    NB_READY();
+    if (bytes < 0 || (bytes > 0 && (!dev_dst || !dev_src))) return set_error(NB200_EINVAL, "nb200_copy_d2d: bad argument");
+    NB_CUDA(cudaMemcpyAsync(dev_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+    return NB200_OK;
+}
+
+extern "C" int nb200_memset_zero(void *dev_ptr, int64_t bytes) {
+    NB_READY();
+    if (bytes < 0 || (bytes > 0 && !dev_ptr)) return set_error(NB200_EINVAL, "nb200_memset_zero: bad argument");
+    NB_CUDA(cudaMemsetAsync(dev_ptr, 0, (size_t)bytes, ctx().stream));
+    return NB200_OK;
+}
+
+extern "C" int nb200_mem_stats(int64_t *live_allocations, int64_t *live_bytes) {
+    if (live_allocations) *live_allocations = ctx().live_allocs;
+    if (live_bytes) *live_bytes = ctx().live_bytes;
+    return NB200_OK;
+}
+
+extern "C" int nb200_host_alloc(void **host_ptr, int64_t bytes) {
+    NB_READY();
+    if (!host_ptr || bytes < 0) return set_error(NB200_EINVAL, "nb200_host_alloc: bad argument");
+    if (cudaMallocHost(host_ptr, bytes == 0 ? 16 : (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(NB200_ENOMEM, "pinned host allocation failed");
+    }
+    return NB200_OK;
+}
+
+extern "C" int nb200_host_free(void *host_ptr) {
+    NB_READY();
+    if (host_ptr) NB_CUDA(cudaFreeHost(host_ptr));
+    return NB200_OK;
+}

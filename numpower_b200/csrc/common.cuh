@@ -1,0 +1,90 @@
+// Shared context, error plumbing and load/store helpers for libnb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include "../../include/nb200.h"
+
+#ifndef NB200_NUM_SMS_DEFAULT
+#define NB200_NUM_SMS_DEFAULT 148
+#endif
+
+namespace nb200 {
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    int num_sms = NB200_NUM_SMS_DEFAULT;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // scratch for two-stage reductions / split-axis partials (device)
+    void *scratch = nullptr;
+    int64_t scratch_bytes = 0;
+    // GEMM workspace (3xTF32 lo parts)
+    void *gemm_ws = nullptr;
+    int64_t gemm_ws_bytes = 0;
+    unsigned int *ticket = nullptr;       // last-block-done counters
+    int *domain_flag = nullptr;           // sticky math-domain flag (device)
+    float *host_result = nullptr;         // pinned 64-byte result slot
+    float *dev_result = nullptr;          // device result slot
+    int64_t live_allocs = 0;
+    int64_t live_bytes = 0;
+    int64_t launches = 0;
+};
+
+Ctx &ctx();
+int set_error(int code, const char *fmt, ...);
+int ensure_ready();
+int ensure_scratch(int64_t bytes);
+int ensure_gemm_ws(int64_t bytes);
+
+#define NB_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return nb200::set_error(NB200_ECUDA, "%s failed: %s (%s:%d)", #expr,               \
+                                    cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)
+
+#define NB_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        nb200::ctx().launches++;                                                              \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return nb200::set_error(NB200_ECUDA, "kernel launch failed: %s (%s:%d)",           \
+                                    cudaGetErrorString(_e), __FILE__, __LINE__);               \
+    } while (0)
+
+#define NB_READY()                                  \
+    do {                                            \
+        int _r = nb200::ensure_ready();             \
+        if (_r != NB200_OK) return _r;              \
+    } while (0)
+
+// ---- streaming 128-bit global access ------------------------------------------------
+// Inputs of the elementwise / reduction kernels are touched exactly once: read through
+// the non-coherent path without allocating in L1, store with the streaming policy.
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, const float4 &v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream(float *p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace nb200

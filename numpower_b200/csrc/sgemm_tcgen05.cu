@@ -1,0 +1,657 @@
+// nd::matmul on the Blackwell tensor pipe: C[M,N] = A[M,K] . B[K,N], row-major fp32 in/out,
+// TF32 multiplies on tcgen05 with fp32 accumulation in TMEM.  Replaces the cublasSgemm call
+// of NDArray_FMatmul (src/ndmath/linalg.c:54-72 in /root/reference); the CPU oracle is
+// cblas_sgemm (linalg.c:75-79).
+//
+// Structure (one persistent CTA — or CTA pair — per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B swizzle) global -> smem ring, mbarrier tx
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.kind::tf32 (smem descriptors),
+//               tcgen05.commit releases smem slots / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld TMEM -> registers -> st.global.v4, overlapped with the next
+//               tile's mainloop through a 2-deep TMEM accumulator ring
+//
+// Operand layouts in shared memory (per pipeline stage, BK = 32 fp32 = one 128-byte swizzle row):
+//   A tile  (BM x BK)  K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO = 1024)
+//   B tile  (BK x BN)  MN-major: B is row-major [K,N], i.e. N is contiguous -> loaded untransposed
+//           as BN/32 chunks of [32 k-rows x 128 B]; chunk stride = LBO = 4096 B, 8-k-row groups
+//           1024 B apart (SBO).  One K=8 MMA consumes one 8-row group of every chunk.
+//
+// Precision modes (include/nb200.h):
+//   TF32X1  operands are fed as raw fp32 (the tensor core reads the top 19 bits)
+//   TF32X3  error-compensated: a = a_hi + a_lo (both TF32-representable, produced by a split
+//           pre-pass), C = a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  — three MMAs per k-step, fp32-class accuracy
+//
+// Flops: 2*M*N*K useful (x3 executes 6*M*N*K on the tensor pipe).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace nb200 {
+
+// ------------------------------------------------------------------ configuration
+template <int CG_, int BN_, int PASSES_>
+struct GemmCfg {
+    static constexpr int CG = CG_;                       // CTAs cooperating on one MMA (cta_group)
+    static constexpr int BN = BN_;                       // tile columns (per CTA pair when CG == 2)
+    static constexpr int PASSES = PASSES_;               // 1 = TF32x1, 3 = TF32x3
+    static constexpr int BM = 128;                       // rows per CTA (TMEM lanes)
+    static constexpr int BK = 32;                        // fp32 per stage along K = 128 B
+    static constexpr int UMMA_K = 8;                     // tf32: 32 B of K per instruction
+    static constexpr int BN_CTA = BN / CG;               // B columns staged by each CTA
+    static constexpr int NPART = PASSES == 3 ? 2 : 1;    // hi (+ lo)
+    static constexpr int A_BYTES = BM * BK * 4;          // 16 KiB
+    static constexpr int B_BYTES = BN_CTA * BK * 4;
+    static constexpr int STAGE_BYTES = NPART * (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
+    static constexpr int ACC_STAGES = 2;
+    static constexpr int TMEM_COLS = ACC_STAGES * BN;    // 256 or 512 (power of two)
+    static constexpr int THREADS = 192;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "need at least a double buffer");
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+};
+
+struct GemmParams {
+    float *C;
+    int64_t M, N, K, ldc, strideC;
+    int64_t batch;
+    int tiles_m, tiles_n;      // tiles per matrix
+    int64_t total_tiles;
+    int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
+    unsigned int *debug;       // [0] = timeout flag, [1..] = info
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// shared::cluster address of the same smem offset in CTA rank 0 of the cluster (the MMA leader)
+__device__ __forceinline__ uint32_t map_to_leader(uint32_t addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0));
+    return r;
+}
+// arrive on the barrier at the same offset in the leader CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(map_to_leader(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int *debug, uint32_t tag) {
+    for (uint32_t spin = 0; spin < (1u << 26); spin++)
+        if (mbar_try_wait(bar, parity)) return;
+    if (debug) {
+        debug[0] = 1u;
+        debug[1] = tag;
+        debug[2] = blockIdx.x;
+        debug[3] = parity;
+    }
+    __threadfence_system();
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    } else {
+        // both CTAs of the pair post their bytes on the LEADER's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(dst), "l"(map), "r"(map_to_leader(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+template <int CG>
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// all previously issued MMAs complete -> one arrival on `bar` (in both CTAs of a pair when CG == 2)
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+            ::"r"(bar), "h"((uint16_t)0x3) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (64-bit), SM100 format:
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
+//   [46,48) version = 1       | [49,52) base offset = 0          | [61,64) layout: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (32-bit): D=f32 (bits 4-5 =1), A=B=tf32 (bits 7-9, 10-12 =2), A K-major (bit 15 =0),
+// B MN-major (bit 16 =1), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const GemmParams p) {
+    constexpr int CG = Cfg::CG, BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+    constexpr int PASSES = Cfg::PASSES, NPART = Cfg::NPART;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+    // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
+    auto a_smem = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + part * Cfg::A_BYTES; };
+    auto b_smem = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + NPART * Cfg::A_BYTES + part * Cfg::B_BYTES; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = (rank == 0);
+    const int64_t cluster_id = blockIdx.x / CG;
+    const int64_t num_clusters = gridDim.x / CG;
+    const int num_kb = (int)((p.K + BK - 1) / BK);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA_hi);
+        tma_prefetch_desc(&tmB_hi);
+        if (PASSES == 3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<CG>(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+    const int64_t tiles_per_mat = (int64_t)p.tiles_m * p.tiles_n;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
+                const int m_tile = (int)(r % p.tiles_m), n_tile = (int)(r / p.tiles_m);
+                const int row0 = m_tile * BM * CG + (int)rank * BM;
+                const int col0 = n_tile * BN + (int)rank * Cfg::BN_CTA;
+                const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u, p.debug, 0x100u + stage);
+                    if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES * CG);
+                    const int k0 = kb * BK;
+                    tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
+                    if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
+#pragma unroll
+                    for (int j = 0; j < Cfg::BN_CTA / 32; j++) {
+                        tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
+                        if (PASSES == 3)
+                            tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * 4096, col0 + j * 32, k0, bb);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM * CG, BN);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        // x3 order: small cross terms first, then the leading product
+                        constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+#pragma unroll
+                        for (int ps = 0; ps < PASSES; ps++) {
+                            const int ia = PASSES == 3 ? pa[ps] : 0, ib = PASSES == 3 ? pb[ps] : 0;
+#pragma unroll
+                            for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                const uint64_t da = make_smem_desc(a_smem(stage, ia) + k * 32, 16, 1024);
+                                const uint64_t db = make_smem_desc(b_smem(stage, ib) + k * 1024, 4096, 1024);
+                                umma_tf32<CG>(d_tmem, da, db, idesc, (kb | ps | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit<CG>(empty_bar(stage));
+                        if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
+        for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
+            const int m_tile = (int)(r % p.tiles_m), n_tile = (int)(r / p.tiles_m);
+            const int64_t row = (int64_t)m_tile * BM * CG + (int64_t)rank * BM + quarter * 32 + lane;
+            const int64_t col0 = (int64_t)n_tile * BN;
+            float *crow = p.C + b * p.strideC + row * p.ldc;
+            mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                const int64_t col = col0 + c * 32;
+                if (row < p.M) {
+                    if (vec_ok && col + 32 <= p.N) {
+                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; q++)
+                            if (col + q < p.N) crow[col + q] = __uint_as_float(v[q]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
+                else mbar_arrive_local(tempty_bar(acc));
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    // ---- teardown: everyone done with TMEM before it is released
+    __syncwarp();  // reconverge the single-lane producer / issuer warps before aligned barriers
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ TF32 split pre-pass (x3)
+// hi = rna_tf32(a) (low 13 bits zero), lo = rna_tf32(a - hi): a == hi + lo up to 2^-22 |a|.
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in, float *__restrict__ hi,
+                                                         float *__restrict__ lo, int64_t n) {
+    const int64_t n4 = n >> 2;
+    const float4 *in4 = reinterpret_cast<const float4 *>(in);
+    float4 *hi4 = reinterpret_cast<float4 *>(hi), *lo4 = reinterpret_cast<float4 *>(lo);
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 a = ldg_stream(in4 + i), h, l;
+        h.x = to_tf32(a.x); h.y = to_tf32(a.y); h.z = to_tf32(a.z); h.w = to_tf32(a.w);
+        l.x = to_tf32(a.x - h.x); l.y = to_tf32(a.y - h.y); l.z = to_tf32(a.z - h.z); l.w = to_tf32(a.w - h.w);
+        hi4[i] = h;
+        lo4[i] = l;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        int64_t i = (n4 << 2) + threadIdx.x;
+        float h = to_tf32(in[i]);
+        hi[i] = h;
+        lo[i] = to_tf32(in[i] - h);
+    }
+}
+
+// ------------------------------------------------------------------ SIMT fp32 GEMM (small / unaligned shapes)
+// 64x64 tile, BK = 16, 256 threads x (4x4) micro-tile, fp32 FMA, k in increasing order.
+__global__ void __launch_bounds__(256) sgemm_simt_kernel(float *__restrict__ C, const float *__restrict__ A,
+                                                         const float *__restrict__ B, int64_t M, int64_t N, int64_t K,
+                                                         int64_t lda, int64_t ldb, int64_t ldc, int64_t sA, int64_t sB,
+                                                         int64_t sC) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int64_t b = blockIdx.z;
+    A += b * sA; B += b * sB; C += b * sC;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int64_t m0 = (int64_t)blockIdx.y * 64, n0 = (int64_t)blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int64_t k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int r = i / 16, c = i % 16;
+            As[c][r] = (m0 + r < M && k0 + c < K) ? A[(m0 + r) * lda + k0 + c] : 0.f;
+            int rk = i / 64, cn = i % 64;
+            Bs[rk][cn] = (k0 + rk < K && n0 + cn < N) ? B[(k0 + rk) * ldb + n0 + cn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a[i] = As[kk][ty * 4 + i]; bb[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
+            if (r < M && c < N) C[r * ldc + c] = acc[i][j];
+        }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D map over (inner, rows, batch) of a row-major fp32 matrix stack; box = (32, box_rows, 1), 128B swizzle.
+static int make_map(CUtensorMap *map, const float *base, int64_t inner, int64_t rows, int64_t ld, int64_t batch,
+                    int64_t batch_stride, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error(NB200_ECUDA, "cuTensorMapEncodeTiled unavailable");
+    if (batch_stride == 0 || batch < 1) { batch = 1; batch_stride = rows * ld; }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch_stride * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(NB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return NB200_OK;
+}
+
+struct GemmArgs {
+    float *C;
+    const float *A, *B, *A_lo, *B_lo;   // A/B are the "hi" (or raw) operands
+    int64_t batch, M, N, K, lda, ldb, ldc, sA, sB, sC;
+};
+
+template <class Cfg>
+static int launch_gemm(const GemmArgs &g) {
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map(&ma_hi, g.A, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM)) != NB200_OK) return rc;
+    if ((rc = make_map(&mb_hi, g.B, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK)) != NB200_OK) return rc;
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+    if (Cfg::PASSES == 3) {
+        if ((rc = make_map(&ma_lo, g.A_lo, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM)) != NB200_OK) return rc;
+        if ((rc = make_map(&mb_lo, g.B_lo, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK)) != NB200_OK) return rc;
+    }
+    GemmParams p;
+    p.C = g.C; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.strideC = g.sC; p.batch = g.batch;
+    p.tiles_m = (int)((g.M + Cfg::BM * Cfg::CG - 1) / (Cfg::BM * Cfg::CG));
+    p.tiles_n = (int)((g.N + Cfg::BN - 1) / Cfg::BN);
+    p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * g.batch;
+    p.a_batched = g.sA != 0;
+    p.b_batched = g.sB != 0;
+    // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
+    p.debug = reinterpret_cast<unsigned int *>(ctx().host_result) + 4;
+    auto kern = sgemm_tf32_kernel<Cfg>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int64_t clusters = ctx().num_sms / Cfg::CG;
+    if (clusters > p.total_tiles) clusters = p.total_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * Cfg::CG));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = ctx().stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Cfg::CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
+    ctx().launches++;
+    return NB200_OK;
+}
+
+static int launch_split(const float *in, float *hi, float *lo, int64_t n) {
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    int64_t cap = (int64_t)ctx().num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in, hi, lo, n);
+    NB_LAUNCH_CHECK();
+    return NB200_OK;
+}
+
+static inline int64_t span(int64_t batch, int64_t stride, int64_t rows, int64_t ld, int64_t cols) {
+    int64_t one = (rows - 1) * ld + cols;
+    return stride == 0 ? one : (batch - 1) * stride + one;
+}
+static inline int64_t round4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+// variant: 0 = auto; otherwise (CG<<8 | BN) for experiments (NB200_GEMM_VARIANT env)
+static int g_variant = -1;
+static int gemm_variant() {
+    if (g_variant < 0) {
+        const char *e = getenv("NB200_GEMM_VARIANT");
+        g_variant = e ? atoi(e) : 0;
+    }
+    return g_variant;
+}
+
+template <int PASSES>
+static int dispatch_cfg(const GemmArgs &g) {
+    int v = gemm_variant();
+    int cg = v ? (v >> 8) : 1;
+    int bn = v ? (v & 0xFF) * 2 : 256;   // encoded as BN/2 to fit a byte: 64 -> 128, 128 -> 256
+    if (cg == 2 && bn == 256) return launch_gemm<GemmCfg<2, 256, PASSES>>(g);
+    if (cg == 2 && bn == 128) return launch_gemm<GemmCfg<2, 128, PASSES>>(g);
+    if (cg == 1 && bn == 128) return launch_gemm<GemmCfg<1, 128, PASSES>>(g);
+    return launch_gemm<GemmCfg<1, 256, PASSES>>(g);
+}
+
+static bool tensor_path_ok(const GemmArgs &g) {
+    auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return al(g.A) && al(g.B) && (g.lda % 4 == 0) && (g.ldb % 4 == 0) && (g.sA % 4 == 0) && (g.sB % 4 == 0) &&
+           g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
+}
+
+static int gemm_impl(GemmArgs g, int precision) {
+    if (g.batch == 0 || g.M == 0 || g.N == 0) return NB200_OK;
+    if (g.K == 0) {
+        for (int64_t b = 0; b < g.batch; b++)
+            for (int64_t r = 0; r < g.M; r++)
+                NB_CUDA(cudaMemsetAsync(g.C + b * g.sC + r * g.ldc, 0, (size_t)g.N * 4, ctx().stream));
+        return NB200_OK;
+    }
+    if (!tensor_path_ok(g) || getenv("NB200_GEMM_FORCE_SIMT")) {
+        dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
+        if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
+        sgemm_simt_kernel<<<grid, 256, 0, ctx().stream>>>(g.C, g.A, g.B, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA,
+                                                          g.sB, g.sC);
+        NB_LAUNCH_CHECK();
+        return NB200_OK;
+    }
+    if (precision == NB200_GEMM_TF32X1) return dispatch_cfg<1>(g);
+    // ---- TF32x3: split pre-pass into the context workspace, batch processed in chunks
+    const int64_t one_a = round4(span(1, 0, g.M, g.lda, g.K)), one_b = round4(span(1, 0, g.K, g.ldb, g.N));
+    int64_t chunk = g.batch;
+    const int64_t budget = (int64_t)4 << 30;  // 4 GiB of workspace per chunk at most
+    if (g.batch > 1) {
+        int64_t per = 2 * 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0));
+        if (per > 0 && per * chunk > budget) chunk = budget / per;
+        if (chunk < 1) chunk = 1;
+    }
+    for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
+        const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
+        const int64_t na = round4(span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K));
+        const int64_t nbb = round4(span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N));
+        (void)one_a; (void)one_b;
+        int rc = ensure_gemm_ws((2 * na + 2 * nbb) * 4 + 256);
+        if (rc != NB200_OK) return rc;
+        float *ws = static_cast<float *>(ctx().gemm_ws);
+        float *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
+        const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
+        if (b0 == 0 || g.sA) { if ((rc = launch_split(a_src, a_hi, a_lo, span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K))) != NB200_OK) return rc; }
+        if (b0 == 0 || g.sB) { if ((rc = launch_split(b_src, b_hi, b_lo, span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N))) != NB200_OK) return rc; }
+        GemmArgs c = g;
+        c.batch = nb;
+        c.A = a_hi; c.A_lo = a_lo; c.B = b_hi; c.B_lo = b_lo;
+        c.C = g.C + b0 * g.sC;
+        if ((rc = dispatch_cfg<3>(c)) != NB200_OK) return rc;
+    }
+    return NB200_OK;
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+extern "C" int nb200_sgemm_batched(float *C, const float *A, const float *B, int64_t batch, int64_t M, int64_t N,
+                                   int64_t K, int64_t strideA, int64_t strideB, int64_t strideC, int precision) {
+    NB_READY();
+    if (!C || !A || !B || batch < 0 || M < 0 || N < 0 || K < 0 || strideA < 0 || strideB < 0 || strideC < 0)
+        return set_error(NB200_EINVAL, "nb200_sgemm_batched: bad argument");
+    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3)
+        return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
+    GemmArgs g{C, A, B, nullptr, nullptr, batch, M, N, K, K, N, N, strideA, strideB, strideC};
+    return gemm_impl(g, precision);
+}
+
+extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, int64_t N, int64_t K, int64_t lda,
+                           int64_t ldb, int64_t ldc, int precision) {
+    NB_READY();
+    if (!C || !A || !B || M < 0 || N < 0 || K < 0 || lda < K || ldb < N || ldc < N)
+        return set_error(NB200_EINVAL, "Shape mismatch for matmul (M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
+                         (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
+    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3)
+        return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
+    GemmArgs g{C, A, B, nullptr, nullptr, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
+    return gemm_impl(g, precision);
+}
+
+extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes) {
+    if (!bytes) return set_error(NB200_EINVAL, "null argument");
+    if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
+    int64_t per = 2 * 4 * (round4(M * K) + round4(K * N));
+    int64_t total = per * batch;
+    const int64_t budget = (int64_t)4 << 30;
+    *bytes = (total > budget && batch > 1) ? (budget / per > 0 ? (budget / per) * per : per) : total;
+    return NB200_OK;
+}

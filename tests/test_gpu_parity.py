@@ -1,0 +1,422 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).
+
+Every test drives the CUDA path through the C-ABI (libnb200.so via the host mirror) and checks it
+against the oracle (the reference's own CPU object code when oracle/_ref is present, else the C port)
+on the same seeded inputs.  Bars (BASELINE.json north_star): bit-exact for arithmetic / index work,
+<= 1e-5 relative for fp32 transcendental and matmul results (tolerance written at each assert).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import assert_php_equal, load_golden, php14, rel_err, run_golden_record
+
+pytestmark = pytest.mark.gpu
+
+ORACLE = oracle.ref if oracle.ref.available else oracle.port
+RTOL = 1e-5  # north_star: "within 1e-5 relative for fp32"
+
+EXACT_OPS = {"add", "sub", "mul", "div", "mod", "abs", "sign", "square", "ceil", "fix", "floor", "rint", "round",
+             "trunc", "clip", "sqrt", "sum", "prod", "max", "min", "matmul", "degrees", "radians"}
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import numpower_b200 as nb
+    nb.lib()  # must load: no fallback
+    return nb
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def eq_zero_sign_free(g, e):
+    """Bit-exact up to the sign of zero (the reference itself does not pin it: its AVX body turns
+    every zero product into -0.0 and its scalar tail into +0.0, arithmetics.c:280-284,409-416)."""
+    g, e = np.asarray(g), np.asarray(e)
+    assert g.shape == e.shape, (g.shape, e.shape)
+    both_nan = np.isnan(g) & np.isnan(e)
+    ok = (g == e) | both_nan
+    assert ok.all(), f"{(~ok).sum()} mismatches, first at {np.argwhere(~ok)[0]}: {g[~ok][0]!r} vs {e[~ok][0]!r}"
+
+
+# --------------------------------------------------------------------- golden vectors
+RECS = load_golden()
+IDS = [f"{r['file'].split('/')[-1].split('.')[0]}#{i}" for i, r in enumerate(RECS)]
+
+
+@pytest.mark.parametrize("rec", RECS, ids=IDS)
+def test_phpt_golden_on_gpu(nb, rec):
+    got = run_golden_record(nb.GoldenBackend, rec)
+    if rec["op"] in EXACT_OPS:
+        assert_php_equal(got, rec["expected"], rec["file"])
+    else:  # libm-backed functors: CUDA libm vs glibc differ by <= 1-2 ulp
+        got = np.asarray(got, np.float32).reshape(-1)
+        for g, e in zip(got, rec["expected"]):
+            if math.isnan(e):
+                assert math.isnan(float(g))
+            else:
+                assert abs(php14(g) - e) <= RTOL * abs(e) + 1e-12, (rec["file"], g, e)
+
+
+# --------------------------------------------------------------------- binary elementwise
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div", "mod", "pow", "maximum", "minimum", "arctan2"])
+@pytest.mark.parametrize("n", [1, 7, 8, 1000, 4099, 1 << 20])
+def test_binary_flat_vs_oracle(nb, op, n):
+    r = _rng(n + len(op))
+    a = (r.random(n, dtype=np.float32) * 8 - 4).astype(np.float32)
+    b = (r.random(n, dtype=np.float32) * 3 + 0.25).astype(np.float32)
+    if op == "pow":
+        a = np.abs(a) + 0.1
+    A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
+    got = nb.nd.binary(op, A, B).toArray()
+    exp = ORACLE.binary(op, a, b)
+    if op in ("pow", "arctan2"):
+        assert rel_err(got, exp).max() <= RTOL
+    elif op == "mod":
+        # the reference computes the first (n//8)*8 elements with the fused floored formula and the
+        # tail with fmodf (arithmetics.c:787-806); same-sign operands agree everywhere up to rounding
+        nbody = (n // 8) * 8
+        eq_zero_sign_free(got[:nbody], exp[:nbody])
+    else:
+        eq_zero_sign_free(got, exp)
+
+
+def test_mod_mixed_signs_body_is_floored(nb):
+    r = _rng(77)
+    n = 4096
+    a = (r.random(n, dtype=np.float32) * 20 - 10).astype(np.float32)
+    b = (r.random(n, dtype=np.float32) * 4 - 2).astype(np.float32)
+    b[np.abs(b) < 0.1] = 0.5
+    got = nb.nd.mod(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    eq_zero_sign_free(got, ORACLE.binary("mod", a, b))  # n % 8 == 0: all body
+
+
+BCAST = [((512, 384), ()), ((512, 384), (384,)), ((300, 257), (257,)), ((640, 128), (640, 1)), ((64, 64), (1, 64)),
+         ((33, 5), (33, 1)), ((7, 1), (7, 9))]
+
+
+@pytest.mark.parametrize("sa,sb", BCAST)
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div"])
+def test_binary_broadcast_vs_oracle(nb, sa, sb, op):
+    r = _rng(len(sa) * 31 + len(sb))
+    a = r.standard_normal(sa).astype(np.float32)
+    b = (r.standard_normal(sb) + 3).astype(np.float32)
+    A = nb.NDArray.array(a).gpu()
+    B = nb.NDArray.array(b).gpu() if b.ndim else nb.NDArray.array(b)
+    eq_zero_sign_free(nb.nd.binary(op, A, B).toArray(), ORACLE.binary(op, a, b))
+    eq_zero_sign_free(nb.NDArray(nb.lib().NB_NDArray_Binary(nb.ndarray.BIN[op], B._h, A._h)).toArray(),
+                      ORACLE.binary(op, b, a))
+
+
+def test_general_nd_broadcast_matches_numpy_semantics(nb):
+    """Stride-0 broadcasting is a superset of the reference's special cases."""
+    r = _rng(5)
+    a = r.standard_normal((4, 1, 6, 5)).astype(np.float32)
+    b = r.standard_normal((3, 1, 5)).astype(np.float32)
+    got = nb.nd.add(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    np.testing.assert_array_equal(got, a + b)
+
+
+def test_views_unaligned_rows(nb):
+    """$a[i] views are only 4-byte aligned: row 1 of an (N,3) array."""
+    r = _rng(9)
+    a = r.standard_normal((5, 3)).astype(np.float32)
+    A = nb.NDArray.array(a).gpu()
+    eq_zero_sign_free((A[1] + A[2]).toArray(), a[1] + a[2])
+    eq_zero_sign_free((A + A[0]).toArray(), ORACLE.binary("add", a, a[0]))
+    assert nb.nd.sum(A[1]) == pytest.approx(float(ORACLE.reduce_full("sum", a[1])), rel=1e-6)
+
+
+def test_mul_add_fused_equals_two_calls_and_oracle(nb):
+    r = _rng(21)
+    for shp_b, shp_c in [((257, 1031), (257, 1031)), ((1031,), (257, 1)), ((257, 1), (1031,))]:
+        a = r.random((257, 1031), dtype=np.float32)
+        b = r.random(shp_b, dtype=np.float32)
+        c = r.random(shp_c, dtype=np.float32)
+        A, B, Cc = (nb.NDArray.array(x).gpu() for x in (a, b, c))
+        fused = nb.nd.mul_add(A, B, Cc).toArray()
+        two = (A * B + Cc).toArray()
+        np.testing.assert_array_equal(fused, two)          # no FMA contraction: fused == unfused bit for bit
+        eq_zero_sign_free(fused, oracle.port.mul_add(a, b, c))
+        if oracle.ref.available:
+            eq_zero_sign_free(fused, oracle.ref.mul_add(a, b, c))
+
+
+# --------------------------------------------------------------------- unary
+UNARY_DOMAINS = {
+    "sqrt": (0, 50), "log": (1e-3, 50), "log2": (1e-3, 50), "log10": (1e-3, 50), "log1p": (-0.9, 50),
+    "logb": (1e-3, 50), "arcsin": (-1, 1), "arccos": (-1, 1), "arccosh": (1, 50), "arctanh": (-0.99, 0.99),
+    "exp": (-20, 20), "exp2": (-20, 20), "expm1": (-20, 20), "sinh": (-10, 10), "cosh": (-10, 10),
+    "rsqrt": (1e-3, 100), "reciprocal": (0.01, 50),
+}
+BITEXACT_UNARY = {"abs", "sqrt", "degrees", "radians", "rint", "fix", "trunc", "floor", "ceil", "negative", "positive",
+                  "sign", "reciprocal", "rsqrt", "clip", "round", "square", "logb"}
+
+
+@pytest.mark.parametrize("op", list(oracle.UN_OPS))
+def test_unary_vs_oracle(nb, op):
+    lo, hi = UNARY_DOMAINS.get(op, (-30, 30))
+    x = (_rng(5).random(100003, dtype=np.float32) * (hi - lo) + lo).astype(np.float32)
+    x[:4] = np.clip(np.array([0.0, 0.5, 1.0, 2.5], np.float32), lo, hi)
+    p0, p1 = (-1.5, 2.5) if op == "clip" else ((2.0, 0.0) if op == "round" else (0.0, 0.0))
+    got = nb.nd.unary(op, nb.NDArray.array(x).gpu(), p0, p1).toArray()
+    exp = ORACLE.unary(op, x, p0, p1)
+    if op in BITEXACT_UNARY:
+        eq_zero_sign_free(got, exp)
+    elif op in ("sin", "cos", "tan", "sinc"):
+        # near the zeros of sin/cos a relative bound is ill-posed; both libms are within 2 ulp of the
+        # true value, so bound the error by 1e-5 of max(|result|, ulp-scale of the argument)
+        err = np.abs(got.astype(np.float64) - exp)
+        assert (err <= RTOL * np.maximum(np.abs(exp), 1e-2)).all()
+    else:
+        assert rel_err(got, exp).max() <= RTOL
+
+
+def test_domain_error_is_reported_not_fatal(nb):
+    """double_math.c:145-148 exit(1)s on arccos(|x|>1); the backend raises instead."""
+    A = nb.NDArray.array(np.array([0.5, 2.0], np.float32)).gpu()
+    with pytest.raises(nb.BackendError, match="arccos"):
+        nb.nd.unary("arccos", A)
+    assert np.isfinite(nb.nd.unary("arccos", nb.NDArray.array(np.array([0.5], np.float32)).gpu()).toArray()).all()
+
+
+# --------------------------------------------------------------------- reductions
+def _set_p(n, seed):  # values in {-1,0,1}: every partial sum is an exact integer (SURVEY §8 d, set P)
+    return _rng(seed).choice(np.array([-1, 0, 0, 1], np.float32), size=n)
+
+
+def _set_p2(shape, seed):  # k/64, k in [-64,64]: exact in any order
+    return (_rng(seed).integers(-64, 65, size=shape).astype(np.float32) / 64).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [1, 5, 1023, 4096, 100003, (1 << 22) + 5])
+def test_full_reductions_exact_sets(nb, n):
+    x = _set_p(n, n)
+    A = nb.NDArray.array(x).gpu()
+    assert nb.nd.sum(A) == float(ORACLE.reduce_full("sum", x))
+    y = _set_p2(n, n + 1)
+    B = nb.NDArray.array(y).gpu()
+    assert nb.nd.sum(B) == float(ORACLE.reduce_full("sum", y))
+    assert nb.nd.max(B) == float(ORACLE.reduce_full("max", y))
+    assert nb.nd.min(B) == float(ORACLE.reduce_full("min", y))
+    z = _rng(n).choice(np.array([1, 1, 1, -1, 2, 0.5], np.float32), size=min(n, 4000))
+    assert nb.nd.prod(nb.NDArray.array(z).gpu()) == float(ORACLE.reduce_full("prod", z))
+
+
+def test_sum_uniform_vs_fp64_truth(nb):
+    """Set U: the reference's sequential fp32 sum drifts/saturates; compare with fp64."""
+    x = _rng(9).random(1 << 24, dtype=np.float32)
+    got = nb.nd.sum(nb.NDArray.array(x).gpu())
+    truth = float(x.astype(np.float64).sum())
+    assert abs(got - truth) <= RTOL * truth
+    # and it is reproducible bit for bit (no float atomics)
+    assert got == nb.nd.sum(nb.NDArray.array(x).gpu())
+
+
+def test_min_max_nan_rules(nb):
+    x = _rng(3).standard_normal(5000).astype(np.float32)
+    x[100] = np.nan
+    for op in ("min", "max"):
+        assert nb.nd.reduce(op, nb.NDArray.array(x).gpu()) == float(ORACLE.reduce_full(op, x))  # later NaN skipped
+    x[0] = np.nan
+    for op in ("min", "max"):
+        assert math.isnan(nb.nd.reduce(op, nb.NDArray.array(x).gpu())) and math.isnan(float(ORACLE.reduce_full(op, x)))
+
+
+AXIS_SHAPES = [((37, 53), 0), ((37, 53), 1), ((4, 5, 6), 1), ((3, 1000, 8), 1), ((2048, 96), 0), ((96, 2048), 1),
+               ((5, 7, 2048), 2), ((3000, 5), 0), ((1, 70000), 1), ((70000, 3), 0)]
+
+
+@pytest.mark.parametrize("shape,axis", AXIS_SHAPES)
+def test_axis_reductions_exact_set_tree(nb, shape, axis):
+    x = _set_p2(shape, sum(shape))
+    A = nb.NDArray.array(x).gpu()
+    np.testing.assert_array_equal(nb.nd.sum(A, axis).toArray(), oracle.port.reduce_axis("sum", x, axis))
+    np.testing.assert_array_equal(nb.nd.max(A, axis).toArray(), oracle.port.reduce_axis("max", x, axis))
+    np.testing.assert_array_equal(nb.nd.min(A, axis).toArray(), oracle.port.reduce_axis("min", x, axis))
+
+
+@pytest.mark.parametrize("shape,axis", AXIS_SHAPES[:8])
+def test_axis_sum_sequential_order_bit_exact_on_random_data(nb, shape, axis):
+    """NB200_ORDER_SEQUENTIAL reproduces the reference's slice-loop order (ndarray.c:394-429)."""
+    x = _rng(1).standard_normal(shape).astype(np.float32)
+    A = nb.NDArray.array(x).gpu()
+    got = nb.nd.sum(A, axis, order=nb.ORDER_SEQUENTIAL).toArray()
+    np.testing.assert_array_equal(got, oracle.port.reduce_axis("sum", x, axis))
+    if oracle.ref.available and x.size < 20000:
+        np.testing.assert_array_equal(got, oracle.ref.reduce_axis("sum", x, axis))
+    tree = nb.nd.sum(A, axis).toArray()
+    assert np.abs(tree - got).max() <= 1e-4  # same values up to summation order
+
+
+# --------------------------------------------------------------------- argmax / argmin
+def test_argminmax_axes_and_ties(nb):
+    x = _rng(9).integers(0, 50, size=(6, 70, 5)).astype(np.float32)
+    A = nb.NDArray.array(x).gpu()
+    for is_max, fn in ((True, nb.nd.argmax), (False, nb.nd.argmin)):
+        assert fn(A) == float(ORACLE.argminmax(is_max, x))
+        for axis in (0, 1, 2):
+            for kd in (False, True):
+                got = fn(A, axis, kd).toArray()
+                np.testing.assert_array_equal(got, oracle.port.argminmax(is_max, x, axis, kd))
+    y = _rng(4).integers(0, 3, size=(300, 2000)).astype(np.float32)  # long rows, heavy ties
+    Y = nb.NDArray.array(y).gpu()
+    np.testing.assert_array_equal(nb.nd.argmax(Y, 1).toArray(), oracle.port.argminmax(True, y, 1))
+    np.testing.assert_array_equal(nb.nd.argmin(Y, 0).toArray(), oracle.port.argminmax(False, y, 0))
+
+
+def test_argminmax_nan_rules(nb):
+    x = _rng(2).standard_normal(100000).astype(np.float32)
+    x[777] = np.nan
+    x[99000] = np.nan
+    A = nb.NDArray.array(x).gpu()
+    assert nb.nd.argmin(A) == float(ORACLE.argminmax(False, x)) == 777.0     # first NaN wins argmin
+    assert nb.nd.argmax(A) == float(ORACLE.argminmax(True, x))               # argmax skips later NaNs
+    x[0] = np.nan
+    A = nb.NDArray.array(x).gpu()
+    assert nb.nd.argmax(A) == 0.0 == float(ORACLE.argminmax(True, x))
+    assert nb.nd.argmin(A) == 0.0
+    z = np.full(5000, -np.inf, np.float32)
+    assert nb.nd.argmax(nb.NDArray.array(z).gpu()) == 0.0
+    z = np.array([0.0, -0.0, 0.0], np.float32)
+    assert nb.nd.argmin(nb.NDArray.array(z).gpu()) == 0.0 == float(ORACLE.argminmax(False, z))
+
+
+def test_argmax_large_index_float_rounding(nb):
+    """The index is returned as float32 (calculation.c:25): an odd index > 2^24 rounds to even."""
+    n = (1 << 24) + 4099
+    x = np.zeros(n, np.float32)
+    idx = (1 << 24) + 1001
+    x[idx] = 5.0
+    x[idx + 2000] = 5.0  # later tie must lose
+    got = nb.nd.argmax(nb.NDArray.array(x).gpu())
+    assert got == float(np.float32(idx)) and got != float(idx)
+
+
+# --------------------------------------------------------------------- matmul
+def _matmul_check(nb, a, b, precision, tol):
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), precision).toArray()
+    exp = ORACLE.matmul(a, b)
+    err = rel_err(got, exp).max()
+    assert err <= tol, f"max rel err {err:.3e} > {tol}"
+    return got
+
+
+@pytest.mark.parametrize("mkn", [(2, 2, 2), (2, 2, 1), (17, 33, 9), (64, 64, 64), (100, 40, 100)])
+def test_matmul_small_shapes_simt_path(nb, mkn):
+    m, k, n = mkn
+    r = _rng(m * 7 + n)
+    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.TF32X3, RTOL)
+
+
+@pytest.mark.parametrize("mkn", [(128, 128, 256), (256, 512, 256), (384, 1024, 640), (1000, 520, 776), (1024, 1024, 1024),
+                                 (130, 36, 260)])
+def test_matmul_tf32x3_vs_cblas_sgemm(nb, mkn):
+    """Positive inputs, per-element relative error <= 1e-5 against the reference's cblas_sgemm."""
+    m, k, n = mkn
+    r = _rng(m + k + n)
+    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.TF32X3, RTOL)
+
+
+def test_matmul_signed_inputs_normwise(nb):
+    """Signed inputs: per-element relative error is ill-posed under cancellation; use the norm-wise
+    metric of SURVEY §8 d: max|G-R| / max_ij (|A|.|B|)_ij <= 1e-5."""
+    r = _rng(12)
+    a = (r.random((512, 768), dtype=np.float32) * 2 - 1).astype(np.float32)
+    b = (r.random((768, 384), dtype=np.float32) * 2 - 1).astype(np.float32)
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    exp = ORACLE.matmul(a, b)
+    scale = (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)).max()
+    assert np.abs(got.astype(np.float64) - exp).max() / scale <= RTOL
+
+
+def test_matmul_tf32x1_fast_mode_is_tf32_accurate(nb):
+    r = _rng(6)
+    a, b = r.random((512, 1024), dtype=np.float32), r.random((1024, 512), dtype=np.float32)
+    _matmul_check(nb, a, b, nb.TF32X1, 2e-3)  # single-pass TF32: ~2^-11 per product
+
+
+def test_matmul_batched_stack_equals_loop(nb):
+    """The reference rejects stacks (linalg.c:240-243); the oracle is a loop of 2-D matmuls."""
+    r = _rng(8)
+    a, b = r.random((5, 256, 128), dtype=np.float32), r.random((5, 128, 384), dtype=np.float32)
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    for i in range(5):
+        assert rel_err(got[i], ORACLE.matmul(a[i], b[i])).max() <= RTOL
+
+
+def test_matmul_error_behaviour(nb):
+    A = nb.NDArray.array(np.ones((4, 5), np.float32)).gpu()
+    B = nb.NDArray.array(np.ones((4, 5), np.float32)).gpu()
+    with pytest.raises(nb.BackendError, match="Shape mismatch for matmul"):
+        nb.nd.matmul(A, B)
+    with pytest.raises(nb.BackendError, match="Device mismatch"):
+        nb.nd.matmul(A, nb.NDArray.array(np.ones((5, 4), np.float32)))
+
+
+def test_dot_variants(nb):
+    r = _rng(10)
+    a, x = r.random((300, 1000), dtype=np.float32), r.random(1000, dtype=np.float32)
+    got = nb.nd.dot(nb.NDArray.array(a).gpu(), nb.NDArray.array(x).gpu()).toArray()
+    assert rel_err(got, ORACLE.dot(a, x) if oracle.ref.available else oracle.port.gemv(a, x)).max() <= RTOL
+    v = _set_p2(5000, 3)
+    w = _set_p2(5000, 4)
+    got = float(nb.nd.dot(nb.NDArray.array(v).gpu(), nb.NDArray.array(w).gpu()).toArray())
+    assert got == pytest.approx(float((v.astype(np.float64) * w).sum()), rel=1e-6)
+
+
+# --------------------------------------------------------------------- BASELINE sizes: size-independent properties
+def test_config3_chain_full_size_properties(nb):
+    """8192x8192 a*b+c: fused == unfused bit for bit; row/col broadcast == materialised; spot rows vs oracle."""
+    n = 8192
+    r = _rng(5)
+    a = r.random((n, n), dtype=np.float32)
+    brow = r.random(n, dtype=np.float32)
+    ccol = r.random((n, 1), dtype=np.float32)
+    A, B, Cc = nb.NDArray.array(a).gpu(), nb.NDArray.array(brow).gpu(), nb.NDArray.array(ccol).gpu()
+    fused = nb.nd.mul_add(A, B, Cc)
+    two = A * B + Cc
+    d = (fused - two)
+    assert nb.nd.max(d) == 0.0 and nb.nd.min(d) == 0.0
+    rows = [0, 1, 4095, 8191]
+    host = fused.toArray()
+    for i in rows:
+        eq_zero_sign_free(host[i], oracle.port.mul_add(a[i], brow, ccol[i]))
+    # linearity-style checksum: sum over an exact-set variant is order independent
+    p = _set_p2((n, n), 1)
+    P = nb.NDArray.array(p).gpu()
+    s_full = nb.nd.sum(P)
+    s_rows = nb.nd.sum(nb.nd.sum(P, 1))
+    s_cols = nb.nd.sum(nb.nd.sum(P, 0))
+    assert s_full == s_rows == s_cols == float(p.astype(np.float64).sum())
+
+
+def test_config4_sum_argmax_2pow28(nb):
+    n = 1 << 28
+    x = _set_p(n, 8)
+    A = nb.NDArray.array(x).gpu()
+    assert nb.nd.sum(A) == float(x.astype(np.float64).sum())   # exact set: any order gives the same integer
+    x[123456789] = 7.0
+    x[200000001] = 7.0
+    A = nb.NDArray.array(x).gpu()
+    assert nb.nd.argmax(A) == float(np.float32(123456789))
+    assert nb.nd.argmin(A) == float(np.argmin(x))
+
+
+def test_config2_matmul_4096_checksum(nb):
+    """4096^3: compare 64 sampled rows against the reference's cblas_sgemm, and the full result through
+    the checksum identity  (1^T A) B == 1^T (A B)  in fp64."""
+    n = 4096
+    r = _rng(3)
+    a, b = r.random((n, n), dtype=np.float32), r.random((n, n), dtype=np.float32)
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    rows = r.choice(n, 64, replace=False)
+    exp = ORACLE.matmul(a[rows], b)
+    assert rel_err(got[rows], exp).max() <= RTOL
+    lhs = a.astype(np.float64).sum(0) @ b.astype(np.float64)
+    rhs = got.astype(np.float64).sum(0)
+    assert np.abs(lhs - rhs).max() / np.abs(lhs).max() <= 1e-6
