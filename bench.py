@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 NDArray backend (contract: task prompt, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1 : workload = BASELINE.json configs[1] "nd::matmul 4096x4096 fp32 (tf32 tensor cores)": one step =
+        one nd::matmul through the C-ABI (nb200_sgemm, TF32x3 parity mode).  `value` = useful TFLOP/s with
+        operands resident in HBM; `e2e` = same call fed from pinned HOST buffers (H2D of A,B and D2H of C
+        inside the timed region).  `extras` reports the other single-GPU configs (a*b+c 8192^2 chain,
+        sum/argmax over 2^28, axis sums) as GB/s against the measured HBM roofline, and the TF32x1 fast mode.
+N > 1 : launched by torchrun, one rank per GPU: BASELINE.json configs[4] batched matmul, the batch dimension
+        sharded with no data-path collective (128 matrices of 2048^2 per rank; N = 8 is exactly
+        1024 x (2048x2048)).  weak scaling; value = total useful TFLOP/s over all ranks, max-over-ranks time.
+--impl reference : the reference's own CPU implementation (oracle/_ref = NumPower's object code ->
+        OpenBLAS cblas_sgemm) timed on the host cores for the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MATMUL_N = 4096
+SHARD_BATCH, SHARD_N = 128, 2048
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback (B200_PROFILING.md)"
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU path for configs[1]: NDArray_Matmul -> cblas_sgemm (oracle/_ref)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import oracle
+    use_ref = oracle.ref.available
+    impl = oracle.ref if use_ref else oracle.port
+    n = MATMUL_N
+    rng = np.random.default_rng(3)
+    a, b = rng.random((n, n), dtype=np.float32), rng.random((n, n), dtype=np.float32)
+    for _ in range(max(1, min(args.warmup, 2))):
+        impl.matmul(a, b)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        impl.matmul(a, b)
+    dt = (time.perf_counter() - t0) / steps
+    info = oracle.ref.blas_info() if use_ref else {}
+    cores = info.get("threads", os.cpu_count() if use_ref else os.cpu_count())
+    val = 2.0 * n ** 3 / dt / 1e12
+    line = {
+        "impl": "reference", "metric": "nd::matmul useful TFLOP/s (fp32 in/out)", "value": val, "unit": "TFLOP/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"nd::matmul {n}x{n} fp32, reference CPU path (NDArray_Matmul -> OpenBLAS cblas_sgemm)"},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                         "sample": f"{steps} full {n}^3 matmuls", "blas": info.get("config", "")},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class Bench:
+    def __init__(self, device: int):
+        import torch
+        import numpower_b200 as nb
+        self.torch, self.nb = torch, nb
+        self.lib = nb.lib()
+        torch.cuda.set_device(device)
+        self.check(self.lib.nb200_init(device))
+        # run the library on torch's current stream so torch.cuda.Event brackets its kernels
+        self.check(self.lib.nb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.nb200_last_error().decode())
+
+    def flush_l2(self):
+        self.flush_buf.zero_()
+
+    def time_steps(self, fn, steps, warmup, flush=False):
+        """ms per step, CUDA events on the launching stream, sync on both sides."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if not flush:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps
+        total = 0.0
+        for _ in range(steps):
+            self.flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        return total / steps
+
+
+def cpu_baseline_matmul(n):
+    import numpy as np
+    import oracle
+    use_ref = oracle.ref.available
+    impl = oracle.ref if use_ref else oracle.port
+    rng = np.random.default_rng(3)
+    a, b = rng.random((n, n), dtype=np.float32), rng.random((n, n), dtype=np.float32)
+    impl.matmul(a, b)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        impl.matmul(a, b)
+        best = min(best, time.perf_counter() - t0)
+    info = oracle.ref.blas_info() if use_ref else {}
+    return {"value": 2.0 * n ** 3 / best / 1e12, "unit": "TFLOP/s", "cores": info.get("threads", os.cpu_count()),
+            "kind": "reference" if use_ref else "port", "sample": f"best of 3 full {n}^3 nd::matmul calls (NDArray_Matmul -> cblas_sgemm)",
+            "blas_core": info.get("core", ""), "ms": best * 1e3}
+
+
+def cpu_baseline_extras():
+    """Reference CPU path on bounded samples of the HBM-bound configs (single-threaded in the reference)."""
+    import numpy as np
+    import oracle
+    impl = oracle.ref if oracle.ref.available else oracle.port
+    out = {}
+    rng = np.random.default_rng(5)
+    n = 2048  # 2048^2 sample of the 8192^2 chain (1/16 of the elements)
+    a, b, c = (rng.random((n, n), dtype=np.float32) for _ in range(3))
+    t0 = time.perf_counter(); impl.mul_add(a, b, c); dt = time.perf_counter() - t0
+    out["chain_mul_add"] = {"GBps_algorithmic_fused": 4 * a.nbytes / dt / 1e9, "sample": "2048^2 slice of the 8192^2 chain, two nd:: calls", "cores": 1}
+    x = rng.random(1 << 24, dtype=np.float32)
+    t0 = time.perf_counter(); impl.reduce_full("sum", x); dt = time.perf_counter() - t0
+    out["sum"] = {"GBps": x.nbytes / dt / 1e9, "sample": "2^24 of the 2^28 elements", "cores": 1}
+    t0 = time.perf_counter(); impl.argminmax(True, x); dt = time.perf_counter() - t0
+    out["argmax"] = {"GBps": x.nbytes / dt / 1e9, "sample": "2^24 of the 2^28 elements", "cores": 1}
+    return out
+
+
+def run_single(args):
+    peaks = load_peaks()
+    B = Bench(0)
+    torch, lib = B.torch, B.lib
+    n = MATMUL_N
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.rand(n, n, device="cuda", generator=g)
+    b = torch.rand(n, n, device="cuda", generator=g)
+    c = torch.empty(n, n, device="cuda")
+    flops = 2.0 * n ** 3
+
+    def mm(prec):
+        B.check(lib.nb200_sgemm(c.data_ptr(), a.data_ptr(), b.data_ptr(), n, n, n, n, n, n, prec))
+
+    launches0 = lib.nb200_launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = B.time_steps(lambda: mm(0), args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = lib.nb200_launch_count() - launches0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    ms_x1 = B.time_steps(lambda: mm(1), args.steps, args.warmup)
+
+    # ---- e2e: pinned host buffers, H2D(A,B) + matmul + D2H(C) per step, through the C-ABI
+    ha, hb, hc = (torch.empty(n, n, dtype=torch.float32).pin_memory() for _ in range(3))
+    ha.copy_(a.cpu()); hb.copy_(b.cpu())
+    nbytes = n * n * 4
+
+    def e2e_step():
+        B.check(lib.nb200_copy_h2d(a.data_ptr(), ha.data_ptr(), nbytes))
+        B.check(lib.nb200_copy_h2d(b.data_ptr(), hb.data_ptr(), nbytes))
+        mm(0)
+        B.check(lib.nb200_copy_d2h(hc.data_ptr(), c.data_ptr(), nbytes))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = B.time_steps(e2e_step, e2e_steps, 2)
+
+    # ---- extras: the HBM-bound configs (inputs > L2, plus an explicit L2 flush between timed launches)
+    hbm = peaks["hbm_gbs"]
+    extras = {}
+    m = 8192
+    x = torch.rand(m, m, device="cuda", generator=g)
+    y = torch.rand(m, m, device="cuda", generator=g)
+    z = torch.rand(m, m, device="cuda", generator=g)
+    out = torch.empty(m, m, device="cuda")
+    tmp = torch.empty(m, m, device="cuda")
+    shp = (C.c_int64 * 2)(m, m)
+    full = (C.c_int64 * 2)(m, 1)
+    rowv = (C.c_int64 * 2)(0, 1)
+    colv = (C.c_int64 * 2)(1, 0)
+    reps = 10
+
+    def gbps(bytes_, ms_):
+        return bytes_ / ms_ / 1e6
+
+    t = B.time_steps(lambda: B.check(lib.nb200_ew_mul_add(out.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(), 2, shp, full, full, full)), reps, 3, flush=True)
+    extras["chain_fused_full"] = {"ms": t, "GBps": gbps(4 * m * m * 4, t), "frac_hbm": gbps(4 * m * m * 4, t) / hbm, "algorithmic_bytes": 4 * m * m * 4}
+
+    def unfused():
+        B.check(lib.nb200_ew_binary(2, tmp.data_ptr(), x.data_ptr(), y.data_ptr(), 2, shp, full, full))
+        B.check(lib.nb200_ew_binary(0, out.data_ptr(), tmp.data_ptr(), z.data_ptr(), 2, shp, full, full))
+    t = B.time_steps(unfused, reps, 3, flush=True)
+    extras["chain_two_calls_full"] = {"ms": t, "GBps": gbps(6 * m * m * 4, t), "frac_hbm": gbps(6 * m * m * 4, t) / hbm, "algorithmic_bytes": 6 * m * m * 4}
+    t = B.time_steps(lambda: B.check(lib.nb200_ew_mul_add(out.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(), 2, shp, full, rowv, colv)), reps, 3, flush=True)
+    bb = 2 * m * m * 4 + 2 * m * 4
+    extras["chain_fused_row_col_broadcast"] = {"ms": t, "GBps": gbps(bb, t), "frac_hbm": gbps(bb, t) / hbm, "algorithmic_bytes": bb}
+    t = B.time_steps(lambda: B.check(lib.nb200_ew_unary(2, out.data_ptr(), x.data_ptr(), m * m, 0.0, 0.0)), reps, 3, flush=True)
+    extras["unary_exp_8192sq"] = {"ms": t, "GBps": gbps(2 * m * m * 4, t), "frac_hbm": gbps(2 * m * m * 4, t) / hbm}
+    res = torch.empty(16, device="cuda")
+    ax = torch.empty(m, device="cuda")
+    for name, fn, bytes_ in (
+        ("sum_axis0_8192sq", lambda: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), x.data_ptr(), 1, m, m, 0)), m * m * 4),
+        ("sum_axis1_8192sq", lambda: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), x.data_ptr(), m, m, 1, 0)), m * m * 4),
+    ):
+        t = B.time_steps(fn, reps, 3, flush=True)
+        extras[name] = {"ms": t, "GBps": gbps(bytes_, t), "frac_hbm": gbps(bytes_, t) / hbm}
+    del y, z, out, tmp
+    big = torch.rand(1 << 28, device="cuda", generator=g)
+    for name, fn in (
+        ("sum_2pow28", lambda: B.check(lib.nb200_reduce_full(0, res.data_ptr(), big.data_ptr(), 1 << 28))),
+        ("argmax_2pow28", lambda: B.check(lib.nb200_argminmax(1, res.data_ptr(), big.data_ptr(), 1, 1 << 28, 1))),
+    ):
+        t = B.time_steps(fn, reps, 3, flush=True)
+        extras[name] = {"ms": t, "GBps": gbps((1 << 30), t), "frac_hbm": gbps(1 << 30, t) / hbm, "algorithmic_bytes": 1 << 30}
+    del big
+    # config[0]: nd::add 1024x1024 (launch-latency bound on a GPU: 12 MiB of traffic)
+    s = torch.rand(1024, 1024, device="cuda"); s2 = torch.rand(1024, 1024, device="cuda"); so = torch.empty(1024, 1024, device="cuda")
+    s1 = (C.c_int64 * 1)(1 << 20); st1 = (C.c_int64 * 1)(1)
+    t = B.time_steps(lambda: B.check(lib.nb200_ew_binary(0, so.data_ptr(), s.data_ptr(), s2.data_ptr(), 1, s1, st1, st1)), 50, 5)
+    extras["add_1024sq_l2_warm"] = {"ms": t, "GBps": gbps(3 * (1 << 22), t)}
+
+    tf32_peak = peaks["bf16_tflops"] / 2.0   # tcgen05 kind::tf32 runs at half the bf16 rate
+    useful = flops / ms / 1e9
+    extras["matmul_4096_tf32x1"] = {"ms": ms_x1, "useful_tflops": flops / ms_x1 / 1e9, "frac_tf32_peak": flops / ms_x1 / 1e9 / tf32_peak,
+                                    "note": "single-pass TF32 fast mode (rel err ~1e-4 vs cblas_sgemm; not the parity mode)"}
+    cpu = cpu_baseline_matmul(n)
+    try:
+        extras["cpu_reference_hbm_configs"] = cpu_baseline_extras()
+    except Exception as e:  # informational
+        extras["cpu_reference_hbm_configs"] = {"error": str(e)}
+
+    line = {
+        "metric": "nd::matmul useful TFLOP/s (fp32 in/out, TF32 tensor cores)", "value": useful, "unit": "TFLOP/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 in/out, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"nd::matmul {n}x{n} fp32 (BASELINE configs[1]) via nb200_sgemm, TF32x3 parity mode",
+                   "l2": "operands 128 MiB + result 64 MiB exceed the 126 MB L2; HBM-bound extras flush L2 between timed launches",
+                   "timing": "CUDA events on the launching stream"},
+        "roofline": {"bound": "tensor", "achieved": useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": useful / tf32_peak,
+                     "traffic": None, "peak_source": peaks["_source"] + ": bf16_tflops / 2 (tf32 = half the bf16 MMA rate)",
+                     "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / tf32_peak,
+                     "note": "achieved counts the algorithmic 2*M*N*K flops; TF32x3 executes 3x that on the tensor pipe"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": flops / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
+                "ms_per_step": ms_e2e, "steps": e2e_steps},
+        "gpu_launches": int(launches_timed),
+        "clocks": clocks,
+        "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_multi(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = load_peaks()
+    B = Bench(local)
+    lib = B.lib
+    nb_, n = SHARD_BATCH, SHARD_N
+    g = torch.Generator(device="cuda").manual_seed(10 + rank)   # resident shard, generated on the owning GPU
+    a = torch.rand(nb_, n, n, device="cuda", generator=g)
+    b = torch.rand(nb_, n, n, device="cuda", generator=g)
+    c = torch.empty(nb_, n, n, device="cuda")
+    flops_rank = nb_ * 2.0 * n ** 3
+
+    def step():
+        B.check(lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), nb_, n, n, n, n * n, n * n, n * n, 0))
+
+    for _ in range(args.warmup):
+        step()
+    launches0 = lib.nb200_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = lib.nb200_launch_count() - launches0
+
+    # e2e: each rank feeds its shard from pinned host memory over its own PCIe link and reads C back
+    e2e_batch = 16
+    ha = torch.empty(e2e_batch, n, n).pin_memory(); hb = torch.empty(e2e_batch, n, n).pin_memory(); hc = torch.empty(e2e_batch, n, n).pin_memory()
+    ha.copy_(a[:e2e_batch].cpu()); hb.copy_(b[:e2e_batch].cpu())
+    nbytes = e2e_batch * n * n * 4
+
+    def e2e_step():
+        B.check(lib.nb200_copy_h2d(a.data_ptr(), ha.data_ptr(), nbytes))
+        B.check(lib.nb200_copy_h2d(b.data_ptr(), hb.data_ptr(), nbytes))
+        B.check(lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), e2e_batch, n, n, n, n * n, n * n, n * n, 0))
+        B.check(lib.nb200_copy_d2h(hc.data_ptr(), c.data_ptr(), nbytes))
+
+    e2e_step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1) / 3], device="cuda")
+    dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t2.item())
+
+    if rank == 0:
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        total = world * flops_rank / ms / 1e9
+        per_gpu = flops_rank / ms / 1e9
+        line = {
+            "metric": "nd::matmul useful TFLOP/s (fp32 in/out, TF32 tensor cores)", "value": total, "unit": "TFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 in/out, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"batched nd::matmul, {nb_} x ({n}x{n}) per GPU, batch sharded across {world} GPUs "
+                                   f"(N=8 is BASELINE configs[4] 1024x(2048x2048)); resident shards, no data-path collective",
+                       "l2": f"per-rank operands {2 * nb_ * n * n * 4 >> 20} MiB exceed L2", "timing": "CUDA events, max over ranks (NCCL all-reduce of the times)"},
+            "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": tf32_peak, "unit": "TFLOP/s", "frac": per_gpu / tf32_peak,
+                         "traffic": None, "peak_source": peaks["_source"] + ": bf16_tflops_sustained / 2", "pipe_executed_tflops": 3 * per_gpu,
+                         "pipe_frac": 3 * per_gpu / tf32_peak, "note": "per-GPU figures"},
+            "e2e": {"value": world * e2e_batch * 2.0 * n ** 3 / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes,
+                    "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e, "note": f"{e2e_batch} matrices per rank per step, pinned host buffers, each rank over its own PCIe link"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_multi(args)
+    return run_single(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -13,8 +13,12 @@
 // Operand layouts in shared memory (per pipeline stage, BK = 32 fp32 = one 128-byte swizzle row):
 //   A tile  (BM x BK)  K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO = 1024)
 //   B tile  (BK x BN)  MN-major: B is row-major [K,N], i.e. N is contiguous -> loaded untransposed
-//           as BN/32 chunks of [32 k-rows x 128 B]; chunk stride = LBO = 4096 B, 8-k-row groups
-//           1024 B apart (SBO).  One K=8 MMA consumes one 8-row group of every chunk.
+//           as BN/32 chunks of [32 k-rows x 128 B]; chunk stride = LBO = 4096 B.  For 4-byte MN-major
+//           operands the tensor core only accepts the "128B swizzle with 32-byte atoms" layout
+//           (UMMA layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: 32-byte chunk index ^= row % 4),
+//           whose atom is 4 k-rows x 128 B: SBO = 512 B.  One K=8 MMA consumes two such atoms of every
+//           chunk (start address advances 1024 B per k-step).  [Measured on B200: the 16-byte-atom
+//           SWIZZLE_128B layout silently yields an all-zero accumulator for MN-major tf32.]
 //
 // Precision modes (include/nb200.h):
 //   TF32X1  operands are fed as raw fp32 (the tensor core reads the top 19 bits)
@@ -193,14 +197,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // Shared-memory matrix descriptor (64-bit), SM100 format:
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1       | [49,52) base offset = 0          | [61,64) layout: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [46,48) version = 1       | [49,52) base offset = 0          | [61,64) layout: 2 = SWIZZLE_128B,
+//                                                                           1 = SWIZZLE_128B with 32-byte atoms
+constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;
     return d;
 }
 // Instruction descriptor (32-bit): D=f32 (bits 4-5 =1), A=B=tf32 (bits 7-9, 10-12 =2), A K-major (bit 15 =0),
@@ -306,8 +312,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             const int ia = PASSES == 3 ? pa[ps] : 0, ib = PASSES == 3 ? pb[ps] : 0;
 #pragma unroll
                             for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                const uint64_t da = make_smem_desc(a_smem(stage, ia) + k * 32, 16, 1024);
-                                const uint64_t db = make_smem_desc(b_smem(stage, ib) + k * 1024, 4096, 1024);
+                                const uint64_t da = make_smem_desc(a_smem(stage, ia) + k * 32, 16, 1024, LAYOUT_SW128);
+                                const uint64_t db = make_smem_desc(b_smem(stage, ib) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
                                 umma_tf32<CG>(d_tmem, da, db, idesc, (kb | ps | k) != 0 ? 1u : 0u);
                             }
                         }
@@ -462,7 +468,7 @@ static EncodeTiledFn get_encode() {
 
 // 3-D map over (inner, rows, batch) of a row-major fp32 matrix stack; box = (32, box_rows, 1), 128B swizzle.
 static int make_map(CUtensorMap *map, const float *base, int64_t inner, int64_t rows, int64_t ld, int64_t batch,
-                    int64_t batch_stride, int box_rows) {
+                    int64_t batch_stride, int box_rows, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error(NB200_ECUDA, "cuTensorMapEncodeTiled unavailable");
     if (batch_stride == 0 || batch < 1) { batch = 1; batch_stride = rows * ld; }
@@ -471,7 +477,7 @@ static int make_map(CUtensorMap *map, const float *base, int64_t inner, int64_t 
     cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(NB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return NB200_OK;
@@ -487,13 +493,14 @@ template <class Cfg>
 static int launch_gemm(const GemmArgs &g) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(&ma_hi, g.A, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM)) != NB200_OK) return rc;
-    if ((rc = make_map(&mb_hi, g.B, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK)) != NB200_OK) return rc;
+    const CUtensorMapSwizzle SWA = CU_TENSOR_MAP_SWIZZLE_128B, SWB = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if ((rc = make_map(&ma_hi, g.A, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA)) != NB200_OK) return rc;
+    if ((rc = make_map(&mb_hi, g.B, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB)) != NB200_OK) return rc;
     ma_lo = ma_hi;
     mb_lo = mb_hi;
     if (Cfg::PASSES == 3) {
-        if ((rc = make_map(&ma_lo, g.A_lo, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM)) != NB200_OK) return rc;
-        if ((rc = make_map(&mb_lo, g.B_lo, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK)) != NB200_OK) return rc;
+        if ((rc = make_map(&ma_lo, g.A_lo, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA)) != NB200_OK) return rc;
+        if ((rc = make_map(&mb_lo, g.B_lo, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB)) != NB200_OK) return rc;
     }
     GemmParams p;
     p.C = g.C; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.strideC = g.sC; p.batch = g.batch;

@@ -69,26 +69,33 @@ def build_ref() -> str:
 
 
 class _Ref:
-    """The reference's own CPU code path (kind = "reference")."""
+    """The reference's own CPU code path (kind = "reference").
 
-    def __init__(self):
+    With ``so_path`` = oracle/_ref/libnumpower_host_b200.so (oracle/build_dropin.sh) the SAME
+    reference host objects are compiled with HAVE_CUBLAS and linked against libnb200.so: arrays are
+    moved with the reference's NDArray_ToGPU and every op takes the reference's GPU branch — the
+    drop-in proof used by tests/test_dropin_gpu.py.
+    """
+
+    def __init__(self, so_path: str = None):
         self._lib = None
+        self._so = so_path or REF_SO
 
     @property
     def available(self) -> bool:
-        return os.path.exists(REF_SO)
+        return os.path.exists(self._so)
 
     @property
     def lib(self):
         if self._lib is None:
-            if not os.path.exists(REF_SO):
+            if not os.path.exists(self._so) and self._so == REF_SO:
                 build_ref()
             blas_txt = os.path.join(HERE, "_ref", "blas_path.txt")
             if os.path.exists(blas_txt):
                 blas = open(blas_txt).read().strip()
                 if os.path.exists(blas):
                     C.CDLL(blas, mode=C.RTLD_GLOBAL)
-            lib = C.CDLL(REF_SO)
+            lib = C.CDLL(self._so)
             lib.ref_last_error.restype = C.c_char_p
             lib.ref_binary.restype = C.c_long
             lib.ref_binary.argtypes = [C.c_int, _fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
@@ -323,5 +330,7 @@ class _Port:
         return out
 
 
+DROPIN_SO = os.path.join(HERE, "_ref", "libnumpower_host_b200.so")
 ref = _Ref()
 port = _Port()
+dropin = _Ref(DROPIN_SO)   # reference host objects (HAVE_CUBLAS) on top of libnb200.so; needs a GPU

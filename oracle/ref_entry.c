@@ -56,14 +56,20 @@ char *print_matrix(double *b, int nd, int *sh, int *st, int n, int dev) {
 char *print_matrix_float(float *b, int nd, int *sh, int *st, int n, int dev) {
     (void) b; (void) nd; (void) sh; (void) st; (void) n; (void) dev; return strdup("");
 }
+#ifndef REF_ENTRY_GPU
 /* linalg.c:204 references vfree outside #ifdef HAVE_CUBLAS */
 void vfree(void *p) { (void) p; }
+#endif
 
 const char *ref_last_error(void) { return g_err_set ? g_err : ""; }
 void ref_clear_error(void) { g_err_set = 0; g_err[0] = 0; }
 
-/* ---- wrapping ----------------------------------------------------------- */
-static NDArray *wrap(const float *data, const int *shape, int ndim) {
+/* ---- wrapping -----------------------------------------------------------
+ * REF_ENTRY_GPU (drop-in build, oracle/build_dropin.sh): operands with ndim > 0 are moved to the
+ * device with the reference's own NDArray_ToGPU (ndarray.c:1037-1068), the reference function then
+ * takes its `NDArray_DEVICE(a) == NDARRAY_DEVICE_GPU` branch — i.e. calls the legacy cuda_* /
+ * vmalloc symbols that libnb200.so now provides — and the result comes back with NDArray_ToCPU. */
+static NDArray *wrap_cpu(const float *data, const int *shape, int ndim) {
     int *sh = (int *) malloc(sizeof(int) * (ndim > 0 ? ndim : 1));
     for (int i = 0; i < ndim; i++) sh[i] = shape[i];
     if (ndim == 0) sh[0] = 1;
@@ -71,11 +77,37 @@ static NDArray *wrap(const float *data, const int *shape, int ndim) {
     a->data = (char *) data;
     return a;
 }
-static void unwrap(NDArray *a) {
+static void unwrap_cpu(NDArray *a) {
     if (a == NULL) return;
     a->data = NULL;            /* caller-owned buffer: NDArray_FREE must not efree it */
     NDArray_FREE(a);
 }
+#ifdef REF_ENTRY_GPU
+static NDArray *wrap(const float *data, const int *shape, int ndim) {
+    NDArray *c = wrap_cpu(data, shape, ndim);
+    if (ndim == 0) return c;   /* PHP scalars stay 0-dim CPU arrays (ZVAL_TO_NDARRAY, numpower.c:89-117) */
+    NDArray *g = NDArray_ToGPU(c);
+    unwrap_cpu(c);
+    return g;
+}
+static void unwrap(NDArray *a) {
+    if (a == NULL) return;
+    if (NDArray_DEVICE(a) == NDARRAY_DEVICE_GPU) NDArray_FREE(a); else unwrap_cpu(a);
+}
+static long take(NDArray *r, float *out, long cap) {
+    if (r == NULL) return -1;
+    NDArray *h = r;
+    if (NDArray_DEVICE(r) == NDARRAY_DEVICE_GPU) { h = NDArray_ToCPU(r); NDArray_FREE(r); }
+    long n = NDArray_NUMELEMENTS(h);
+    if (n > cap) n = cap;
+    memcpy(out, NDArray_FDATA(h), (size_t) n * sizeof(float));
+    long total = NDArray_NUMELEMENTS(h);
+    NDArray_FREE(h);
+    return total;
+}
+#else
+#define wrap wrap_cpu
+#define unwrap unwrap_cpu
 static long take(NDArray *r, float *out, long cap) {
     if (r == NULL) return -1;
     long n = NDArray_NUMELEMENTS(r);
@@ -85,6 +117,7 @@ static long take(NDArray *r, float *out, long cap) {
     NDArray_FREE(r);
     return total;
 }
+#endif
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -159,10 +192,40 @@ static un_fn un_table(int op) {
         default: return NULL;
     }
 }
+#ifdef REF_ENTRY_GPU
+/* GPU dispatch exactly as the PHP methods do it (numpower.c:1648...3348: one
+ * `NDArrayMathGPU_ElementWise(nda, cuda_float_<op>)` per method).  Ops whose PHP method has no GPU
+ * branch in the reference (exp2 numpower.c:3153, rsqrt :1788-1791 wrong branch) return NULL here. */
+#include "ndmath/cuda/cuda_math.h"
+typedef void (*gpu_fn)(int, float *);
+static gpu_fn gpu_table(int op) {
+    switch (op) {
+        case 0: return cuda_float_abs;     case 1: return cuda_float_sqrt;    case 2: return cuda_float_exp;
+        case 4: return cuda_float_expm1;   case 5: return cuda_float_log;     case 6: return cuda_float_log2;
+        case 7: return cuda_float_log10;   case 8: return cuda_float_log1p;   case 9: return cuda_float_logb;
+        case 10: return cuda_float_sin;    case 11: return cuda_float_cos;    case 12: return cuda_float_tan;
+        case 13: return cuda_float_arcsin; case 14: return cuda_float_arccos; case 15: return cuda_float_arctan;
+        case 16: return cuda_float_sinh;   case 17: return cuda_float_cosh;   case 18: return cuda_float_tanh;
+        case 19: return cuda_float_arcsinh; case 20: return cuda_float_arccosh; case 21: return cuda_float_arctanh;
+        case 22: return cuda_float_degrees; case 23: return cuda_float_radians; case 24: return cuda_float_rint;
+        case 25: return cuda_float_fix;    case 26: return cuda_float_trunc;  case 27: return cuda_float_floor;
+        case 28: return cuda_float_ceil;   case 29: return cuda_float_sinc;   case 30: return cuda_float_negate;
+        case 31: return cuda_float_positive; case 32: return cuda_float_sign; case 33: return cuda_float_reciprocal;
+        default: return NULL;
+    }
+}
+#endif
 long ref_unary(int op, const float *in, long n, float *out, float p0, float p1, double *seconds) {
     int shape[1] = {(int) n};
     NDArray *na = wrap(in, shape, 1), *r = NULL;
     double t0 = now_s();
+#ifdef REF_ENTRY_GPU
+    if (op == 35) r = NDArrayMathGPU_ElementWise2F(na, cuda_float_clip, p0, p1);
+    else if (op == 36) r = NDArrayMathGPU_ElementWise1F(na, cuda_float_round, p0);
+    else if (op == 37) r = NDArray_Multiply_Float(na, na);
+    else { gpu_fn f = gpu_table(op); if (f) r = NDArrayMathGPU_ElementWise(na, f); }
+    if (0)
+#endif
     if (op == 35) r = NDArray_Map2F(na, float_clip, p0, p1);        /* clip(min,max) */
     else if (op == 36) r = NDArray_Map1F(na, float_round, p0);      /* round(decimals) */
     else if (op == 37) r = NDArray_Multiply_Float(na, na);          /* square: numpower.c:3093 */
