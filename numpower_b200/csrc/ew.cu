@@ -191,63 +191,73 @@ __global__ void __launch_bounds__(EW_THREADS) ew_flat_scalar(float *__restrict__
 // 2-D broadcast: out is (R, C) contiguous.  Each operand is described by a row stride
 // (elements, 0 = same row for every r) and a column mode (1 = contiguous along C,
 // 0 = one value per row).  Thread (tx, ty): tx walks column groups, ty interleaves rows.
-// An operand with row stride 0 and column mode 1 (a row vector) is loaded ONCE per thread
-// and kept in registers; a per-row scalar (column vector) is one broadcast load per row.
+// SMASK (compile time) marks the operands that STREAM from HBM (one fresh 128-bit load per
+// row); the others are broadcast operands that cost no bandwidth: a row vector (row stride 0)
+// is loaded ONCE per thread and kept in registers, a column vector is one broadcast scalar
+// load per row.  Only streaming operands occupy the U-deep register pipeline, so a kernel with
+// a single streaming input keeps 8 rows (8 x 16 B per thread) in flight instead of 4.
 struct Operand2D {
     const float *p;
     int64_t rs;
     int cm;
 };
+__host__ __device__ constexpr int popc3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
 
-template <int NIN, class F, int VEC>
+template <int NIN, class F, int VEC, int SMASK>
 __global__ void __launch_bounds__(EW_THREADS) ew_bcast2d(float *__restrict__ out, Operand2D A, Operand2D B, Operand2D Cc,
                                                          int64_t R, int64_t Ccols, int bx, F f) {
+    constexpr int NS = popc3(SMASK);
+    constexpr int U = NS <= 1 ? 8 : 4;
     const int tx = threadIdx.x % bx, ty = threadIdx.x / bx, by = EW_THREADS / bx;
     const int64_t CG = Ccols / VEC;  // column groups
+    const Operand2D ops[3] = {A, B, Cc};
     for (int64_t cg = (int64_t)blockIdx.x * bx + tx; cg < CG; cg += (int64_t)gridDim.x * bx) {
         const int64_t col = cg * VEC;
         float4 hoist[3];
-        const Operand2D ops[3] = {A, B, Cc};
 #pragma unroll
         for (int k = 0; k < NIN; k++) {
             hoist[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ops[k].rs == 0 && ops[k].cm == 1) {
+            if (!((SMASK >> k) & 1) && ops[k].cm == 1) {   // row vector
                 if (VEC == 4) hoist[k] = *reinterpret_cast<const float4 *>(ops[k].p + col);
                 else hoist[k].x = ops[k].p[col];
             }
         }
-        for (int64_t r0 = (int64_t)blockIdx.y * by * EW_UNROLL + ty; r0 < R; r0 += (int64_t)gridDim.y * by * EW_UNROLL) {
-            float4 v[3][EW_UNROLL];
+        for (int64_t r0 = (int64_t)blockIdx.y * by * U + ty; r0 < R; r0 += (int64_t)gridDim.y * by * U) {
+            float4 v[NS > 0 ? NS : 1][U];
+            float sc[3][U];
 #pragma unroll
-            for (int u = 0; u < EW_UNROLL; u++) {
+            for (int u = 0; u < U; u++) {
                 const int64_t r = r0 + (int64_t)u * by;
                 if (r < R) {
 #pragma unroll
                     for (int k = 0; k < NIN; k++) {
                         const Operand2D &o = ops[k];
-                        if (o.cm == 0) {
-                            float s = __ldg(o.p + r * o.rs);
-                            v[k][u] = make_float4(s, s, s, s);
-                        } else if (o.rs == 0) {
-                            v[k][u] = hoist[k];
-                        } else if (VEC == 4) {
-                            v[k][u] = ldg_stream(reinterpret_cast<const float4 *>(o.p + r * o.rs + col));
-                        } else {
-                            v[k][u].x = ldg_stream(o.p + r * o.rs + col);
+                        if ((SMASK >> k) & 1) {
+                            constexpr int dummy = 0;
+                            (void)dummy;
+                            const int slot = popc3(SMASK & ((1 << k) - 1));
+                            if (VEC == 4) v[slot][u] = ldg_stream(reinterpret_cast<const float4 *>(o.p + r * o.rs + col));
+                            else v[slot][u].x = ldg_stream(o.p + r * o.rs + col);
+                        } else if (o.cm == 0) {
+                            sc[k][u] = __ldg(o.p + r * o.rs);
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < EW_UNROLL; u++) {
+            for (int u = 0; u < U; u++) {
                 const int64_t r = r0 + (int64_t)u * by;
                 if (r < R) {
-                    if (VEC == 4) {
-                        stg_stream(reinterpret_cast<float4 *>(out + r * Ccols + col),
-                                   apply4(f, v[0][u], NIN > 1 ? v[1][u] : v[0][u], NIN > 2 ? v[2][u] : v[0][u]));
-                    } else {
-                        out[r * Ccols + col] = f(v[0][u].x, NIN > 1 ? v[1][u].x : 0.f, NIN > 2 ? v[2][u].x : 0.f);
+                    float4 arg[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (k >= NIN) arg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        else if ((SMASK >> k) & 1) arg[k] = v[popc3(SMASK & ((1 << k) - 1))][u];
+                        else if (ops[k].cm == 1) arg[k] = hoist[k];
+                        else arg[k] = make_float4(sc[k][u], sc[k][u], sc[k][u], sc[k][u]);
                     }
+                    if (VEC == 4) stg_stream(reinterpret_cast<float4 *>(out + r * Ccols + col), apply4(f, arg[0], arg[1], arg[2]));
+                    else out[r * Ccols + col] = f(arg[0].x, arg[1].x, arg[2].x);
                 }
             }
         }
@@ -366,6 +376,7 @@ static int launch_strided(float *out, const float *const *in, int ndim, const in
         int64_t R = c.ndim == 2 ? c.shape[0] : 1, C = c.ndim == 2 ? c.shape[1] : c.shape[0];
         Operand2D ops[3];
         bool ok = true, vec = aligned16(out) && (C % 4 == 0);
+        int smask = 0;
         for (int k = 0; k < NIN; k++) {
             int64_t rs = c.ndim == 2 ? c.st[k][0] : 0, cs = c.ndim == 2 ? c.st[k][1] : c.st[k][0];
             if (cs != 0 && cs != 1) ok = false;
@@ -373,22 +384,45 @@ static int launch_strided(float *out, const float *const *in, int ndim, const in
             ops[k].rs = rs;
             ops[k].cm = (int)cs;
             if (cs == 1) vec = vec && aligned16(in[k]) && (rs % 4 == 0);
+            if (cs == 1 && (rs != 0 || R == 1)) smask |= 1 << k;   // streams from HBM
         }
         for (int k = NIN; k < 3; k++) ops[k] = ops[0];
         if (ok) {
             const int V = vec ? 4 : 1;
+            const int U = popc3(smask) <= 1 ? 8 : 4;
             int64_t CG = C / V;
             int bx = 1;
             while (bx < EW_THREADS && bx < CG) bx <<= 1;
             int by = EW_THREADS / bx;
-            int64_t gx = (CG + bx - 1) / bx, gy = (R + (int64_t)by * EW_UNROLL - 1) / ((int64_t)by * EW_UNROLL);
+            int64_t gx = (CG + bx - 1) / bx, gy = (R + (int64_t)by * U - 1) / ((int64_t)by * U);
             int64_t cap = (int64_t)ctx().num_sms * 16;
             if (gx > cap) gx = cap;
             if (gy > 65535) gy = 65535;
             if (gx * gy > cap * 4 && gy > 1) { gy = (cap * 4) / gx; if (gy < 1) gy = 1; }
             dim3 grid((unsigned)gx, (unsigned)gy);
-            if (vec) ew_bcast2d<NIN, F, 4><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);
-            else ew_bcast2d<NIN, F, 1><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);
+#define NB_BCAST_LAUNCH(MASK)                                                                                          \
+    case MASK:                                                                                                         \
+        if (vec) ew_bcast2d<NIN, F, 4, MASK><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);     \
+        else ew_bcast2d<NIN, F, 1, MASK><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);         \
+        break;
+            switch (smask) {
+                NB_BCAST_LAUNCH(0)
+                NB_BCAST_LAUNCH(1)
+                NB_BCAST_LAUNCH(2)
+                NB_BCAST_LAUNCH(3)
+                default:
+                    if constexpr (NIN == 3) {
+                        switch (smask) {
+                            NB_BCAST_LAUNCH(4)
+                            NB_BCAST_LAUNCH(5)
+                            NB_BCAST_LAUNCH(6)
+                            NB_BCAST_LAUNCH(7)
+                            default: break;
+                        }
+                    }
+                    break;
+            }
+#undef NB_BCAST_LAUNCH
             NB_LAUNCH_CHECK();
             return NB200_OK;
         }

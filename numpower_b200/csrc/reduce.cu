@@ -194,8 +194,10 @@ __global__ void __launch_bounds__(128) reduce_rows_seq_kernel(float *__restrict_
 constexpr int COL_BX = 32;
 template <int OP, int VEC, int BY, bool SEQ>
 __global__ void __launch_bounds__(COL_BX *BY) reduce_cols_kernel(float *__restrict__ out, const float *__restrict__ in,
-                                                                 int64_t len, int64_t inner, int S, int64_t seg) {
+                                                                 int64_t len, int64_t inner, int S, int64_t seg,
+                                                                 float *__restrict__ final_out, unsigned int *__restrict__ ticket) {
     __shared__ float smem[BY][COL_BX * VEC + 1];
+    __shared__ bool is_last;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t o = blockIdx.y / S;
     const int s = (int)(blockIdx.y % S);
@@ -267,6 +269,46 @@ __global__ void __launch_bounds__(COL_BX *BY) reduce_cols_kernel(float *__restri
             }
             dst[v] = a;
         }
+    }
+    // S > 1 with a ticket: the last block of this (o, column tile) folds the S partials in fixed order,
+    // so the split reduction is still ONE launch and deterministic.
+    if (S > 1 && ticket != nullptr) {
+        __threadfence();
+        __syncthreads();
+        if (tx == 0 && ty == 0) {
+            unsigned int t = atomicAdd(&ticket[o * gridDim.x + blockIdx.x], 1u);
+            is_last = (t == (unsigned)S - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        float a[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) a[v] = Red<OP>::identity();
+        if (col < inner) {
+            for (int ss = ty; ss < S; ss += BY) {
+                const float *src = out + (o * S + ss) * inner + col;
+#pragma unroll
+                for (int v = 0; v < VEC; v++) a[v] = Red<OP>::comb(a[v], __ldcg(src + v));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < VEC; v++) smem[ty][tx * VEC + v] = a[v];
+        __syncthreads();
+        if (ty == 0 && col < inner) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                float r = smem[0][tx * VEC + v];
+                for (int y = 1; y < BY; y++) r = Red<OP>::comb(r, smem[y][tx * VEC + v]);
+                if (OP == NB200_MIN || OP == NB200_MAX) {   // index-0 NaN planted in partial 0 (see above)
+                    float first = __ldcg(out + (o * S) * inner + col + v);
+                    if (isnan(first)) r = first;
+                }
+                final_out[o * inner + col + v] = r;
+            }
+        }
+        if (tx == 0 && ty == 0) ticket[o * gridDim.x + blockIdx.x] = 0;
     }
 }
 
@@ -505,7 +547,8 @@ static int reduce_rows(float *out, const float *in, int64_t rows, int64_t len, i
 }
 
 template <int OP, int VEC, int BY, bool SEQ>
-static int launch_cols(float *out, const float *in, int64_t outer, int64_t len, int64_t inner, int S, int64_t seg) {
+static int launch_cols(float *out, const float *in, int64_t outer, int64_t len, int64_t inner, int S, int64_t seg,
+                       float *final_out = nullptr, unsigned int *ticket = nullptr) {
     int64_t gx = (inner + (int64_t)COL_BX * VEC - 1) / ((int64_t)COL_BX * VEC);
     for (int64_t o0 = 0; o0 < outer * S; o0 += 65535) {
         int64_t ny = outer * S - o0 < 65535 ? outer * S - o0 : 65535;
@@ -513,7 +556,7 @@ static int launch_cols(float *out, const float *in, int64_t outer, int64_t len, 
         dim3 grid((unsigned)gx, (unsigned)ny), block(COL_BX, BY);
         // with S == 1 blockIdx.y == o - o0/S
         reduce_cols_kernel<OP, VEC, BY, SEQ><<<grid, block, 0, ctx().stream>>>(
-            out + (S == 1 ? o0 * inner : 0), in + (S == 1 ? o0 * len * inner : 0), len, inner, S, seg);
+            out + (S == 1 ? o0 * inner : 0), in + (S == 1 ? o0 * len * inner : 0), len, inner, S, seg, final_out, ticket);
         NB_LAUNCH_CHECK();
     }
     return NB200_OK;
@@ -529,7 +572,7 @@ static int reduce_cols(float *out, const float *in, int64_t outer, int64_t len, 
     // TREE: BY = 8 threads split the axis inside a block; S segments across blocks if the grid is small
     const int VEC = vec ? 4 : 1;
     int64_t blocks = ((inner + COL_BX * VEC - 1) / (COL_BX * VEC)) * outer;
-    int64_t target = (int64_t)ctx().num_sms * 8;
+    int64_t target = (int64_t)ctx().num_sms * 16;
     int S = 1;
     if (blocks < target && len >= 64) {
         int64_t want = (target + blocks - 1) / blocks, maxS = len / 32;
@@ -547,6 +590,11 @@ static int reduce_cols(float *out, const float *in, int64_t outer, int64_t len, 
     int rc = ensure_scratch(outer * S * inner * (int64_t)sizeof(float));
     if (rc != NB200_OK) return rc;
     float *partials = static_cast<float *>(ctx().scratch);
+    const int64_t gx = (inner + (int64_t)COL_BX * VEC - 1) / ((int64_t)COL_BX * VEC);
+    if (outer * gx <= 4096) {   // one launch: last block per column tile folds the partials (ticket array has 4096 slots)
+        return vec ? launch_cols<OP, 4, 8, false>(partials, in, outer, len, inner, S, seg, out, ctx().ticket)
+                   : launch_cols<OP, 1, 8, false>(partials, in, outer, len, inner, S, seg, out, ctx().ticket);
+    }
     rc = vec ? launch_cols<OP, 4, 8, false>(partials, in, outer, len, inner, S, seg)
              : launch_cols<OP, 1, 8, false>(partials, in, outer, len, inner, S, seg);
     if (rc != NB200_OK) return rc;

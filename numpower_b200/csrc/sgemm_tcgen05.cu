@@ -47,7 +47,17 @@ struct GemmCfg {
     static constexpr int STAGE_BYTES = NPART * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
     static constexpr int ACC_STAGES = 2;
-    static constexpr int TMEM_COLS = ACC_STAGES * BN;    // 256 or 512 (power of two)
+    // TF32x3 keeps fp32-class accuracy only if the tensor core's truncating (round-toward-zero) fp32
+    // accumulation is kept short: measured on B200 the bias grows ~ -1e-8 * K (4.3e-5 at K = 4096).
+    // CHUNKED mode therefore (a) accumulates the leading product a_hi.b_hi in chunks of KC along K into a
+    // 2-deep TMEM ring that the epilogue warps drain into a running total with round-to-nearest adds
+    // (tcgen05.ld / FADD / tcgen05.st), and (b) keeps the 2^-11-smaller cross terms in their own
+    // accumulator.  TMEM columns: [0,BN) [BN,2BN) main ring | [2BN,3BN) cross terms | [3BN,4BN) running total.
+    static constexpr bool CHUNKED = PASSES == 3;
+    static constexpr int KC = 256;                       // K elements per accumulation chunk
+    static constexpr int KB_PER_CHUNK = KC / BK;
+    static constexpr int TMEM_COLS = CHUNKED ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
+    static_assert(!CHUNKED || BN == 128, "chunked TF32x3 uses 128-column tiles (4 x 128 TMEM columns)");
     static constexpr int THREADS = 192;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(STAGES >= 2, "need at least a double buffer");
@@ -194,6 +204,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (64-bit), SM100 format:
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
@@ -233,7 +254,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t cross_empty_bar = bar_base + 8u * (2 * STAGES + 4);
+    const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
     // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
     auto a_smem = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + part * Cfg::A_BYTES; };
     auto b_smem = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + NPART * Cfg::A_BYTES + part * Cfg::B_BYTES; };
@@ -253,6 +275,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
+        mbar_init(cross_empty_bar, 4 * CG);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<CG>(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -296,34 +319,71 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         if (leader) {
             constexpr uint32_t idesc = make_idesc_tf32(BM * CG, BN);
             int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
+            uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
             for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_kb; kb++) {
-                    mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                if constexpr (!Cfg::CHUNKED) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
                     tc_fence_after();
-                    if (elect_one()) {
-                        // x3 order: small cross terms first, then the leading product
-                        constexpr int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
-#pragma unroll
-                        for (int ps = 0; ps < PASSES; ps++) {
-                            const int ia = PASSES == 3 ? pa[ps] : 0, ib = PASSES == 3 ? pb[ps] : 0;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < num_kb; kb++) {
+                        mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                        tc_fence_after();
+                        if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                const uint64_t da = make_smem_desc(a_smem(stage, ia) + k * 32, 16, 1024, LAYOUT_SW128);
-                                const uint64_t db = make_smem_desc(b_smem(stage, ib) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                                umma_tf32<CG>(d_tmem, da, db, idesc, (kb | ps | k) != 0 ? 1u : 0u);
+                                const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
+                                const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                                umma_tf32<CG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
+                            umma_commit<CG>(empty_bar(stage));
+                            if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
                         }
-                        umma_commit<CG>(empty_bar(stage));
-                        if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                } else {
+                    // cross-term accumulator of the previous tile must have been read out
+                    mbar_wait(cross_empty_bar, tile_phase ^ 1u, p.debug, 0x500u);
+                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+                    for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
+                        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
+                        tc_fence_after();
+                        const uint32_t d_main = tmem_base + (uint32_t)(acc * BN);
+                        const int kb1 = kb0 + Cfg::KB_PER_CHUNK < num_kb ? kb0 + Cfg::KB_PER_CHUNK : num_kb;
+                        for (int kb = kb0; kb < kb1; kb++) {
+                            mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                // a_lo.b_hi and a_hi.b_lo -> cross accumulator (whole K); a_hi.b_hi -> this chunk's accumulator
+#pragma unroll
+                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                    const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                                    umma_tf32<CG>(d_cross, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                }
+#pragma unroll
+                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                    const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                                    umma_tf32<CG>(d_cross, da, db, idesc, 1u);
+                                }
+#pragma unroll
+                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                    const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                                    umma_tf32<CG>(d_main, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                                }
+                                umma_commit<CG>(empty_bar(stage));
+                                if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(acc));
+                            }
+                            __syncwarp();
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                    }
+                    tile_phase ^= 1u;
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
@@ -332,20 +392,14 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
             const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
             const int m_tile = (int)(r % p.tiles_m), n_tile = (int)(r / p.tiles_m);
             const int64_t row = (int64_t)m_tile * BM * CG + (int64_t)rank * BM + quarter * 32 + lane;
             const int64_t col0 = (int64_t)n_tile * BN;
             float *crow = p.C + b * p.strideC + row * p.ldc;
-            mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
-                tmem_ld_wait();
+            auto store_row = [&](int c, const uint32_t (&v)[32]) {
                 const int64_t col = col0 + c * 32;
                 if (row < p.M) {
                     if (vec_ok && col + 32 <= p.N) {
@@ -360,14 +414,67 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             if (col + q < p.N) crow[col + q] = __uint_as_float(v[q]);
                     }
                 }
+            };
+            if constexpr (!Cfg::CHUNKED) {
+                mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
+                tc_fence_after();
+                const uint32_t taddr0 = tmem_base + lane_sel + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    store_row(c, v);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
+                    else mbar_arrive_local(tempty_bar(acc));
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            } else {
+                const uint32_t t_cross = tmem_base + lane_sel + (uint32_t)(2 * BN);
+                const uint32_t t_total = tmem_base + lane_sel + (uint32_t)(3 * BN);
+                for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
+                    const bool first = kb0 == 0, last = kb0 + Cfg::KB_PER_CHUNK >= num_kb;
+                    mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
+                    tc_fence_after();
+                    const uint32_t t_main = tmem_base + lane_sel + (uint32_t)(acc * BN);
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; c++) {
+                        uint32_t m[32], x[32];
+                        tmem_ld_32x32(t_main + (uint32_t)(c * 32), m);
+                        if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
+                        tmem_ld_wait();
+                        if (!first) {
+#pragma unroll
+                            for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
+                        }
+                        if (last) {
+                            tmem_ld_32x32(t_cross + (uint32_t)(c * 32), x);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(m[q]), __uint_as_float(x[q])));
+                            store_row(c, m);
+                        } else {
+                            tmem_st_32x32(t_total + (uint32_t)(c * 32), m);
+                        }
+                    }
+                    if (!last) tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
+                        else mbar_arrive_local(tempty_bar(acc));
+                        if (last) {
+                            if (CG == 2) mbar_arrive_leader(cross_empty_bar);
+                            else mbar_arrive_local(cross_empty_bar);
+                        }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
-                else mbar_arrive_local(tempty_bar(acc));
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     }
 
@@ -562,15 +669,22 @@ static int gemm_variant() {
     return g_variant;
 }
 
+// Default tiles: CTA pairs (cta_group::2) whenever there is more than one 128-row block;
+// TF32x1 256x256 per pair, TF32x3 256x128 per pair (chunked accumulation needs 4 x BN TMEM columns).
 template <int PASSES>
 static int dispatch_cfg(const GemmArgs &g) {
     int v = gemm_variant();
-    int cg = v ? (v >> 8) : 1;
-    int bn = v ? (v & 0xFF) * 2 : 256;   // encoded as BN/2 to fit a byte: 64 -> 128, 128 -> 256
-    if (cg == 2 && bn == 256) return launch_gemm<GemmCfg<2, 256, PASSES>>(g);
-    if (cg == 2 && bn == 128) return launch_gemm<GemmCfg<2, 128, PASSES>>(g);
-    if (cg == 1 && bn == 128) return launch_gemm<GemmCfg<1, 128, PASSES>>(g);
-    return launch_gemm<GemmCfg<1, 256, PASSES>>(g);
+    int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
+    int bn = v ? (v & 0xFF) * 2 : (PASSES == 3 ? 128 : (g.N > 128 ? 256 : 128));   // encoded as BN/2
+    if constexpr (PASSES == 3) {
+        if (cg == 2) return launch_gemm<GemmCfg<2, 128, 3>>(g);
+        return launch_gemm<GemmCfg<1, 128, 3>>(g);
+    } else {
+        if (cg == 2 && bn == 256) return launch_gemm<GemmCfg<2, 256, 1>>(g);
+        if (cg == 2 && bn == 128) return launch_gemm<GemmCfg<2, 128, 1>>(g);
+        if (cg == 1 && bn == 128) return launch_gemm<GemmCfg<1, 128, 1>>(g);
+        return launch_gemm<GemmCfg<1, 256, 1>>(g);
+    }
 }
 
 static bool tensor_path_ok(const GemmArgs &g) {

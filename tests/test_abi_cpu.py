@@ -1,0 +1,65 @@
+"""CPU tests of the boundary: libnb200.so loads, exports every symbol include/*.h declares, matches the
+ctypes prototypes, and fails LOUDLY (no CPU fallback) when no GPU is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b((?:nb200|NB|cuda|v(?:malloc|free|memcheck|memcpyd2d|memcpyh2d)|NDArray_VFLOAT\w*|NDArrayMathGPU)\w*)\s*\(", text))
+    return {n for n in names if not n.startswith("NB200_") and n not in ("NB_NDArray",)}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import numpower_b200 as nb
+    return nb.lib()
+
+
+@pytest.mark.parametrize("header", ["nb200.h", "nb200_host.h", "nb200_legacy.h"])
+def test_every_declared_symbol_is_exported(lib, header):
+    names = _declared(header)
+    assert len(names) > 10
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, f"{header}: not exported by libnb200.so: {missing}"
+
+
+def test_cublas_shim_symbols_exported(lib):
+    for n in ("nb200_shim_cublasCreate", "nb200_shim_cublasSgemm", "nb200_shim_cublasDestroy"):
+        assert hasattr(lib, n)
+
+
+def test_ctypes_table_matches_header():
+    from numpower_b200._lib import ABI
+    declared = _declared("nb200.h") | _declared("nb200_host.h")
+    assert declared <= set(ABI), sorted(declared - set(ABI))
+
+
+def test_no_cpu_fallback_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpower_b200 as nb
+    with pytest.raises(nb.BackendError, match="no CPU fallback"):
+        nb.NDArray.array(np.ones((2, 2), np.float32)).gpu()
+    a = nb.NDArray.array(np.ones((2, 2), np.float32))   # host container works without a device
+    assert a.shape == (2, 2) and not a.isGPU()
+    with pytest.raises(nb.BackendError, match="GPU only"):
+        nb.nd.add(a, a)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under numpower_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "numpower_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
