@@ -100,26 +100,38 @@ def run_reference(args):
     import oracle
     use_ref = oracle.ref.available
     impl = oracle.ref if use_ref else oracle.port
-    n = MATMUL_N
+    if use_ref:
+        oracle.ref.lib  # load
+        oracle.ref.set_blas_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
     rng = np.random.default_rng(3)
+    if args.gpus > 1:
+        # same workload as our multi-GPU arm (batched 2048^2 matmuls = a loop of NDArray_Matmul calls),
+        # bounded sample: 4 matrices per step
+        n, per_step = SHARD_N, 4
+        workload = (f"batched nd::matmul {SHARD_BATCH} x ({n}x{n}) per GPU x {args.gpus} GPUs, reference CPU path: loop of "
+                    f"NDArray_Matmul -> cblas_sgemm; bounded sample of {per_step} matrices per step")
+    else:
+        n, per_step = MATMUL_N, 1
+        workload = f"nd::matmul {n}x{n} fp32, reference CPU path (NDArray_Matmul -> OpenBLAS cblas_sgemm)"
     a, b = rng.random((n, n), dtype=np.float32), rng.random((n, n), dtype=np.float32)
     for _ in range(max(1, min(args.warmup, 2))):
         impl.matmul(a, b)
     steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(steps):
-        impl.matmul(a, b)
+        for _ in range(per_step):
+            impl.matmul(a, b)
     dt = (time.perf_counter() - t0) / steps
     info = oracle.ref.blas_info() if use_ref else {}
     cores = info.get("threads", os.cpu_count() if use_ref else os.cpu_count())
-    val = 2.0 * n ** 3 / dt / 1e12
+    val = per_step * 2.0 * n ** 3 / dt / 1e12
     line = {
         "impl": "reference", "metric": "nd::matmul useful TFLOP/s (fp32 in/out)", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"nd::matmul {n}x{n} fp32, reference CPU path (NDArray_Matmul -> OpenBLAS cblas_sgemm)"},
+        "config": {"workload": workload},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "reference" if use_ref else "port",
-                         "sample": f"{steps} full {n}^3 matmuls", "blas": info.get("config", "")},
+                         "sample": f"{steps} steps x {per_step} full {n}^3 matmuls", "blas": info.get("config", "")},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -178,6 +190,9 @@ def cpu_baseline_matmul(n):
     import oracle
     use_ref = oracle.ref.available
     impl = oracle.ref if use_ref else oracle.port
+    if use_ref:
+        oracle.ref.lib
+        oracle.ref.set_blas_threads(os.cpu_count() or 1)
     rng = np.random.default_rng(3)
     a, b = rng.random((n, n), dtype=np.float32), rng.random((n, n), dtype=np.float32)
     impl.matmul(a, b)
@@ -302,6 +317,17 @@ def run_single(args):
     t = B.time_steps(lambda: B.check(lib.nb200_ew_binary(0, so.data_ptr(), s.data_ptr(), s2.data_ptr(), 1, s1, st1, st1)), 50, 5)
     extras["add_1024sq_l2_warm"] = {"ms": t, "GBps": gbps(3 * (1 << 22), t)}
 
+    # the N>1 workload on ONE GPU (weak-scaling base for bench.py --gpus N): 128 x (2048x2048), TF32x3
+    del x
+    ab = torch.rand(SHARD_BATCH, SHARD_N, SHARD_N, device="cuda", generator=g)
+    bb_ = torch.rand(SHARD_BATCH, SHARD_N, SHARD_N, device="cuda", generator=g)
+    cb = torch.empty(SHARD_BATCH, SHARD_N, SHARD_N, device="cuda")
+    sn = SHARD_N
+    t = B.time_steps(lambda: B.check(lib.nb200_sgemm_batched(cb.data_ptr(), ab.data_ptr(), bb_.data_ptr(), SHARD_BATCH, sn, sn, sn,
+                                                             sn * sn, sn * sn, sn * sn, 0)), 5, 3)
+    extras["batched_matmul_128x2048sq_1gpu"] = {"ms": t, "useful_tflops": SHARD_BATCH * 2.0 * sn ** 3 / t / 1e9,
+                                                "note": "same per-GPU workload as bench.py --gpus N (weak-scaling base; sustained, power-capped)"}
+    del ab, bb_, cb
     tf32_peak = peaks["bf16_tflops"] / 2.0   # tcgen05 kind::tf32 runs at half the bf16 rate
     useful = flops / ms / 1e9
     extras["matmul_4096_tf32x1"] = {"ms": ms_x1, "useful_tflops": flops / ms_x1 / 1e9, "frac_tf32_peak": flops / ms_x1 / 1e9 / tf32_peak,

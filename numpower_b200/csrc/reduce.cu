@@ -211,10 +211,11 @@ __global__ void __launch_bounds__(COL_BX *BY) reduce_cols_kernel(float *__restri
     if (col < inner) {
         const float *base = in + o * len * inner + col;
         int64_t l = l0 + ty;
-        for (; l + 3 * BY < l1; l += 4 * BY) {
-            float x[4][VEC];
+        constexpr int CU = 8;   // rows in flight per thread
+        for (; l + (CU - 1) * BY < l1; l += CU * BY) {
+            float x[CU][VEC];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < CU; u++) {
                 const float *p = base + (l + (int64_t)u * BY) * inner;
                 if (VEC == 4) {
                     float4 t = ldg_stream(reinterpret_cast<const float4 *>(p));
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(COL_BX *BY) reduce_cols_kernel(float *__restri
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int u = 0; u < CU; u++)
 #pragma unroll
                 for (int v = 0; v < VEC; v++) {
                     if (SEQ) acc[v] = started ? Red<OP>::seq(acc[v], x[u][v]) : x[u][v];
@@ -572,10 +573,11 @@ static int reduce_cols(float *out, const float *in, int64_t outer, int64_t len, 
     // TREE: BY = 8 threads split the axis inside a block; S segments across blocks if the grid is small
     const int VEC = vec ? 4 : 1;
     int64_t blocks = ((inner + COL_BX * VEC - 1) / (COL_BX * VEC)) * outer;
-    int64_t target = (int64_t)ctx().num_sms * 16;
+    // one balanced wave: 8 resident 256-thread CTAs per SM, so split the axis into floor(slots / tiles) segments
+    int64_t target = (int64_t)ctx().num_sms * 8;
     int S = 1;
-    if (blocks < target && len >= 64) {
-        int64_t want = (target + blocks - 1) / blocks, maxS = len / 32;
+    if (blocks * 2 <= target && len >= 64) {
+        int64_t want = target / blocks, maxS = len / 32;
         S = (int)(want < maxS ? want : maxS);
         if (S < 1) S = 1;
         if (S > 256) S = 256;

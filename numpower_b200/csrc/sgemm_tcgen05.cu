@@ -22,8 +22,9 @@
 //
 // Precision modes (include/nb200.h):
 //   TF32X1  operands are fed as raw fp32 (the tensor core reads the top 19 bits)
-//   TF32X3  error-compensated: a = a_hi + a_lo (both TF32-representable, produced by a split
-//           pre-pass), C = a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  — three MMAs per k-step, fp32-class accuracy
+//   TF32X3  error-compensated: a = a_hi + a_lo with a_hi = trunc_tf32(a) (what the tensor core reads from the raw
+//           array) and a_lo = rna_tf32(a - a_hi) from the pre-pass; C = a_lo.b_hi + a_hi.b_lo + a_hi.b_hi —
+//           three MMAs per k-step, chunked round-to-nearest accumulation (GemmCfg::CHUNKED), fp32-class accuracy
 //
 // Flops: 2*M*N*K useful (x3 executes 6*M*N*K on the tensor pipe).
 #include "common.cuh"
@@ -489,29 +490,35 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 }
 
 // ------------------------------------------------------------------ TF32 split pre-pass (x3)
-// hi = rna_tf32(a) (low 13 bits zero), lo = rna_tf32(a - hi): a == hi + lo up to 2^-22 |a|.
+// The tensor core reads an fp32 operand as TF32 by TRUNCATION (measured), so the raw array already is
+// a_hi = trunc_tf32(a).  The pre-pass only writes the remainder  a_lo = rna_tf32(a - trunc_tf32(a))
+// (a - trunc(a) is exact in fp32; the final rounding to TF32 is unbiased, relative 2^-21 of a).
+// One launch covers both operands: 4 B read + 4 B written per operand element.
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in, float *__restrict__ hi,
-                                                         float *__restrict__ lo, int64_t n) {
-    const int64_t n4 = n >> 2;
-    const float4 *in4 = reinterpret_cast<const float4 *>(in);
-    float4 *hi4 = reinterpret_cast<float4 *>(hi), *lo4 = reinterpret_cast<float4 *>(lo);
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
-        float4 a = ldg_stream(in4 + i), h, l;
-        h.x = to_tf32(a.x); h.y = to_tf32(a.y); h.z = to_tf32(a.z); h.w = to_tf32(a.w);
-        l.x = to_tf32(a.x - h.x); l.y = to_tf32(a.y - h.y); l.z = to_tf32(a.z - h.z); l.w = to_tf32(a.w - h.w);
-        hi4[i] = h;
-        lo4[i] = l;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-        int64_t i = (n4 << 2) + threadIdx.x;
-        float h = to_tf32(in[i]);
-        hi[i] = h;
-        lo[i] = to_tf32(in[i] - h);
+__device__ __forceinline__ float lo_part(float a) {
+    const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+    return to_tf32(a - hi);
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
+                                                         const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1) {
+    const int64_t g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;   // 4-element groups (spans are padded to a multiple of 4)
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
+        const bool second = i >= g0;
+        const int64_t j = second ? i - g0 : i;
+        const float *in = second ? in1 : in0;
+        float *lo = second ? lo1 : lo0;
+        const int64_t n = second ? n1 : n0;
+        if ((j << 2) + 4 <= n) {
+            float4 a = ldg_stream(reinterpret_cast<const float4 *>(in) + j), l;
+            l.x = lo_part(a.x); l.y = lo_part(a.y); l.z = lo_part(a.z); l.w = lo_part(a.w);
+            reinterpret_cast<float4 *>(lo)[j] = l;
+        } else {
+            for (int64_t e = j << 2; e < n; e++) lo[e] = lo_part(in[e]);
+        }
     }
 }
 
@@ -643,12 +650,13 @@ static int launch_gemm(const GemmArgs &g) {
     return NB200_OK;
 }
 
-static int launch_split(const float *in, float *hi, float *lo, int64_t n) {
-    int64_t blocks = ((n >> 2) + 255) / 256;
+static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1) {
+    int64_t groups = ((n0 + 3) >> 2) + ((n1 + 3) >> 2);
+    if (groups == 0) return NB200_OK;
+    int64_t blocks = (groups + 255) / 256;
     int64_t cap = (int64_t)ctx().num_sms * 16;
     if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in, hi, lo, n);
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1);
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }
@@ -710,30 +718,30 @@ static int gemm_impl(GemmArgs g, int precision) {
         return NB200_OK;
     }
     if (precision == NB200_GEMM_TF32X1) return dispatch_cfg<1>(g);
-    // ---- TF32x3: split pre-pass into the context workspace, batch processed in chunks
-    const int64_t one_a = round4(span(1, 0, g.M, g.lda, g.K)), one_b = round4(span(1, 0, g.K, g.ldb, g.N));
+    // ---- TF32x3: lo-part pre-pass into the context workspace, batch processed in chunks
     int64_t chunk = g.batch;
-    const int64_t budget = (int64_t)4 << 30;  // 4 GiB of workspace per chunk at most
+    const int64_t budget = (int64_t)4 << 30;  // at most 4 GiB of workspace per chunk
     if (g.batch > 1) {
-        int64_t per = 2 * 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0));
+        int64_t per = 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0));
         if (per > 0 && per * chunk > budget) chunk = budget / per;
         if (chunk < 1) chunk = 1;
     }
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
-        const int64_t na = round4(span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K));
-        const int64_t nbb = round4(span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N));
-        (void)one_a; (void)one_b;
-        int rc = ensure_gemm_ws((2 * na + 2 * nbb) * 4 + 256);
+        const int64_t sa = span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K), sb = span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N);
+        const int64_t na = round4(sa), nbb = round4(sb);
+        int rc = ensure_gemm_ws((na + nbb) * 4 + 256);
         if (rc != NB200_OK) return rc;
         float *ws = static_cast<float *>(ctx().gemm_ws);
-        float *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
+        float *a_lo = ws, *b_lo = ws + na;
         const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
-        if (b0 == 0 || g.sA) { if ((rc = launch_split(a_src, a_hi, a_lo, span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K))) != NB200_OK) return rc; }
-        if (b0 == 0 || g.sB) { if ((rc = launch_split(b_src, b_hi, b_lo, span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N))) != NB200_OK) return rc; }
+        // a shared (stride-0) operand is split once, with the first chunk
+        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);
+        // the vector path needs 16-byte aligned sources (tensor_path_ok guarantees it for the bases and strides)
+        if ((rc = launch_split(a_src, a_lo, do_a ? sa : 0, b_src, b_lo, do_b ? sb : 0)) != NB200_OK) return rc;
         GemmArgs c = g;
         c.batch = nb;
-        c.A = a_hi; c.A_lo = a_lo; c.B = b_hi; c.B_lo = b_lo;
+        c.A = a_src; c.A_lo = a_lo; c.B = b_src; c.B_lo = b_lo;
         c.C = g.C + b0 * g.sC;
         if ((rc = dispatch_cfg<3>(c)) != NB200_OK) return rc;
     }
@@ -770,7 +778,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
 extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes) {
     if (!bytes) return set_error(NB200_EINVAL, "null argument");
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
-    int64_t per = 2 * 4 * (round4(M * K) + round4(K * N));
+    int64_t per = 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = (int64_t)4 << 30;
     *bytes = (total > budget && batch > 1) ? (budget / per > 0 ? (budget / per) * per : per) : total;

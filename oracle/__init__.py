@@ -141,6 +141,17 @@ class _Ref:
             info = {"error": str(e)}
         return info
 
+    def set_blas_threads(self, n: int) -> int:
+        """cblas_sgemm uses OpenBLAS's own threads (all host cores in the reference); launchers such as
+        torchrun export OMP_NUM_THREADS=1, so the benchmark sets the count explicitly."""
+        try:
+            b = C.CDLL(open(os.path.join(HERE, "_ref", "blas_path.txt")).read().strip())
+            b.scipy_openblas_set_num_threads(int(n))
+            b.scipy_openblas_get_num_threads.restype = C.c_int
+            return b.scipy_openblas_get_num_threads()
+        except Exception:
+            return 0
+
     def binary(self, op: str, a, b) -> np.ndarray:
         a, b = _c32(a), _c32(b)
         big = a if a.size >= b.size else b

@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+tail -4 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -5 gpurun_out/bench_n1.err
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_n1.json").read().strip().splitlines()[-1])
+print("value", d["value"], "ms", d["ms_per_step"], "roofline", d["roofline"]["frac"], d["roofline"]["pipe_frac"], "e2e", d["e2e"]["value"], "launches", d["gpu_launches"], "clocks", d["clocks"])
+for k, v in d["extras"].items():
+    if isinstance(v, dict) and "ms" in v: print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a != "note"})
+PY
+ncu --set full --clock-control none --import-source on -k regex:"sgemm_tf32|ew_bcast2d|reduce_cols|split_tf32" -c 10 -o gpurun_out/prof_r1b \
+    python scripts/profile_targets.py gemm ew > gpurun_out/ncu_r1b.log 2>&1
+tail -2 gpurun_out/ncu_r1b.log
