@@ -166,6 +166,11 @@ int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, int64_t N, 
 /* batch of independent products; stride* in elements (0 = shared operand). */
 int nb200_sgemm_batched(float *C, const float *A, const float *B, int64_t batch, int64_t M, int64_t N, int64_t K,
                         int64_t strideA, int64_t strideB, int64_t strideC, int precision);
+/* nd::matmul on HOST operands (what `$a->gpu(); nd::matmul; ->cpu()` does in three steps, NDArray_ToGPU/ToCPU
+ * ndarray.c:1037-1093): B is uploaded once, then row blocks of A stream in, are multiplied and stream out, so the
+ * H2D and D2H copies overlap each other (full-duplex PCIe) and the compute.  Blocking; C_host complete on return.
+ * Host buffers should be pinned (nb200_host_alloc) for full PCIe speed; pageable memory works but is staged. */
+int nb200_sgemm_host(float *C_host, const float *A_host, const float *B_host, int64_t M, int64_t N, int64_t K, int precision);
 /* scratch the 3xTF32 split needs for an (M,N,K,batch) problem; allocated lazily from the
  * context and reused (bytes reported for capacity planning). */
 int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes);

@@ -52,6 +52,7 @@ ABI = {
     "nb200_argminmax_host": (C.c_int, [C.c_int, C.POINTER(C.c_float), fp, i64]),
     "nb200_sgemm": (C.c_int, [fp, fp, fp, i64, i64, i64, i64, i64, i64, C.c_int]),
     "nb200_sgemm_batched": (C.c_int, [fp, fp, fp, i64, i64, i64, i64, i64, i64, i64, C.c_int]),
+    "nb200_sgemm_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i64, i64, i64, C.c_int]),
     "nb200_sgemm_workspace_bytes": (C.c_int, [i64, i64, i64, i64, C.c_int, i64p]),
     "nb200_gemv": (C.c_int, [fp, fp, fp, i64, i64]),
     "nb200_transpose2d": (C.c_int, [fp, fp, i64, i64]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libnb200.so")
-SOURCES = ["abi.cu", "ew.cu", "reduce.cu", "sgemm_tcgen05.cu", "sgemm_debug.cu", "misc.cu", "legacy.cu", "host/ndarray_host.cpp"]
+SOURCES = ["abi.cu", "ew.cu", "reduce.cu", "sgemm_tcgen05.cu", "sgemm_debug.cu", "misc.cu", "host_pipeline.cu", "legacy.cu", "host/ndarray_host.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]

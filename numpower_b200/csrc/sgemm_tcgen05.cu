@@ -748,6 +748,15 @@ static int gemm_impl(GemmArgs g, int precision) {
     return NB200_OK;
 }
 
+// ---- internal hooks for the host-buffer pipeline (host_pipeline.cu): split one operand / run with given lo parts
+int gemm_split_operand(const float *in, float *lo, int64_t n) { return launch_split(in, lo, n, nullptr, nullptr, 0); }
+int gemm_presplit(float *C, const float *A, const float *A_lo, const float *B, const float *B_lo, int64_t M, int64_t N,
+                  int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int precision) {
+    GemmArgs g{C, A, B, A_lo, B_lo, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
+    if (!tensor_path_ok(g)) return set_error(NB200_EINVAL, "gemm_presplit: shape not served by the tensor path");
+    return precision == NB200_GEMM_TF32X1 ? dispatch_cfg<1>(g) : dispatch_cfg<3>(g);
+}
+
 }  // namespace nb200
 
 using namespace nb200;

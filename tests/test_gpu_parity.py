@@ -420,3 +420,68 @@ def test_config2_matmul_4096_checksum(nb):
     lhs = a.astype(np.float64).sum(0) @ b.astype(np.float64)
     rhs = got.astype(np.float64).sum(0)
     assert np.abs(lhs - rhs).max() / np.abs(lhs).max() <= RTOL   # systematic part of the error (measured ~1.4e-6)
+
+
+# --------------------------------------------------------------------- C-ABI level GEMM edge cases
+def _dev(nb, arr):
+    import ctypes as C
+    lib = nb.lib()
+    p = C.c_void_p()
+    assert lib.nb200_alloc(C.byref(p), arr.nbytes) == 0
+    assert lib.nb200_copy_h2d(p, arr.ctypes.data, arr.nbytes) == 0
+    return p
+
+
+def _fetch(nb, p, shape):
+    out = np.empty(shape, np.float32)
+    assert nb.lib().nb200_copy_d2h(out.ctypes.data, p, out.nbytes) == 0
+    return out
+
+
+def test_sgemm_leading_dimensions_and_ragged_edges(nb):
+    """lda/ldb/ldc larger than the logical extents (sub-matrix views) and M, N, K not multiples of the tile."""
+    lib = nb.lib()
+    r = _rng(31)
+    M, N, K, lda, ldb, ldc = 300, 200, 136, 160, 256, 208
+    abuf, bbuf = r.random((M, lda), dtype=np.float32), r.random((K, ldb), dtype=np.float32)
+    cbuf = np.full((M, ldc), -1.0, np.float32)
+    da, db, dc = _dev(nb, abuf), _dev(nb, bbuf), _dev(nb, cbuf)
+    for prec, tol in ((0, RTOL), (1, 2e-3)):
+        assert lib.nb200_sgemm(dc, da, db, M, N, K, lda, ldb, ldc, prec) == 0, lib.nb200_last_error()
+        got = _fetch(nb, dc, (M, ldc))
+        exp = ORACLE.matmul(np.ascontiguousarray(abuf[:, :K]), np.ascontiguousarray(bbuf[:, :N]))
+        assert rel_err(got[:, :N], exp).max() <= tol
+        assert (got[:, N:] == -1.0).all()   # padding columns untouched
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
+def test_sgemm_batched_shared_operand_and_many_batches(nb):
+    """strideB = 0 (one B for the whole batch) and a batch large enough to exercise several tiles per matrix."""
+    lib = nb.lib()
+    r = _rng(32)
+    batch, M, N, K = 9, 256, 128, 96
+    a, b = r.random((batch, M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
+    da, db = _dev(nb, a), _dev(nb, b)
+    dc = _dev(nb, np.zeros((batch, M, N), np.float32))
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, 0) == 0, lib.nb200_last_error()
+    got = _fetch(nb, dc, (batch, M, N))
+    for i in range(batch):
+        assert rel_err(got[i], ORACLE.matmul(a[i], b)).max() <= RTOL
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
+@pytest.mark.parametrize("mkn", [(1024, 512, 768), (700, 260, 132), (64, 64, 64)])
+def test_sgemm_host_pipeline_matches_resident_call(nb, mkn):
+    """nb200_sgemm_host (B once, A row blocks in, C row blocks out) == the resident nb200_sgemm result, bit for bit
+    for the pipelined shapes (same kernels, same order) and within 1e-5 of cblas_sgemm."""
+    lib = nb.lib()
+    M, K, N = mkn
+    r = _rng(M)
+    a, b = r.random((M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
+    c = np.empty((M, N), np.float32)
+    assert lib.nb200_sgemm_host(c.ctypes.data, a.ctypes.data, b.ctypes.data, M, N, K, 0) == 0, lib.nb200_last_error()
+    assert rel_err(c, ORACLE.matmul(a, b)).max() <= RTOL
+    resident = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    assert rel_err(c, resident).max() <= 2e-6
