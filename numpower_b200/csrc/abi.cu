@@ -4,11 +4,35 @@
 // process-global cudaSetDevice of NDArray::setDevice (numpower.c:615-635).
 #include "common.cuh"
 #include <unordered_map>
+#include <map>
+#include <cstdlib>
 
 namespace nb200 {
 
 static Ctx g_ctx;
 static std::unordered_map<void *, int64_t> g_ledger;  // live device blocks handed to the host (vmalloc leak counter, gpu_alloc.c:12,31)
+// Caching allocator behind nb200_alloc / vmalloc (SURVEY.md §8 f, N3).  The reference pays a cudaMalloc and a
+// device-synchronising cudaFree for every result array (gpu_alloc.c:11-34); here freed blocks go to a size-keyed pool
+// and are reused by later requests of a similar size.  Reuse is safe without synchronisation because every kernel of
+// this library runs on the single context stream (a block handed out again is only touched by later work on that
+// stream).  NB200_NO_CACHE=1 restores plain cudaMalloc/cudaFree.
+static std::multimap<int64_t, void *> g_pool;   // capacity -> free block
+static int64_t g_pool_bytes = 0;
+static int g_cache_enabled = -1;
+static bool cache_enabled() {
+    if (g_cache_enabled < 0) g_cache_enabled = getenv("NB200_NO_CACHE") ? 0 : 1;
+    return g_cache_enabled == 1;
+}
+static int64_t round_capacity(int64_t bytes) {
+    if (bytes < 512) return 512;
+    if (bytes < ((int64_t)1 << 20)) return (bytes + 511) & ~int64_t(511);
+    return (bytes + ((int64_t)2 << 20) - 1) & ~(((int64_t)2 << 20) - 1);   // 2 MiB granules
+}
+static void pool_release_all() {
+    for (auto &kv : g_pool) cudaFree(kv.second);
+    g_pool.clear();
+    g_pool_bytes = 0;
+}
 static thread_local char g_err[512] = "";
 
 Ctx &ctx() { return g_ctx; }
@@ -120,6 +144,7 @@ extern "C" int nb200_shutdown(void) {
     if (c.domain_flag) cudaFree(c.domain_flag);
     if (c.dev_result) cudaFree(c.dev_result);
     if (c.host_result) cudaFreeHost(c.host_result);
+    pool_release_all();
     int64_t launches = c.launches;
     c = Ctx();
     c.launches = launches;
@@ -185,14 +210,31 @@ extern "C" int nb200_alloc(void **dev_ptr, int64_t bytes) {
     NB_READY();
     if (!dev_ptr || bytes < 0) return set_error(NB200_EINVAL, "nb200_alloc: bad argument");
     *dev_ptr = nullptr;
-    size_t sz = bytes == 0 ? 16 : (size_t)bytes;
-    if (cudaMalloc(dev_ptr, sz) != cudaSuccess) {
+    const int64_t cap = round_capacity(bytes);
+    if (cache_enabled()) {
+        auto it = g_pool.lower_bound(cap);
+        if (it != g_pool.end() && it->first <= cap + cap / 4) {   // accept up to 25 % slack
+            *dev_ptr = it->second;
+            g_pool_bytes -= it->first;
+            g_ledger[*dev_ptr] = it->first;
+            g_pool.erase(it);
+            ctx().live_allocs++;
+            ctx().live_bytes += g_ledger[*dev_ptr];
+            return NB200_OK;
+        }
+    }
+    if (cudaMalloc(dev_ptr, (size_t)cap) != cudaSuccess) {
         cudaGetLastError();
-        return set_error(NB200_ENOMEM, "device memory allocation failed");  // gpu_alloc.c:15 message
+        pool_release_all();   // give cached blocks back to the driver and retry once
+        if (cudaMalloc(dev_ptr, (size_t)cap) != cudaSuccess) {
+            cudaGetLastError();
+            *dev_ptr = nullptr;
+            return set_error(NB200_ENOMEM, "device memory allocation failed");  // gpu_alloc.c:15 message
+        }
     }
     ctx().live_allocs++;
-    ctx().live_bytes += bytes;
-    g_ledger[*dev_ptr] = bytes;
+    ctx().live_bytes += cap;
+    g_ledger[*dev_ptr] = cap;
     return NB200_OK;
 }
 
@@ -202,10 +244,23 @@ extern "C" int nb200_free(void *dev_ptr) {
     // cudaFree synchronises the device, so no kernel on the context stream can still use the block
     auto it = g_ledger.find(dev_ptr);
     if (it == g_ledger.end()) return set_error(NB200_EINVAL, "nb200_free: pointer %p was not allocated by nb200_alloc", dev_ptr);
-    NB_CUDA(cudaFree(dev_ptr));
-    ctx().live_allocs--;
-    ctx().live_bytes -= it->second;
+    const int64_t cap = it->second;
     g_ledger.erase(it);
+    ctx().live_allocs--;
+    ctx().live_bytes -= cap;
+    // keep at most 32 GiB cached; larger pools are trimmed by releasing the biggest blocks first
+    if (cache_enabled() && cap <= ((int64_t)8 << 30)) {
+        g_pool.emplace(cap, dev_ptr);
+        g_pool_bytes += cap;
+        while (g_pool_bytes > ((int64_t)32 << 30) && !g_pool.empty()) {
+            auto big = std::prev(g_pool.end());
+            NB_CUDA(cudaFree(big->second));
+            g_pool_bytes -= big->first;
+            g_pool.erase(big);
+        }
+        return NB200_OK;
+    }
+    NB_CUDA(cudaFree(dev_ptr));
     return NB200_OK;
 }
 

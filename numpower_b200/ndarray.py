@@ -156,6 +156,28 @@ class nd:
     @staticmethod
     def arctan2(a, b): return nd.binary("arctan2", a, b)
 
+    # comparisons -> 0/1 float masks (src/logic.c:68-660; SURVEY §8 f, N2)
+    @staticmethod
+    def equal(a, b): return nd.binary("equal", a, b)
+    @staticmethod
+    def not_equal(a, b): return nd.binary("not_equal", a, b)
+    @staticmethod
+    def greater(a, b): return nd.binary("greater", a, b)
+    @staticmethod
+    def greater_equal(a, b): return nd.binary("greater_equal", a, b)
+    @staticmethod
+    def less(a, b): return nd.binary("less", a, b)
+    @staticmethod
+    def less_equal(a, b): return nd.binary("less_equal", a, b)
+
+    @staticmethod
+    def array_equal(a, b) -> bool:
+        """NDArray_ArrayEqual (logic.c:703-716): same shape and every element pair equal."""
+        a, b = nd._a(a), nd._a(b)
+        if a.shape != b.shape:
+            return False
+        return a.size == 0 or nd.min(nd.equal(a, b)) == 1.0
+
     @staticmethod
     def mul_add(a, b, c) -> NDArray:
         """Fused ``$a * $b + $c`` (nb200_ew_mul_add): one pass, same bits as the two nd:: calls."""

@@ -22,7 +22,8 @@ REF_SO = os.path.join(HERE, "_ref", "libnumpower_ref.so")
 PORT_SO = os.path.join(HERE, "liboracle_port.so")
 
 # op ids shared with include/nb200.h
-BIN_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "mod": 4, "pow": 5, "maximum": 6, "minimum": 7, "arctan2": 8}
+BIN_OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "mod": 4, "pow": 5, "maximum": 6, "minimum": 7, "arctan2": 8,
+           "equal": 10, "not_equal": 11, "greater": 12, "greater_equal": 13, "less": 14, "less_equal": 15}
 UN_OPS = {
     "abs": 0, "sqrt": 1, "exp": 2, "exp2": 3, "expm1": 4, "log": 5, "log2": 6, "log10": 7, "log1p": 8,
     "logb": 9, "sin": 10, "cos": 11, "tan": 12, "arcsin": 13, "arccos": 14, "arctan": 15, "sinh": 16,

@@ -38,7 +38,7 @@ for s in cblas_sgemm cblas_sgemv cblas_sasum cblas_sdot cblas_sger cblas_snrm2 \
 done
 CFLAGS="-O2 -mavx2 -march=x86-64-v3 -fPIC -w $REN -I$SHIM -I$SHIM/a/b -I$SHIM/x -I$REF -I$REF/src"
 OBJS=""
-for f in src/types src/buffer src/iterators src/initializers src/ndarray src/manipulation src/indexing \
+for f in src/types src/buffer src/iterators src/initializers src/ndarray src/manipulation src/indexing src/logic \
          src/ndmath/double_math src/ndmath/arithmetics src/ndmath/calculation src/ndmath/linalg; do
   o="$OUT/obj/$(basename $f).o"
   gcc $CFLAGS -c "$REF/$f.c" -o "$o"

@@ -66,6 +66,14 @@ void port_binary(int op, const float *a, const float *b, float *out, long n) {
     case 8: /* NDArray_Map1ND + float_arctan2 ndarray.c:715-727, double_math.c:259-261 */
         for (i = 0; i < n; i++) out[i] = atan2f(a[i], b[i]);
         break;
+    /* comparisons -> 1.0f / 0.0f, all ORDERED predicates (_mm256_cmp_ps ..._OQ / _OS and the scalar tails of
+       src/logic.c:121-660): a NaN operand gives 0 for every one of them, including not_equal (_CMP_NEQ_OQ). */
+    case 10: for (i = 0; i < n; i++) out[i] = a[i] == b[i] ? 1.0f : 0.0f; break;
+    case 11: for (i = 0; i < n; i++) out[i] = (a[i] < b[i] || a[i] > b[i]) ? 1.0f : 0.0f; break;
+    case 12: for (i = 0; i < n; i++) out[i] = a[i] > b[i] ? 1.0f : 0.0f; break;
+    case 13: for (i = 0; i < n; i++) out[i] = a[i] >= b[i] ? 1.0f : 0.0f; break;
+    case 14: for (i = 0; i < n; i++) out[i] = a[i] < b[i] ? 1.0f : 0.0f; break;
+    case 15: for (i = 0; i < n; i++) out[i] = a[i] <= b[i] ? 1.0f : 0.0f; break;
     default: break;
     }
 }

@@ -20,6 +20,7 @@
 #include "ndmath/double_math.h"
 #include "ndmath/calculation.h"
 #include "ndmath/linalg.h"
+#include "logic.h"
 
 /* ---- Zend runtime pieces the reference objects link against ------------- */
 static char g_err[1024];
@@ -145,6 +146,14 @@ long ref_binary(int op, const float *a, const int *ashape, int andim,
         case 6: r = NDArray_Maximum(na, nb); break;
         case 7: r = NDArray_Minimum(na, nb); break;
         case 8: r = NDArray_Map1ND(na, float_arctan2, nb); break;
+        /* comparisons -> 0/1 masks: src/logic.c:68 (greater), :172 (less), :272 (less_equal), :378 (greater_equal),
+         * :479 (equal), :580 (not_equal); ids = NB200_CMP_* of include/nb200.h */
+        case 10: r = NDArray_Equal(na, nb); break;
+        case 11: r = NDArray_NotEqual(na, nb); break;
+        case 12: r = NDArray_Greater(na, nb); break;
+        case 13: r = NDArray_GreaterEqual(na, nb); break;
+        case 14: r = NDArray_Less(na, nb); break;
+        case 15: r = NDArray_LessEqual(na, nb); break;
         default: break;
     }
     double t1 = now_s();

@@ -485,3 +485,32 @@ def test_sgemm_host_pipeline_matches_resident_call(nb, mkn):
     assert rel_err(c, ORACLE.matmul(a, b)).max() <= RTOL
     resident = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
     assert rel_err(c, resident).max() <= 2e-6
+
+
+# --------------------------------------------------------------------- comparisons (SURVEY §8 f, N2)
+@pytest.mark.parametrize("op", ["equal", "not_equal", "greater", "greater_equal", "less", "less_equal"])
+def test_comparisons_vs_oracle(nb, op):
+    r = _rng(14)
+    a = r.integers(-3, 4, size=(257, 130)).astype(np.float32)
+    b = r.integers(-3, 4, size=(257, 130)).astype(np.float32)
+    A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
+    np.testing.assert_array_equal(nb.nd.binary(op, A, B).toArray(), ORACLE.binary(op, a, b))
+    # broadcast: the port (the reference's less / less_equal read out of bounds when shapes differ, logic.c:229-244)
+    np.testing.assert_array_equal(nb.nd.binary(op, A, nb.NDArray.array(b[0]).gpu()).toArray(), oracle.port.binary(op, a, b[0]))
+    np.testing.assert_array_equal(nb.nd.binary(op, A, 1.0).toArray(), ORACLE.binary(op, a, np.float32(1.0)))
+    # NaN operands: every predicate is ordered in the reference (incl. not_equal)
+    a2 = a.copy().reshape(-1)[:4096]
+    a2[::7] = np.nan
+    got = nb.nd.binary(op, nb.NDArray.array(a2).gpu(), nb.NDArray.array(b.reshape(-1)[:4096]).gpu()).toArray()
+    np.testing.assert_array_equal(got, oracle.port.binary(op, a2, b.reshape(-1)[:4096]))
+    assert (got[::7] == 0).all()
+
+
+def test_array_equal(nb):
+    a = _rng(1).random((100, 37), dtype=np.float32)
+    A = nb.NDArray.array(a).gpu()
+    assert nb.nd.array_equal(A, nb.NDArray.array(a.copy()).gpu())
+    b = a.copy()
+    b[50, 3] += 1
+    assert not nb.nd.array_equal(A, nb.NDArray.array(b).gpu())
+    assert not nb.nd.array_equal(A, nb.NDArray.array(a[:50]).gpu())
