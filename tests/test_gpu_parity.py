@@ -495,7 +495,7 @@ def test_comparisons_vs_oracle(nb, op):
     b = r.integers(-3, 4, size=(257, 130)).astype(np.float32)
     A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
     np.testing.assert_array_equal(nb.nd.binary(op, A, B).toArray(), ORACLE.binary(op, a, b))
-    # broadcast: the port (the reference's less / less_equal read out of bounds when shapes differ, logic.c:229-244)
+    # broadcast: the port (the reference's less / equal read out of bounds when shapes differ, logic.c:229-244, :534-553)
     np.testing.assert_array_equal(nb.nd.binary(op, A, nb.NDArray.array(b[0]).gpu()).toArray(), oracle.port.binary(op, a, b[0]))
     np.testing.assert_array_equal(nb.nd.binary(op, A, 1.0).toArray(), ORACLE.binary(op, a, np.float32(1.0)))
     # NaN operands: every predicate is ordered in the reference (incl. not_equal)
