@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -73,7 +73,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -81,13 +81,14 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx = float(f[2])
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -244,7 +245,6 @@ def run_single(args):
     sampler = ClockSampler(0)
     sampler.start()
     ms = B.time_steps(lambda: mm(0), args.steps, args.warmup)
-    clocks = sampler.stop()
     launches = lib.nb200_launch_count() - launches0
     launches_timed = launches * args.steps // (args.steps + args.warmup)
     ms_x1 = B.time_steps(lambda: mm(1), args.steps, args.warmup)
@@ -260,6 +260,14 @@ def run_single(args):
 
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = B.time_steps(e2e_step, e2e_steps, 2)
+    clocks = sampler.stop()   # sampled across the timed matmul / TF32x1 / e2e regions (the 10 ms headline loop alone is shorter than one nvidia-smi period)
+    # raw PCIe ceilings for the e2e number: 256 MiB pinned copies
+    pin = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+    dbuf = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    t_h2d = B.time_steps(lambda: dbuf.copy_(pin, non_blocking=True), 5, 2)
+    t_d2h = B.time_steps(lambda: pin.copy_(dbuf, non_blocking=True), 5, 2)
+    pcie = {"h2d_GBps": pin.numel() * 4 / t_h2d / 1e6, "d2h_GBps": pin.numel() * 4 / t_d2h / 1e6}
+    del pin, dbuf
     e2e_err = float((hc.cuda() - c).abs().max() / c.abs().max())   # same result as the resident call
 
     # ---- extras: the HBM-bound configs (inputs > L2, plus an explicit L2 flush between timed launches)
@@ -351,7 +359,9 @@ def run_single(args):
         "cpu_baseline": cpu,
         "e2e": {"value": flops / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": ms_e2e, "steps": e2e_steps, "api": "nb200_sgemm_host (pinned host buffers, pipelined H2D/compute/D2H)",
-                "max_rel_diff_vs_resident": e2e_err},
+                "max_rel_diff_vs_resident": e2e_err, "pcie_measured": pcie,
+                "pcie_bound_ms": 2 * nbytes / pcie["h2d_GBps"] / 1e6,
+                "note": "H2D of A and B (128 MiB) is the floor: D2H of C and the GEMM overlap it"},
         "gpu_launches": int(launches_timed),
         "clocks": clocks,
         "extras": extras,
