@@ -154,11 +154,6 @@ void NB_NDArray_FREE(NB_NDArray *a) {
 NB_NDArray *NB_NDArray_Binary(int op, NB_NDArray *a, NB_NDArray *b) {
     if (!a || !b) return (NB_NDArray *)fail("null operand");
     if (!gpu_pair(a, b)) return nullptr;
-    if (a->ndim == 0 && b->ndim == 0) {  // arithmetics.c:302-316 (0-dim x 0-dim)
-        bool ok1, ok2;
-        float x = scalar_value(a, &ok1), y = scalar_value(b, &ok2);
-        (void)x; (void)y;
-    }
     if ((a->ndim == 0) != (b->ndim == 0)) {
         NB_NDArray *arr = a->ndim == 0 ? b : a, *sc = a->ndim == 0 ? a : b;
         bool ok;
@@ -276,7 +271,10 @@ NB_NDArray *NB_reduce(NB_NDArray *a, int axis, int op, int order) {
     }
     NB_NDArray *r = make(a->ndim - 1, oshape, NB_DEVICE_GPU, true);
     if (!r) return nullptr;
-    if (a->shape[axis] == 0) return r;
+    if (a->shape[axis] == 0) {   // no slices: the reference returns its NDArray_Zeros result untouched (ndarray.c:568-569)
+        if (r->numel > 0 && nb200_memset_zero(r->data, r->numel * 4) != NB200_OK) { NB_NDArray_FREE(r); return (NB_NDArray *)fail_backend("reduce"); }
+        return r;
+    }
     if (nb200_reduce_axis(op, r->data, a->data, outer, a->shape[axis], inner, order) != NB200_OK) {
         NB_NDArray_FREE(r);
         return (NB_NDArray *)fail_backend("reduce");

@@ -514,3 +514,48 @@ def test_array_equal(nb):
     b[50, 3] += 1
     assert not nb.nd.array_equal(A, nb.NDArray.array(b).gpu())
     assert not nb.nd.array_equal(A, nb.NDArray.array(a[:50]).gpu())
+
+
+# --------------------------------------------------------------------- empty / degenerate inputs
+def test_empty_and_degenerate_inputs(nb):
+    e = nb.NDArray.array(np.zeros((0,), np.float32)).gpu()
+    assert (e + e).shape == (0,) and (e + e).toArray().size == 0
+    assert nb.nd.exp(e).toArray().size == 0
+    assert nb.nd.sum(e) == 0.0 and nb.nd.prod(e) == 1.0          # empty loops of arithmetics.c:44-46, 66-68
+    with pytest.raises(nb.BackendError, match="empty sequence"):  # calculation.c:169-172
+        nb.nd.argmax(e)
+    z = nb.NDArray.array(np.zeros((4, 0, 3), np.float32)).gpu()
+    assert nb.nd.sum(z, 1).shape == (4, 3)
+    one = nb.NDArray.array(np.array([[3.5]], np.float32)).gpu()
+    assert nb.nd.argmax(one) == 0.0 and nb.nd.sum(one) == 3.5 and nb.nd.max(one) == 3.5
+    with pytest.raises(nb.BackendError, match="out of bounds"):   # ndarray.c:534-538
+        nb.nd.sum(one, 5)
+    with pytest.raises(nb.BackendError, match="broadcast"):       # arithmetics.c:199-202
+        nb.nd.add(nb.NDArray.array(np.ones((3, 4), np.float32)).gpu(), nb.NDArray.array(np.ones((5,), np.float32)).gpu())
+    with pytest.raises(nb.BackendError, match="Device mismatch"):  # arithmetics.c:163-166
+        nb.nd.add(one, nb.NDArray.array(np.ones((1, 1), np.float32)))
+    # 0-dim op 0-dim, and a CPU scalar next to a GPU array (exempt from the device check)
+    s = (one * 2.0).toArray()
+    assert s[0, 0] == 7.0
+
+
+def test_config5_batched_matmul_slice_properties(nb):
+    """BASELINE configs[4] is 1024 x (2048x2048); one GPU's shard at N = 16 (64 matrices, 1/16 of the job) through
+    the batched entry point: two sampled matrices against the reference's cblas_sgemm and every matrix through the
+    fp64 checksum identity (1^T A_i) B_i == 1^T C_i."""
+    import ctypes as C
+    import torch
+    lib = nb.lib()
+    batch, n = 64, 2048
+    g = torch.Generator(device="cuda").manual_seed(10)
+    a = torch.rand(batch, n, n, device="cuda", generator=g)
+    b = torch.rand(batch, n, n, device="cuda", generator=g)
+    c = torch.empty(batch, n, n, device="cuda")
+    torch.cuda.synchronize()
+    assert lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), batch, n, n, n, n * n, n * n, n * n, 0) == 0
+    assert lib.nb200_synchronize() == 0
+    for i in (0, 37):
+        assert rel_err(c[i].cpu().numpy(), ORACLE.matmul(a[i].cpu().numpy(), b[i].cpu().numpy())).max() <= RTOL
+    lhs = torch.bmm(a.double().sum(1, keepdim=True), b.double()).squeeze(1)   # (batch, n) fp64 checker on the GPU
+    rhs = c.double().sum(1)
+    assert float(((lhs - rhs).abs().amax(1) / lhs.abs().amax(1)).max()) <= RTOL
