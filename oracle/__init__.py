@@ -114,6 +114,8 @@ class _Ref:
             lib.ref_matmul.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _dp]
             lib.ref_dot.restype = C.c_long
             lib.ref_dot.argtypes = [_fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
+            lib.ref_matmul_nd.restype = C.c_long
+            lib.ref_matmul_nd.argtypes = [_fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
             self._lib = lib
         return self._lib
 
@@ -227,6 +229,15 @@ class _Ref:
         out = np.empty((M, N), dtype=np.float32)
         sec = C.c_double()
         n = self.lib.ref_matmul(_f(a), _f(b), M, K, N, _f(out), C.byref(sec))
+        self._check(n, "matmul")
+        self.last_seconds = sec.value
+        return out
+
+    def matmul_nd(self, a, b) -> np.ndarray:
+        a, b = _c32(a), _c32(b)
+        out = np.empty(a.shape[:-1] + (b.shape[-1],), dtype=np.float32)
+        sec = C.c_double()
+        n = self.lib.ref_matmul_nd(_f(a), _shape(a), a.ndim, _f(b), _shape(b), b.ndim, _f(out), out.size, C.byref(sec))
         self._check(n, "matmul")
         self.last_seconds = sec.value
         return out
@@ -346,3 +357,5 @@ DROPIN_SO = os.path.join(HERE, "_ref", "libnumpower_host_b200.so")
 ref = _Ref()
 port = _Port()
 dropin = _Ref(DROPIN_SO)   # reference host objects (HAVE_CUBLAS) on top of libnb200.so; needs a GPU
+N1_SO = os.path.join(HERE, "_ref", "libnumpower_host_b200_n1.so")
+dropin_n1 = _Ref(N1_SO)    # same, with the Level-1 host patches (oracle/n1_patch.py + integration/nb200_numpower_glue.c)

@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE — applies the Level-1 host patches to copies of four reference files at BUILD
+time: one inserted call per hot-path function, right after its opening brace.  Inputs are read from /root/reference,
+outputs go to oracle/_ref/n1_src/ (git-ignored); no reference source is stored in this repo.
+
+    python oracle/n1_patch.py <reference_dir> <out_dir>
+"""
+import os
+import re
+import sys
+
+DECL = ('\n#include <nb200.h>\n'
+        'NDArray *nb200_glue_binary(int op, NDArray *a, NDArray *b);\n'
+        'NDArray *nb200_glue_reduce(NDArray *array, int *axis, NDArray *(*operation)(NDArray *, NDArray *));\n'
+        'NDArray *nb200_glue_argminmax(NDArray *op, int axis, bool keepdims, bool is_argmax);\n'
+        'NDArray *nb200_glue_matmul(NDArray *a, NDArray *b);\n')
+
+# file -> [(regex matching the function's definition line incl. "{", code inserted after it)]
+PATCHES = {
+    "src/ndmath/arithmetics.c": [
+        (r"^NDArray_Add_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_ADD"),
+        (r"^NDArray_Subtract_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_SUB"),
+        (r"^NDArray_Multiply_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_MUL"),
+        (r"^NDArray_Divide_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_DIV"),
+        (r"^NDArray_Mod_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_MOD"),
+        (r"^NDArray_Pow_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_POW"),
+    ],
+    "src/ndarray.c": [(r"^reduce\(NDArray \*array, int \*axis, NDArray \*\(\*operation\)\(NDArray \*, NDArray \*\)\) \{", "REDUCE")],
+    "src/ndmath/calculation.c": [(r"^NDArray_ArgMinMaxCommon\(NDArray \*op, int axis, bool keepdims, bool is_argmax\) \{", "ARG")],
+    "src/ndmath/linalg.c": [(r"^NDArray_Matmul\(NDArray \*a, NDArray \*b\) \{", "MATMUL")],
+}
+
+
+def snippet(kind):
+    if kind.startswith("NB200_"):
+        return f"    {{ NDArray *nb200_r = nb200_glue_binary({kind}, a, b); if (nb200_r != NULL) return nb200_r; }}\n"
+    if kind == "REDUCE":
+        return "    { NDArray *nb200_r = nb200_glue_reduce(array, axis, operation); if (nb200_r != NULL) return nb200_r; }\n"
+    if kind == "ARG":
+        return ("    if (NDArray_DEVICE(op) == NDARRAY_DEVICE_GPU) return nb200_glue_argminmax(op, axis, keepdims, is_argmax);\n")
+    if kind == "MATMUL":
+        return "    { NDArray *nb200_r = nb200_glue_matmul(a, b); if (nb200_r != NULL) return nb200_r; }\n"
+    raise ValueError(kind)
+
+
+def main(ref, out):
+    for rel, plist in PATCHES.items():
+        text = open(os.path.join(ref, rel)).read()
+        lines = text.splitlines(keepends=True)
+        done = 0
+        res = []
+        # declarations go after the last #include of the file header block
+        last_inc = max(i for i, l in enumerate(lines[:80]) if l.startswith("#include"))
+        for i, l in enumerate(lines):
+            res.append(l)
+            if i == last_inc:
+                res.append(DECL)
+            for rx, kind in plist:
+                if re.match(rx, l):
+                    res.append(snippet(kind))
+                    done += 1
+        if done != len(plist):
+            raise SystemExit(f"{rel}: applied {done} of {len(plist)} patches (anchor not found)")
+        dst = os.path.join(out, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        open(dst, "w").write("".join(res))
+        print(f"patched {rel}: {done} insertion(s)")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2])

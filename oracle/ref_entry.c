@@ -311,6 +311,19 @@ long ref_matmul(const float *a, const float *b, int M, int K, int N, float *out,
     unwrap(na); unwrap(nb);
     return n;
 }
+/* NDArray_Matmul on N-D operands: the reference rejects ndim > 2 ("Stack of matrices not allowed", linalg.c:240-243);
+ * the Level-1 patched host (oracle/build_dropin_n1.sh) serves stacks with one batched launch. */
+long ref_matmul_nd(const float *a, const int *ashape, int andim, const float *b, const int *bshape, int bndim,
+                   float *out, long out_cap, double *seconds) {
+    NDArray *na = wrap(a, ashape, andim), *nb = wrap(b, bshape, bndim);
+    double t0 = now_s();
+    NDArray *r = NDArray_Matmul(na, nb);
+    double t1 = now_s();
+    if (seconds) *seconds = t1 - t0;
+    long n = take(r, out, out_cap);
+    unwrap(na); unwrap(nb);
+    return n;
+}
 /* NDArray_Dot (linalg.c:354-393): general dispatcher (1-D.1-D, 2-D.2-D, N-D.1-D). */
 long ref_dot(const float *a, const int *ashape, int andim, const float *b, const int *bshape, int bndim,
              float *out, long out_cap, double *seconds) {
