@@ -202,46 +202,52 @@ __global__ void __launch_bounds__(COL_BX *BY) reduce_cols_kernel(float *__restri
     const int64_t o = blockIdx.y / S;
     const int s = (int)(blockIdx.y % S);
     const int64_t col = ((int64_t)blockIdx.x * COL_BX + tx) * VEC;
-    const int64_t l0 = (int64_t)s * seg;
-    const int64_t l1 = (l0 + seg < len) ? l0 + seg : len;
+    // The S segments are INTERLEAVED along the axis in chunks of BY*CU rows: block (x, s) takes chunks s, s+S, s+2S, ...
+    // so at any time the whole grid sweeps one contiguous band of rows (DRAM-page friendly) instead of S far-apart bands.
+    constexpr int CU = 8;                  // rows in flight per thread
+    constexpr int CHUNK = BY * CU;
+    (void)seg;
     float acc[VEC];
     bool started = false;
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = Red<OP>::identity();
     if (col < inner) {
         const float *base = in + o * len * inner + col;
-        int64_t l = l0 + ty;
-        constexpr int CU = 8;   // rows in flight per thread
-        for (; l + (CU - 1) * BY < l1; l += CU * BY) {
-            float x[CU][VEC];
+        const int64_t nchunks = (len + CHUNK - 1) / CHUNK;
+        for (int64_t ch = s; ch < nchunks; ch += S) {
+            const int64_t l = ch * CHUNK + ty;
+            if (l + (int64_t)(CU - 1) * BY < len) {
+                float x[CU][VEC];
 #pragma unroll
-            for (int u = 0; u < CU; u++) {
-                const float *p = base + (l + (int64_t)u * BY) * inner;
-                if (VEC == 4) {
-                    float4 t = ldg_stream(reinterpret_cast<const float4 *>(p));
-                    x[u][0] = t.x; x[u][1 % VEC] = t.y; x[u][2 % VEC] = t.z; x[u][3 % VEC] = t.w;
-                } else {
-                    x[u][0] = ldg_stream(p);
+                for (int u = 0; u < CU; u++) {
+                    const float *p = base + (l + (int64_t)u * BY) * inner;
+                    if (VEC == 4) {
+                        float4 t = ldg_stream(reinterpret_cast<const float4 *>(p));
+                        x[u][0] = t.x; x[u][1 % VEC] = t.y; x[u][2 % VEC] = t.z; x[u][3 % VEC] = t.w;
+                    } else {
+                        x[u][0] = ldg_stream(p);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CU; u++)
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        if (SEQ) acc[v] = started ? Red<OP>::seq(acc[v], x[u][v]) : x[u][v];
+                        else acc[v] = Red<OP>::comb(acc[v], x[u][v]);
+                        if (SEQ && v == VEC - 1) started = true;
+                    }
+            } else {
+                for (int64_t ll = l; ll < len; ll += BY) {
+                    const float *p = base + ll * inner;
+#pragma unroll
+                    for (int v = 0; v < VEC; v++) {
+                        float xv = p[v];
+                        if (SEQ) acc[v] = started ? Red<OP>::seq(acc[v], xv) : xv;
+                        else acc[v] = Red<OP>::comb(acc[v], xv);
+                    }
+                    if (SEQ) started = true;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < CU; u++)
-#pragma unroll
-                for (int v = 0; v < VEC; v++) {
-                    if (SEQ) acc[v] = started ? Red<OP>::seq(acc[v], x[u][v]) : x[u][v];
-                    else acc[v] = Red<OP>::comb(acc[v], x[u][v]);
-                    if (SEQ && v == VEC - 1) started = true;
-                }
-        }
-        for (; l < l1; l += BY) {
-            const float *p = base + l * inner;
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                float xv = p[v];
-                if (SEQ) acc[v] = started ? Red<OP>::seq(acc[v], xv) : xv;
-                else acc[v] = Red<OP>::comb(acc[v], xv);
-            }
-            if (SEQ) started = true;
         }
     }
     if (BY > 1) {
@@ -587,8 +593,17 @@ static int reduce_cols(float *out, const float *in, int64_t outer, int64_t len, 
         if (vec) return launch_cols<OP, 4, 8, false>(out, in, outer, len, inner, 1, len);
         return launch_cols<OP, 1, 8, false>(out, in, outer, len, inner, 1, len);
     }
+    {   // chunks of 64 rows are dealt round-robin to the S segments: pick the smallest S with the same makespan
+        const int64_t nchunks = (len + 63) / 64;
+        if (S > nchunks) S = (int)nchunks;
+        const int64_t span = (nchunks + S - 1) / S;
+        while (S > 1 && (nchunks + (S - 1) - 1) / (S - 1) == span) S--;
+    }
+    if (S <= 1) {
+        if (vec) return launch_cols<OP, 4, 8, false>(out, in, outer, len, inner, 1, len);
+        return launch_cols<OP, 1, 8, false>(out, in, outer, len, inner, 1, len);
+    }
     int64_t seg = (len + S - 1) / S;
-    S = (int)((len + seg - 1) / seg);  // no empty segments
     int rc = ensure_scratch(outer * S * inner * (int64_t)sizeof(float));
     if (rc != NB200_OK) return rc;
     float *partials = static_cast<float *>(ctx().scratch);

@@ -1,0 +1,41 @@
+"""Small-shape pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck).
+Shapes are ragged on purpose (non-multiples of the vector width / tile sizes, unaligned views)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpower_b200 as nb
+
+nd, A = nb.nd, nb.NDArray.array
+r = np.random.default_rng(0)
+a = A(r.random((37, 53), dtype=np.float32)).gpu()
+b = A(r.random((37, 53), dtype=np.float32)).gpu()
+row = A(r.random(53, dtype=np.float32)).gpu()
+col = A(r.random((37, 1), dtype=np.float32)).gpu()
+for op in ("add", "sub", "mul", "div", "mod", "pow", "maximum", "minimum", "arctan2", "equal", "less"):
+    nd.binary(op, a, b).toArray(); nd.binary(op, a, row).toArray(); nd.binary(op, a, col).toArray(); nd.binary(op, a, 2.0).toArray()
+(a[1] + a[2]).toArray()                      # 4-byte aligned views
+nd.mul_add(a, row, col).toArray(); nd.mul_add(a, b, b).toArray()
+x4 = A(r.random((3, 1, 5, 7), dtype=np.float32)).gpu(); y4 = A(r.random((4, 1, 7), dtype=np.float32)).gpu()
+nd.add(x4, y4).toArray()                     # generic N-D path
+for op in ("exp", "log", "sin", "sqrt", "rsqrt", "sinc", "sign", "rint", "degrees"):
+    nd.unary(op, a).toArray()
+nd.clip(a, 0.2, 0.8).toArray(); nd.round(a, 2).toArray()
+big = A(r.random(100003, dtype=np.float32)).gpu()
+for op in ("sum", "prod", "min", "max"):
+    nd.reduce(op, big); nd.reduce(op, a, 0).toArray(); nd.reduce(op, a, 1).toArray()
+t3 = A(r.random((5, 70, 9), dtype=np.float32)).gpu()
+for ax in (0, 1, 2):
+    nd.sum(t3, ax).toArray(); nd.sum(t3, ax, order=nb.ORDER_SEQUENTIAL).toArray(); nd.argmax(t3, ax).toArray(); nd.argmin(t3, ax).toArray()
+tall = A(r.random((3000, 5), dtype=np.float32)).gpu(); nd.sum(tall, 0).toArray()
+wide = A(r.random((3, 70001), dtype=np.float32)).gpu(); nd.sum(wide, 1).toArray(); nd.argmax(wide, 1).toArray()
+nd.argmax(big); nd.argmin(big)
+m1, m2 = A(r.random((300, 136), dtype=np.float32)).gpu(), A(r.random((136, 200), dtype=np.float32)).gpu()
+nd.matmul(m1, m2).toArray(); nd.matmul(m1, m2, nb.TF32X1).toArray()            # tcgen05 path, ragged tiles
+nd.matmul(A(r.random((3, 130, 64), dtype=np.float32)).gpu(), A(r.random((3, 64, 260), dtype=np.float32)).gpu()).toArray()
+nd.matmul(A(r.random((5, 7), dtype=np.float32)).gpu(), A(r.random((7, 3), dtype=np.float32)).gpu()).toArray()   # SIMT path
+nd.dot(m1, A(r.random(136, dtype=np.float32)).gpu()).toArray()
+print("sanitizer targets done;", nb.lib().nb200_launch_count(), "launches")
