@@ -5,6 +5,7 @@
 //   compute stream : lo-split + tcgen05 GEMM per row block  (waits on the block's H2D event)
 //   copy-out stream: C row blocks                           D2H (overlaps the next blocks' H2D: PCIe is full duplex)
 #include "common.cuh"
+#include <cstdlib>
 
 namespace nb200 {
 namespace {
@@ -75,7 +76,8 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
         NB_CUDA(cudaStreamSynchronize(c.stream));
         return NB200_OK;
     }
-    const bool x3 = precision == NB200_GEMM_TF32X3;
+    // lo parts come from the pre-pass (B once, A per row block) unless NB200_GEMM_INKERNEL=1 selects the in-kernel split
+    const bool x3 = precision == NB200_GEMM_TF32X3 && getenv("NB200_GEMM_INKERNEL") == nullptr;
     if (x3) {
         if ((rc = ensure_gemm_ws((M * K + K * N) * 4 + 256)) != NB200_OK) return rc;
         P.dAlo = static_cast<float *>(c.gemm_ws);

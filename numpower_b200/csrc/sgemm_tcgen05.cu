@@ -33,8 +33,12 @@
 namespace nb200 {
 
 // ------------------------------------------------------------------ configuration
-template <int CG_, int BN_, int PASSES_>
+template <int CG_, int BN_, int PASSES_, bool INK_ = false>
 struct GemmCfg {
+    // INK (TF32x3 only): the lo parts are computed INSIDE the kernel by four converter warps (smem raw tile ->
+    // a_lo / b_lo smem tiles) instead of by the split pre-pass: TMA moves only the raw operands (half the L2->SM
+    // bytes) and the 8 B/element pre-pass traffic disappears.
+    static constexpr bool INK = INK_;
     static constexpr int CG = CG_;                       // CTAs cooperating on one MMA (cta_group)
     static constexpr int BN = BN_;                       // tile columns (per CTA pair when CG == 2)
     static constexpr int PASSES = PASSES_;               // 1 = TF32x1, 3 = TF32x3
@@ -59,8 +63,10 @@ struct GemmCfg {
     static constexpr int KB_PER_CHUNK = KC / BK;
     static constexpr int TMEM_COLS = CHUNKED ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
     static_assert(!CHUNKED || BN == 128, "chunked TF32x3 uses 128-column tiles (4 x 128 TMEM columns)");
-    static constexpr int THREADS = 192;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int THREADS = INK_ ? 320 : 192;     // + 4 converter warps
+    static constexpr int TMA_BYTES = INK_ ? (A_BYTES + B_BYTES) : STAGE_BYTES;   // bytes the TMA lands per stage per CTA
+    static_assert(!INK_ || PASSES_ == 3, "in-kernel split only exists for TF32x3");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/;
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
@@ -104,7 +110,7 @@ __device__ __forceinline__ uint32_t map_to_leader(uint32_t addr) {
 }
 // arrive on the barrier at the same offset in the leader CTA of the pair
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(map_to_leader(bar)) : "memory");
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_leader(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -257,6 +263,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t cross_empty_bar = bar_base + 8u * (2 * STAGES + 4);
     const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * STAGES + 5);
+    auto conv_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 6 + s); };   // INK: lo parts of stage s ready (leader's copy is the one waited on)
     // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
     auto a_smem = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + part * Cfg::A_BYTES; };
     auto b_smem = [&](int s, int part) { return smem_base + s * Cfg::STAGE_BYTES + NPART * Cfg::A_BYTES + part * Cfg::B_BYTES; };
@@ -271,12 +278,13 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA_hi);
         tma_prefetch_desc(&tmB_hi);
-        if (PASSES == 3) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+        if (PASSES == 3 && !Cfg::INK) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
         mbar_init(cross_empty_bar, 4 * CG);
+        if (Cfg::INK) for (int s = 0; s < STAGES; s++) mbar_init(conv_bar(s), 4 * CG);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<CG>(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -301,15 +309,24 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.debug, 0x100u + stage);
-                    if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES * CG);
                     const int k0 = kb * BK;
-                    tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
-                    if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
+                    if constexpr (Cfg::INK) {
+                        // raw operands only, signalled on THIS CTA's full barrier (its converter warps wait on it)
+                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::TMA_BYTES);
+                        tma_load_3d<1>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
 #pragma unroll
-                    for (int j = 0; j < Cfg::BN_CTA / 32; j++) {
-                        tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
-                        if (PASSES == 3)
-                            tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * 4096, col0 + j * 32, k0, bb);
+                        for (int j = 0; j < Cfg::BN_CTA / 32; j++)
+                            tma_load_3d<1>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
+                    } else {
+                        if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES * CG);
+                        tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
+                        if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
+#pragma unroll
+                        for (int j = 0; j < Cfg::BN_CTA / 32; j++) {
+                            tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
+                            if (PASSES == 3)
+                                tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * 4096, col0 + j * 32, k0, bb);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -353,7 +370,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         const uint32_t d_main = tmem_base + (uint32_t)(acc * BN);
                         const int kb1 = kb0 + Cfg::KB_PER_CHUNK < num_kb ? kb0 + Cfg::KB_PER_CHUNK : num_kb;
                         for (int kb = kb0; kb < kb1; kb++) {
-                            mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                            if (Cfg::INK) mbar_wait(conv_bar(stage), phase, p.debug, 0x600u + stage);
+                            else mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
                             tc_fence_after();
                             if (elect_one()) {
                                 // a_lo.b_hi and a_hi.b_lo -> cross accumulator (whole K); a_hi.b_hi -> this chunk's accumulator
@@ -387,7 +405,43 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 }
             }
         }
-    } else {
+    } else if (Cfg::INK && warp >= 6) {
+        // ===================== lo-part converters (warps 6..9, TF32x3 in-kernel split) =====================
+        // a_lo = rna_tf32(a - trunc_tf32(a)) element for element: the swizzled layout of the raw tile carries over
+        // unchanged because the lo tile sits at the same offset modulo 1024 B.
+        const int ct = threadIdx.x - 192;   // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        auto lo_of = [](float a) {
+            const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a - hi));
+            return __uint_as_float(r);
+        };
+        auto convert = [&](uint32_t src, uint32_t dst, int bytes) {
+#pragma unroll 4
+            for (int off = ct * 16; off < bytes; off += 128 * 16) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + off));
+                v.x = lo_of(v.x); v.y = lo_of(v.y); v.z = lo_of(v.z); v.w = lo_of(v.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+        };
+        for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait(full_bar(stage), phase, p.debug, 0x700u + stage);
+                convert(a_smem(stage, 0), a_smem(stage, 1), Cfg::A_BYTES);
+                convert(b_smem(stage, 0), b_smem(stage, 1), Cfg::B_BYTES);
+                fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(conv_bar(stage));
+                    else mbar_arrive_local(conv_bar(stage));
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 2 && warp < 6) {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
         int acc = 0;
@@ -612,7 +666,7 @@ static int launch_gemm(const GemmArgs &g) {
     if ((rc = make_map(&mb_hi, g.B, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB)) != NB200_OK) return rc;
     ma_lo = ma_hi;
     mb_lo = mb_hi;
-    if (Cfg::PASSES == 3) {
+    if (Cfg::PASSES == 3 && !Cfg::INK) {
         if ((rc = make_map(&ma_lo, g.A_lo, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA)) != NB200_OK) return rc;
         if ((rc = make_map(&mb_lo, g.B_lo, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB)) != NB200_OK) return rc;
     }
@@ -685,6 +739,10 @@ static int dispatch_cfg(const GemmArgs &g) {
     int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
     int bn = v ? (v & 0xFF) * 2 : (PASSES == 3 ? 128 : (g.N > 128 ? 256 : 128));   // encoded as BN/2
     if constexpr (PASSES == 3) {
+        if (g.A_lo == nullptr) {   // in-kernel split (default): no lo arrays exist
+            if (cg == 2) return launch_gemm<GemmCfg<2, 128, 3, true>>(g);
+            return launch_gemm<GemmCfg<1, 128, 3, true>>(g);
+        }
         if (cg == 2) return launch_gemm<GemmCfg<2, 128, 3>>(g);
         return launch_gemm<GemmCfg<1, 128, 3>>(g);
     } else {
@@ -718,7 +776,16 @@ static int gemm_impl(GemmArgs g, int precision) {
         return NB200_OK;
     }
     if (precision == NB200_GEMM_TF32X1) return dispatch_cfg<1>(g);
-    // ---- TF32x3: lo-part pre-pass into the context workspace, batch processed in chunks
+    // Measured on B200 (profiles/r1_summary.md §4): producing the lo parts INSIDE the kernel (GemmCfg::INK, four converter
+    // warps) halves TMA traffic but the extra LDS/STS contends with the tensor core's operand reads for shared-memory
+    // bandwidth: 0.98 ms vs 0.53 ms at 4096^3.  The HBM-roofline pre-pass is therefore the default; NB200_GEMM_INKERNEL=1
+    // selects the in-kernel variant for experiments.
+    static const bool inkernel = getenv("NB200_GEMM_INKERNEL") != nullptr;
+    if (inkernel) {
+        g.A_lo = g.B_lo = nullptr;
+        return dispatch_cfg<3>(g);
+    }
+    // ---- TF32x3 with the lo-part pre-pass into the context workspace, batch processed in chunks
     int64_t chunk = g.batch;
     const int64_t budget = (int64_t)4 << 30;  // at most 4 GiB of workspace per chunk
     if (g.batch > 1) {
