@@ -221,6 +221,15 @@ class nd:
     def max(a, axis=None): return nd.reduce("max", a, axis)
 
     @staticmethod
+    def mean(a, axis=None):
+        """nd::mean (numpower.c:2642-2688): no axis -> (float) sum / numElements; axis -> reduce(sum) then a
+        float division by the axis length (NDArray_Divide_Float by a 0-dim scalar)."""
+        a = nd._a(a)
+        if axis is None:
+            return float(np.float32(nd.sum(a)) / np.float32(a.size))
+        return nd.sum(a, axis) / float(a.shape[int(axis)])
+
+    @staticmethod
     def _arg(a, axis, keepdims, is_max):
         a = nd._a(a)
         r = NDArray(L.check_ptr(L.lib().NB_NDArray_ArgMinMaxCommon(a._h, 128 if axis is None else int(axis), int(keepdims), int(is_max))))

@@ -559,3 +559,13 @@ def test_config5_batched_matmul_slice_properties(nb):
     lhs = torch.bmm(a.double().sum(1, keepdim=True), b.double()).squeeze(1)   # (batch, n) fp64 checker on the GPU
     rhs = c.double().sum(1)
     assert float(((lhs - rhs).abs().amax(1) / lhs.abs().amax(1)).max()) <= RTOL
+
+
+def test_mean_composition(nb):
+    """nd::mean = sum / n (numpower.c:2642-2688), composed from the same kernels."""
+    x = _set_p2((300, 40), 5)
+    A = nb.NDArray.array(x).gpu()
+    assert nb.nd.mean(A) == float(np.float32(ORACLE.reduce_full("sum", x)) / np.float32(x.size))
+    for axis in (0, 1):
+        exp = ORACLE.binary("div", oracle.port.reduce_axis("sum", x, axis), np.float32(x.shape[axis]))
+        np.testing.assert_array_equal(nb.nd.mean(A, axis).toArray(), exp)
