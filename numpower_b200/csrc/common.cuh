@@ -66,9 +66,17 @@ int gemm_presplit(float *C, const float *A, const float *A_lo, const float *B, c
         if (_r != NB200_OK) return _r;              \
     } while (0)
 
-// ---- streaming 128-bit global access ------------------------------------------------
-// Inputs of the elementwise / reduction kernels are touched exactly once: read through
-// the non-coherent path without allocating in L1, store with the streaming policy.
+// ---- 128-bit global access ---------------------------------------------------------------------------
+// Measured on B200 (scripts/probes/copy_probe.cu -> profiles/r1_copy_probe.log, and bench.py before/after):
+//  * read+write streaming kernels (elementwise): default-policy ld.global.nc / st.global with ONE tile per CTA reach
+//    6.25-6.6 TB/s; the "streaming" hints (L1::no_allocate loads + st.global.cs, persistent grid) stop at 5.7 TB/s.
+//  * read-only streaming kernels (reductions, argmax, gemv): the L1::no_allocate loads are the faster ones
+//    (sum over 2^28: 6.13 vs 5.97 TB/s; row sums of 8192^2: 5.87 vs 4.80 TB/s).
+__device__ __forceinline__ float4 ld_ew(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ float ld_ew(const float *p) { return __ldg(p); }
+__device__ __forceinline__ void st_ew(float4 *p, const float4 &v) { *p = v; }
+__device__ __forceinline__ void st_ew(float *p, float v) { *p = v; }
+
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     float4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -79,13 +87,6 @@ __device__ __forceinline__ float ldg_stream(const float *p) {
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
-}
-__device__ __forceinline__ void stg_stream(float4 *p, const float4 &v) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void stg_stream(float *p, float v) {
-    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -161,16 +161,16 @@ __global__ void __launch_bounds__(EW_THREADS) ew_flat_vec(float *__restrict__ ou
         for (int u = 0; u < EW_UNROLL; u++) {
             int64_t i = base + (int64_t)u * EW_THREADS + threadIdx.x;
             if (i < n4) {
-                if (NIN > 0) va[u] = ldg_stream(a4 + i);
+                if (NIN > 0) va[u] = ld_ew(a4 + i);
                 else va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (NIN > 1) vb[u] = ldg_stream(b4 + i);
-                if (NIN > 2) vc[u] = ldg_stream(c4 + i);
+                if (NIN > 1) vb[u] = ld_ew(b4 + i);
+                if (NIN > 2) vc[u] = ld_ew(c4 + i);
             }
         }
 #pragma unroll
         for (int u = 0; u < EW_UNROLL; u++) {
             int64_t i = base + (int64_t)u * EW_THREADS + threadIdx.x;
-            if (i < n4) stg_stream(o4 + i, apply4(f, va[u], NIN > 1 ? vb[u] : va[u], NIN > 2 ? vc[u] : va[u]));
+            if (i < n4) st_ew(o4 + i, apply4(f, va[u], NIN > 1 ? vb[u] : va[u], NIN > 2 ? vc[u] : va[u]));
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(EW_THREADS) ew_bcast2d(float *__restrict__ out
                             constexpr int dummy = 0;
                             (void)dummy;
                             const int slot = popc3(SMASK & ((1 << k) - 1));
-                            if (VEC == 4) v[slot][u] = ldg_stream(reinterpret_cast<const float4 *>(o.p + r * o.rs + col));
-                            else v[slot][u].x = ldg_stream(o.p + r * o.rs + col);
+                            if (VEC == 4) v[slot][u] = ld_ew(reinterpret_cast<const float4 *>(o.p + r * o.rs + col));
+                            else v[slot][u].x = ld_ew(o.p + r * o.rs + col);
                         } else if (o.cm == 0) {
                             sc[k][u] = __ldg(o.p + r * o.rs);
                         }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(EW_THREADS) ew_bcast2d(float *__restrict__ out
                         else if (ops[k].cm == 1) arg[k] = hoist[k];
                         else arg[k] = make_float4(sc[k][u], sc[k][u], sc[k][u], sc[k][u]);
                     }
-                    if (VEC == 4) stg_stream(reinterpret_cast<float4 *>(out + r * Ccols + col), apply4(f, arg[0], arg[1], arg[2]));
+                    if (VEC == 4) st_ew(reinterpret_cast<float4 *>(out + r * Ccols + col), apply4(f, arg[0], arg[1], arg[2]));
                     else out[r * Ccols + col] = f(arg[0].x, arg[1].x, arg[2].x);
                 }
             }
@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(EW_THREADS) ew_nd(float *__restrict__ out, con
 // ------------------------------------------------------------------ host-side planning
 static inline int grid_for(int64_t work_items, int64_t per_block) {
     int64_t blocks = (work_items + per_block - 1) / per_block;
-    int64_t cap = (int64_t)ctx().num_sms * 16;  // 8 resident 256-thread CTAs/SM, 2 waves
+    // one tile per CTA (non-persistent): measured faster than a capped grid-stride grid for streaming kernels
+    // (profiles/r1_copy_probe.log); the grid-stride loop only matters beyond 2^31-1 tiles
+    int64_t cap = 0x7FFFFFFF;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;

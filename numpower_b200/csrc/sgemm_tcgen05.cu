@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
         float *lo = second ? lo1 : lo0;
         const int64_t n = second ? n1 : n0;
         if ((j << 2) + 4 <= n) {
-            float4 a = ldg_stream(reinterpret_cast<const float4 *>(in) + j), l;
+            float4 a = ld_ew(reinterpret_cast<const float4 *>(in) + j), l;
             l.x = lo_part(a.x); l.y = lo_part(a.y); l.z = lo_part(a.z); l.w = lo_part(a.w);
             reinterpret_cast<float4 *>(lo)[j] = l;
         } else {
@@ -707,9 +707,8 @@ static int launch_gemm(const GemmArgs &g) {
 static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1) {
     int64_t groups = ((n0 + 3) >> 2) + ((n1 + 3) >> 2);
     if (groups == 0) return NB200_OK;
-    int64_t blocks = (groups + 255) / 256;
-    int64_t cap = (int64_t)ctx().num_sms * 16;
-    if (blocks > cap) blocks = cap;
+    int64_t blocks = (groups + 255) / 256;   // one 4-element group per thread, non-persistent (see common.cuh)
+    if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
     split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1);
     NB_LAUNCH_CHECK();
     return NB200_OK;
