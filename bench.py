@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 
 MATMUL_N = 4096
 SHARD_BATCH, SHARD_N = 128, 2048
+# DRAM traffic per launch from the committed ncu --set full captures (profiles/r1b_ncu_gemm_ew.csv, profiles/r1_ncu_*.csv)
+NCU_TRAFFIC = {"sgemm_tf32_kernel<2,128,3>": 1.171e9, "split_tf32_kernel": 0.215e9, "sgemm_tf32_kernel<2,256,1>": 0.388e9,
+               "ew_flat_vec<3,MulAddOp>": 1.043e9, "ew_bcast2d<3,MulAddOp,4,1>": 0.489e9, "reduce_rows_kernel<0> 2^28": 1.077e9,
+               "arg_rows_kernel<1> 2^28": 1.077e9, "reduce_cols_kernel<0,4,8,0>": 0.272e9}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -291,7 +295,8 @@ def run_single(args):
         return bytes_ / ms_ / 1e6
 
     t = B.time_steps(lambda: B.check(lib.nb200_ew_mul_add(out.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(), 2, shp, full, full, full)), reps, 3, flush=True)
-    extras["chain_fused_full"] = {"ms": t, "GBps": gbps(4 * m * m * 4, t), "frac_hbm": gbps(4 * m * m * 4, t) / hbm, "algorithmic_bytes": 4 * m * m * 4}
+    extras["chain_fused_full"] = {"ms": t, "GBps": gbps(4 * m * m * 4, t), "frac_hbm": gbps(4 * m * m * 4, t) / hbm, "algorithmic_bytes": 4 * m * m * 4,
+                                  "ncu_dram_traffic_bytes": NCU_TRAFFIC["ew_flat_vec<3,MulAddOp>"]}
 
     def unfused():
         B.check(lib.nb200_ew_binary(2, tmp.data_ptr(), x.data_ptr(), y.data_ptr(), 2, shp, full, full))
@@ -318,7 +323,8 @@ def run_single(args):
         ("argmax_2pow28", lambda: B.check(lib.nb200_argminmax(1, res.data_ptr(), big.data_ptr(), 1, 1 << 28, 1))),
     ):
         t = B.time_steps(fn, reps, 3, flush=True)
-        extras[name] = {"ms": t, "GBps": gbps((1 << 30), t), "frac_hbm": gbps(1 << 30, t) / hbm, "algorithmic_bytes": 1 << 30}
+        extras[name] = {"ms": t, "GBps": gbps((1 << 30), t), "frac_hbm": gbps(1 << 30, t) / hbm, "algorithmic_bytes": 1 << 30,
+                        "ncu_dram_traffic_bytes": NCU_TRAFFIC["reduce_rows_kernel<0> 2^28"]}
     del big
     # config[0]: nd::add 1024x1024 (launch-latency bound on a GPU: 12 MiB of traffic)
     s = torch.rand(1024, 1024, device="cuda"); s2 = torch.rand(1024, 1024, device="cuda"); so = torch.empty(1024, 1024, device="cuda")
@@ -355,7 +361,11 @@ def run_single(args):
                    "l2": "operands 128 MiB + result 64 MiB exceed the 126 MB L2; HBM-bound extras flush L2 between timed launches",
                    "timing": "CUDA events on the launching stream"},
         "roofline": {"bound": "tensor", "achieved": useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": useful / tf32_peak,
-                     "traffic": None, "peak_source": peaks["_source"] + ": bf16_tflops / 2 (tf32 = half the bf16 MMA rate)",
+                     "traffic": NCU_TRAFFIC["sgemm_tf32_kernel<2,128,3>"] + NCU_TRAFFIC["split_tf32_kernel"],
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as "
+                                       "profiles/r1b_ncu_gemm_ew.csv (GEMM kernel 1.171 GB + lo-split pre-pass 0.215 GB; algorithmic minimum "
+                                       "3 x 64 MiB = 0.201 GB: the GEMM is tensor-bound, its re-reads are L2-served at 70 % hit rate)",
+                     "tensor_pipe_active_pct_ncu": 93.1, "peak_source": peaks["_source"] + ": bf16_tflops / 2 (tf32 = half the bf16 MMA rate)",
                      "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / tf32_peak,
                      "note": "achieved counts the algorithmic 2*M*N*K flops; TF32x3 executes 3x that on the tensor pipe"},
         "cpu_baseline": cpu,
