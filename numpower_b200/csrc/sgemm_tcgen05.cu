@@ -78,6 +78,7 @@ struct GemmParams {
     int tiles_m, tiles_n;      // tiles per matrix
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
+    int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
 };
 
@@ -496,35 +497,89 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
                     tc_fence_after();
                     const uint32_t t_main = tmem_base + lane_sel + (uint32_t)(acc * BN);
+                    if (!last) {
+                        // total (+)= this chunk, round-to-nearest, all in TMEM
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; c++) {
-                        uint32_t m[32], x[32];
-                        tmem_ld_32x32(t_main + (uint32_t)(c * 32), m);
-                        if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
-                        tmem_ld_wait();
-                        if (!first) {
+                        for (int c = 0; c < BN / 32; c++) {
+                            uint32_t m[32], x[32];
+                            tmem_ld_32x32(t_main + (uint32_t)(c * 32), m);
+                            if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
+                            tmem_ld_wait();
+                            if (!first) {
 #pragma unroll
-                            for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
+                                for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
+                            }
+                            tmem_st_32x32(t_total + (uint32_t)(c * 32), m);
                         }
-                        if (last) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
+                            else mbar_arrive_local(tempty_bar(acc));
+                        }
+                    } else if (!p.early_cross) {
+                        // last chunk, single pass: C = (total + chunk) + cross; the next tile's MMAs wait for all of it
+#pragma unroll 1
+                        for (int c = 0; c < BN / 32; c++) {
+                            uint32_t m[32], x[32];
+                            tmem_ld_32x32(t_main + (uint32_t)(c * 32), m);
+                            if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
+                            tmem_ld_wait();
+                            if (!first) {
+#pragma unroll
+                                for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
+                            }
                             tmem_ld_32x32(t_cross + (uint32_t)(c * 32), x);
                             tmem_ld_wait();
 #pragma unroll
                             for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(m[q]), __uint_as_float(x[q])));
                             store_row(c, m);
-                        } else {
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) { mbar_arrive_leader(tempty_bar(acc)); mbar_arrive_leader(cross_empty_bar); }
+                            else { mbar_arrive_local(tempty_bar(acc)); mbar_arrive_local(cross_empty_bar); }
+                        }
+                    } else {
+                        // last chunk.  Pass 1 (TMEM only, a few hundred cycles): total (+)= cross terms, then hand the cross
+                        // accumulator back so the NEXT tile's MMAs start while this tile is still being written out.
+#pragma unroll 1
+                        for (int c = 0; c < BN / 32; c++) {
+                            uint32_t m[32], x[32];
+                            tmem_ld_32x32(t_cross + (uint32_t)(c * 32), m);
+                            if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
+                            tmem_ld_wait();
+                            if (!first) {
+#pragma unroll
+                                for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
+                            }
                             tmem_st_32x32(t_total + (uint32_t)(c * 32), m);
                         }
-                    }
-                    if (!last) tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
-                        else mbar_arrive_local(tempty_bar(acc));
-                        if (last) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
                             if (CG == 2) mbar_arrive_leader(cross_empty_bar);
                             else mbar_arrive_local(cross_empty_bar);
+                        }
+                        // Pass 2: C = total + last chunk -> global memory
+#pragma unroll 1
+                        for (int c = 0; c < BN / 32; c++) {
+                            uint32_t m[32], x[32];
+                            tmem_ld_32x32(t_main + (uint32_t)(c * 32), m);
+                            tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
+                            store_row(c, m);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
+                            else mbar_arrive_local(tempty_bar(acc));
                         }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -675,6 +730,8 @@ static int launch_gemm(const GemmArgs &g) {
     p.tiles_m = (int)((g.M + Cfg::BM * Cfg::CG - 1) / (Cfg::BM * Cfg::CG));
     p.tiles_n = (int)((g.N + Cfg::BN - 1) / Cfg::BN);
     p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * g.batch;
+    static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
+    p.early_cross = early;
     p.a_batched = g.sA != 0;
     p.b_batched = g.sB != 0;
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
