@@ -229,6 +229,33 @@ class nd:
             return float(np.float32(nd.sum(a)) / np.float32(a.size))
         return nd.sum(a, axis) / float(a.shape[int(axis)])
 
+    # ---- statistics composed from the hot-path kernels (src/ndmath/statistics.c:87-153; SURVEY §8 f, N4).  The
+    # reference's GPU branches throw ("NDArray::std not available for GPU."); the op sequence is the CPU one.
+    @staticmethod
+    def variance(a) -> float:
+        """NDArray_Variance (statistics.c:110-124): mean(|a - mean|^2), the square taken with pow(.., 2)."""
+        a = nd._a(a)
+        m = np.float32(nd.sum(a)) / np.float32(a.size)
+        p = nd.pow(nd.unary("abs", a - float(m)), 2.0)
+        return float(np.float32(nd.sum(p)) / np.float32(p.size))
+
+    @staticmethod
+    def std(a) -> float:
+        """NDArray_Std (statistics.c:86-101): sqrt(sum((a - mean)^2) / n)."""
+        a = nd._a(a)
+        m = np.float32(nd.sum(a)) / np.float32(a.size)
+        d = a - float(m)
+        return float(np.sqrt(np.float32(nd.sum(nd.pow(d, 2.0))) / np.float32(a.size), dtype=np.float32))
+
+    @staticmethod
+    def average(a, weights=None) -> float:
+        """NDArray_Average (statistics.c:133-153): sum(a*w) / sum(w), or the mean without weights."""
+        a = nd._a(a)
+        if weights is None:
+            return float(np.float32(nd.sum(a)) / np.float32(a.size))
+        w = nd._a(weights)
+        return float(np.float32(nd.sum(a * w)) / np.float32(nd.sum(w)))
+
     @staticmethod
     def _arg(a, axis, keepdims, is_max):
         a = nd._a(a)

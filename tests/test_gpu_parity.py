@@ -569,3 +569,19 @@ def test_mean_composition(nb):
     for axis in (0, 1):
         exp = ORACLE.binary("div", oracle.port.reduce_axis("sum", x, axis), np.float32(x.shape[axis]))
         np.testing.assert_array_equal(nb.nd.mean(A, axis).toArray(), exp)
+
+
+def test_statistics_compositions(nb):
+    """variance / std / average = the reference's own compositions of hot-path ops (statistics.c:87-153)."""
+    x = _set_p2((200, 50), 6)
+    w = (_rng(7).integers(1, 9, size=(200, 50)).astype(np.float32) / 8)
+    A, W = nb.NDArray.array(x).gpu(), nb.NDArray.array(w).gpu()
+    n = np.float32(x.size)
+    mean = np.float32(ORACLE.reduce_full("sum", x)) / n
+    var_ref = np.float32(ORACLE.reduce_full("sum", ORACLE.binary("pow", ORACLE.unary("abs", ORACLE.binary("sub", x, mean)), np.float32(2.0)))) / n
+    assert nb.nd.variance(A) == pytest.approx(float(var_ref), rel=RTOL)
+    std_ref = np.sqrt(np.float32(ORACLE.reduce_full("sum", ORACLE.binary("pow", ORACLE.binary("sub", x, mean), np.float32(2.0)))) / n, dtype=np.float32)
+    assert nb.nd.std(A) == pytest.approx(float(std_ref), rel=RTOL)
+    avg_ref = np.float32(ORACLE.reduce_full("sum", ORACLE.binary("mul", x, w))) / np.float32(ORACLE.reduce_full("sum", w))
+    assert nb.nd.average(A, W) == pytest.approx(float(avg_ref), rel=RTOL)
+    assert nb.nd.average(A) == float(mean)
