@@ -17,6 +17,7 @@
 //   unaries          src/ndmath/double_math.c (line per op in include/nb200.h)
 #include "common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace nb200 {
 
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(EW_THREADS) ew_flat_scalar(float *__restrict__
 // SMASK (compile time) marks the operands that STREAM from HBM (one fresh 128-bit load per
 // row); the others are broadcast operands that cost no bandwidth: a row vector (row stride 0)
 // is loaded ONCE per thread and kept in registers, a column vector is one broadcast scalar
-// load per row.  Only streaming operands occupy the U-deep register pipeline, so a kernel with
-// a single streaming input keeps 8 rows (8 x 16 B per thread) in flight instead of 4.
+// load per row.  Only streaming operands occupy the U-deep register pipeline (U = 4 rows, 62 registers,
+// 4 resident CTAs per SM).
 struct Operand2D {
     const float *p;
     int64_t rs;
@@ -203,11 +204,10 @@ struct Operand2D {
 };
 __host__ __device__ constexpr int popc3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
 
-template <int NIN, class F, int VEC, int SMASK>
-__global__ void __launch_bounds__(EW_THREADS) ew_bcast2d(float *__restrict__ out, Operand2D A, Operand2D B, Operand2D Cc,
+template <int NIN, class F, int VEC, int SMASK, int U>
+__global__ void __launch_bounds__(EW_THREADS, U == 8 ? 2 : 4) ew_bcast2d(float *__restrict__ out, Operand2D A, Operand2D B, Operand2D Cc,
                                                          int64_t R, int64_t Ccols, int bx, F f) {
     constexpr int NS = popc3(SMASK);
-    constexpr int U = NS <= 1 ? 8 : 4;
     const int tx = threadIdx.x % bx, ty = threadIdx.x / bx, by = EW_THREADS / bx;
     const int64_t CG = Ccols / VEC;  // column groups
     const Operand2D ops[3] = {A, B, Cc};
@@ -391,7 +391,8 @@ static int launch_strided(float *out, const float *const *in, int ndim, const in
         for (int k = NIN; k < 3; k++) ops[k] = ops[0];
         if (ok) {
             const int V = vec ? 4 : 1;
-            const int U = popc3(smask) <= 1 ? 8 : 4;
+            static const int u_env = getenv("NB200_BCAST_U") ? atoi(getenv("NB200_BCAST_U")) : 0;
+            const int U = u_env == 8 ? 8 : 4;   // measured (scripts/bcast_probe.py): 4 rows x 4 CTAs/SM = 0.0874 ms vs 8 rows x 2 CTAs/SM = 0.0970 ms on config 3b
             int64_t CG = C / V;
             int bx = 1;
             while (bx < EW_THREADS && bx < CG) bx <<= 1;
@@ -404,8 +405,9 @@ static int launch_strided(float *out, const float *const *in, int ndim, const in
             dim3 grid((unsigned)gx, (unsigned)gy);
 #define NB_BCAST_LAUNCH(MASK)                                                                                          \
     case MASK:                                                                                                         \
-        if (vec) ew_bcast2d<NIN, F, 4, MASK><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);     \
-        else ew_bcast2d<NIN, F, 1, MASK><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);         \
+        if (vec && U == 8) ew_bcast2d<NIN, F, 4, MASK, 8><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f); \
+        else if (vec) ew_bcast2d<NIN, F, 4, MASK, 4><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);   \
+        else ew_bcast2d<NIN, F, 1, MASK, 4><<<grid, EW_THREADS, 0, s>>>(out, ops[0], ops[1], ops[2], R, C, bx, f);         \
         break;
             switch (smask) {
                 NB_BCAST_LAUNCH(0)
