@@ -325,6 +325,14 @@ def run_single(args):
         t = B.time_steps(fn, reps, 3, flush=True)
         extras[name] = {"ms": t, "GBps": gbps((1 << 30), t), "frac_hbm": gbps(1 << 30, t) / hbm, "algorithmic_bytes": 1 << 30,
                         "ncu_dram_traffic_bytes": NCU_TRAFFIC["reduce_rows_kernel<0> 2^28"]}
+    # the 8192^2 axis sums are only 256 MiB (~45 us): launch + fold latency is visible, so also the 1 GiB shape
+    ax2 = torch.empty(32768, device="cuda")
+    for name, fn in (
+        ("sum_axis0_32768x8192", lambda: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), big.data_ptr(), 1, 32768, 8192, 0))),
+        ("sum_axis1_32768x8192", lambda: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), big.data_ptr(), 32768, 8192, 1, 0))),
+    ):
+        t = B.time_steps(fn, reps, 3, flush=True)
+        extras[name] = {"ms": t, "GBps": gbps((1 << 30), t), "frac_hbm": gbps(1 << 30, t) / hbm, "algorithmic_bytes": 1 << 30}
     del big
     # config[0]: nd::add 1024x1024 (launch-latency bound on a GPU: 12 MiB of traffic)
     s = torch.rand(1024, 1024, device="cuda"); s2 = torch.rand(1024, 1024, device="cuda"); so = torch.empty(1024, 1024, device="cuda")

@@ -579,8 +579,17 @@ static int reduce_cols(float *out, const float *in, int64_t outer, int64_t len, 
     // TREE: BY = 8 threads split the axis inside a block; S segments across blocks if the grid is small
     const int VEC = vec ? 4 : 1;
     int64_t blocks = ((inner + COL_BX * VEC - 1) / (COL_BX * VEC)) * outer;
-    // one balanced wave: 8 resident 256-thread CTAs per SM, so split the axis into floor(slots / tiles) segments
-    int64_t target = (int64_t)ctx().num_sms * 8;
+    // one balanced wave: as many CTAs as are actually co-resident (occupancy query: registers limit the 256-thread
+    // CTAs to fewer than 8 per SM; sizing for 8 left a 0.3-wave tail, ncu "Waves Per SM 1.30"), so split the axis
+    // into floor(slots / tiles) segments
+    static int bps_vec = 0, bps_scalar = 0;
+    if (!bps_vec) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_vec, reduce_cols_kernel<OP, 4, 8, false>, COL_BX * 8, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_scalar, reduce_cols_kernel<OP, 1, 8, false>, COL_BX * 8, 0);
+        if (bps_vec < 1) bps_vec = 1;
+        if (bps_scalar < 1) bps_scalar = 1;
+    }
+    int64_t target = (int64_t)ctx().num_sms * (vec ? bps_vec : bps_scalar);
     int S = 1;
     if (blocks * 2 <= target && len >= 64) {
         int64_t want = target / blocks, maxS = len / 32;
