@@ -95,6 +95,7 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
         NB_CUDA(cudaEventRecord(P.ev_in[i], P.s_in));
     }
     NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_b, 0));
+    if (x3 && (rc = gemm_reset_nonfinite()) != NB200_OK) return rc;
     if (x3 && (rc = gemm_split_operand(P.dB, P.dBlo, K * N)) != NB200_OK) return rc;
     for (int64_t i = 0; i < nblk; i++) {
         const int64_t r0 = i * rb, rows = (r0 + rb <= M) ? rb : M - r0;

@@ -29,6 +29,7 @@
 // Flops: 2*M*N*K useful (x3 executes 6*M*N*K on the tensor pipe).
 #include "common.cuh"
 #include <cuda.h>
+#include <math_constants.h>
 
 namespace nb200 {
 
@@ -79,6 +80,7 @@ struct GemmParams {
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
     int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
+    const int *nonfinite;      // TF32x3: set by the split pre-pass when an operand holds +-inf (see lo_part)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
 };
 
@@ -364,6 +366,10 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 } else {
                     // cross-term accumulator of the previous tile must have been read out
                     mbar_wait(cross_empty_bar, tile_phase ^ 1u, p.debug, 0x500u);
+                    // An operand with +-inf: a_hi = inf times b_lo = 0 would turn cblas_sgemm's inf into NaN.  The pre-pass
+                    // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
+                    // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
+                    const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite)) ? 1 : 0;
                     const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
                     for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
                         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
@@ -379,12 +385,12 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
                                     umma_tf32<CG>(d_cross, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                    const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
                                     umma_tf32<CG>(d_cross, da, db, idesc, 1u);
                                 }
@@ -608,12 +614,15 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ float lo_part(float a) {
+// +-inf has no finite remainder (inf - inf = NaN): its lo part is 0 and the call is flagged, see the MMA issuer.
+__device__ __forceinline__ float lo_part(float a, int *nonfinite) {
+    if (fabsf(a) == CUDART_INF_F) { *nonfinite = 1; return 0.f; }
     const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
     return to_tf32(a - hi);
 }
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
-                                                         const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1) {
+                                                         const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
+                                                         int *__restrict__ nonfinite) {
     const int64_t g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;   // 4-element groups (spans are padded to a multiple of 4)
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= g0;
@@ -623,10 +632,10 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
         const int64_t n = second ? n1 : n0;
         if ((j << 2) + 4 <= n) {
             float4 a = ld_ew(reinterpret_cast<const float4 *>(in) + j), l;
-            l.x = lo_part(a.x); l.y = lo_part(a.y); l.z = lo_part(a.z); l.w = lo_part(a.w);
+            l.x = lo_part(a.x, nonfinite); l.y = lo_part(a.y, nonfinite); l.z = lo_part(a.z, nonfinite); l.w = lo_part(a.w, nonfinite);
             reinterpret_cast<float4 *>(lo)[j] = l;
         } else {
-            for (int64_t e = j << 2; e < n; e++) lo[e] = lo_part(in[e]);
+            for (int64_t e = j << 2; e < n; e++) lo[e] = lo_part(in[e], nonfinite);
         }
     }
 }
@@ -732,6 +741,7 @@ static int launch_gemm(const GemmArgs &g) {
     p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * g.batch;
     static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
     p.early_cross = early;
+    p.nonfinite = nonfinite_flag();
     p.a_batched = g.sA != 0;
     p.b_batched = g.sB != 0;
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
@@ -761,12 +771,18 @@ static int launch_gemm(const GemmArgs &g) {
     return NB200_OK;
 }
 
+// device flag "an operand of the current TF32x3 call contains +-inf" (reset by gemm_reset_nonfinite before each call)
+static int *nonfinite_flag() { return reinterpret_cast<int *>(ctx().dev_result) + 8; }
+int gemm_reset_nonfinite() {
+    NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, sizeof(int), ctx().stream));
+    return NB200_OK;
+}
 static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1) {
     int64_t groups = ((n0 + 3) >> 2) + ((n1 + 3) >> 2);
     if (groups == 0) return NB200_OK;
     int64_t blocks = (groups + 255) / 256;   // one 4-element group per thread, non-persistent (see common.cuh)
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1);
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag());
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }

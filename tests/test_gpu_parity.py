@@ -585,3 +585,29 @@ def test_statistics_compositions(nb):
     avg_ref = np.float32(ORACLE.reduce_full("sum", ORACLE.binary("mul", x, w))) / np.float32(ORACLE.reduce_full("sum", w))
     assert nb.nd.average(A, W) == pytest.approx(float(avg_ref), rel=RTOL)
     assert nb.nd.average(A) == float(mean)
+
+
+def test_matmul_inf_nan_propagation_and_dynamic_range(nb):
+    """IEEE special values must propagate like cblas_sgemm (inf stays inf, inf*0 and NaN give NaN), and rows with a wide
+    dynamic range keep fp32-class accuracy (TF32 has the full 8-bit exponent)."""
+    r = _rng(41)
+    a = r.random((256, 128), dtype=np.float32)
+    b = r.random((128, 256), dtype=np.float32)
+    a[3, 7] = np.inf
+    a[100, 5] = -np.inf
+    b[9, 200] = np.nan
+    b[7, 50] = 0.0          # inf * 0 -> NaN in row 3, column 50
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    exp = ORACLE.matmul(a, b)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    np.testing.assert_array_equal(np.isposinf(got), np.isposinf(exp))
+    np.testing.assert_array_equal(np.isneginf(got), np.isneginf(exp))
+    fin = np.isfinite(exp)
+    assert rel_err(got[fin], exp[fin]).max() <= 2e-3      # a flagged call runs at TF32x1 accuracy (documented)
+    # wide dynamic range, finite: every row scaled by 2^k, k in [-60, 60]
+    a2 = (r.random((256, 160), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(256, 1))).astype(np.float32)).astype(np.float32)
+    b2 = (r.random((160, 128), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(1, 128))).astype(np.float32)).astype(np.float32)
+    got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu()).toArray()
+    exp2 = ORACLE.matmul(a2, b2)
+    ok = np.isfinite(exp2) & (np.abs(exp2) > 1e-30)
+    assert rel_err(got2[ok], exp2[ok]).max() <= RTOL
