@@ -614,6 +614,12 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// device flag "an operand of the current TF32x3 call contains +-inf" (reset by gemm_reset_nonfinite before each call)
+static int *nonfinite_flag() { return reinterpret_cast<int *>(ctx().dev_result) + 8; }
+int gemm_reset_nonfinite() {
+    NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, sizeof(int), ctx().stream));
+    return NB200_OK;
+}
 // +-inf has no finite remainder (inf - inf = NaN): its lo part is 0 and the call is flagged, see the MMA issuer.
 __device__ __forceinline__ float lo_part(float a, int *nonfinite) {
     if (fabsf(a) == CUDART_INF_F) { *nonfinite = 1; return 0.f; }
@@ -771,12 +777,6 @@ static int launch_gemm(const GemmArgs &g) {
     return NB200_OK;
 }
 
-// device flag "an operand of the current TF32x3 call contains +-inf" (reset by gemm_reset_nonfinite before each call)
-static int *nonfinite_flag() { return reinterpret_cast<int *>(ctx().dev_result) + 8; }
-int gemm_reset_nonfinite() {
-    NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, sizeof(int), ctx().stream));
-    return NB200_OK;
-}
 static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1) {
     int64_t groups = ((n0 + 3) >> 2) + ((n1 + 3) >> 2);
     if (groups == 0) return NB200_OK;
@@ -865,6 +865,7 @@ static int gemm_impl(GemmArgs g, int precision) {
         if (per > 0 && per * chunk > budget) chunk = budget / per;
         if (chunk < 1) chunk = 1;
     }
+    { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }   // once per call: shared operands are split once
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t sa = span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K), sb = span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N);
