@@ -30,12 +30,17 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <math_constants.h>
+#include <cuda_bf16.h>
 
 namespace nb200 {
 
 // ------------------------------------------------------------------ configuration
-template <int CG_, int BN_, int PASSES_, bool INK_ = false>
+template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false>
 struct GemmCfg {
+    // BF16 (x3 only): operands are pre-split into two bfloat16 arrays each and multiplied with kind::f16 MMAs at twice
+    // the TF32 rate; everything else (ring, chunked accumulation, epilogue) is shared with TF32x3.
+    static constexpr bool BF16 = BF16_;
+    static constexpr int ESZ = BF16_ ? 2 : 4;            // operand element size in shared memory
     // INK (TF32x3 only): the lo parts are computed INSIDE the kernel by four converter warps (smem raw tile ->
     // a_lo / b_lo smem tiles) instead of by the split pre-pass: TMA moves only the raw operands (half the L2->SM
     // bytes) and the 8 B/element pre-pass traffic disappears.
@@ -44,12 +49,17 @@ struct GemmCfg {
     static constexpr int BN = BN_;                       // tile columns (per CTA pair when CG == 2)
     static constexpr int PASSES = PASSES_;               // 1 = TF32x1, 3 = TF32x3
     static constexpr int BM = 128;                       // rows per CTA (TMEM lanes)
-    static constexpr int BK = 32;                        // fp32 per stage along K = 128 B
-    static constexpr int UMMA_K = 8;                     // tf32: 32 B of K per instruction
+    static constexpr int BK = 128 / ESZ;                 // elements per stage along K = one 128-byte swizzle row
+    static constexpr int UMMA_K = 32 / ESZ;              // 32 B of K per instruction (tf32: 8, bf16: 16)
+    // MN-major B tile = BN_CTA/B_CHUNK_N chunks of [BK k-rows x 128 B]
+    static constexpr int B_CHUNK_N = 128 / ESZ;          // n-columns per chunk
+    static constexpr int B_CHUNK_BYTES = BK * 128;       // = LBO
+    static constexpr int B_SBO = BF16_ ? 1024 : 512;     // 16-bit: 8-row swizzle atoms; 32-bit: 4-row atoms (32-byte-atom layout)
+    static constexpr int B_KSTEP = UMMA_K * 128;         // start-address advance per MMA k-step
     static constexpr int BN_CTA = BN / CG;               // B columns staged by each CTA
     static constexpr int NPART = PASSES == 3 ? 2 : 1;    // hi (+ lo)
-    static constexpr int A_BYTES = BM * BK * 4;          // 16 KiB
-    static constexpr int B_BYTES = BN_CTA * BK * 4;
+    static constexpr int A_BYTES = BM * 128;             // 16 KiB
+    static constexpr int B_BYTES = BN_CTA * BK * ESZ;
     static constexpr int STAGE_BYTES = NPART * (A_BYTES + B_BYTES);
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;
     static constexpr int ACC_STAGES = 2;
@@ -60,13 +70,14 @@ struct GemmCfg {
     // (tcgen05.ld / FADD / tcgen05.st), and (b) keeps the 2^-11-smaller cross terms in their own
     // accumulator.  TMEM columns: [0,BN) [BN,2BN) main ring | [2BN,3BN) cross terms | [3BN,4BN) running total.
     static constexpr bool CHUNKED = PASSES == 3;
-    static constexpr int KC = 256;                       // K elements per accumulation chunk
+    static constexpr int KC = BF16_ ? 512 : 256;         // K elements per accumulation chunk (32 MMA k-steps either way)
     static constexpr int KB_PER_CHUNK = KC / BK;
     static constexpr int TMEM_COLS = CHUNKED ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
     static_assert(!CHUNKED || BN == 128, "chunked TF32x3 uses 128-column tiles (4 x 128 TMEM columns)");
     static constexpr int THREADS = INK_ ? 320 : 192;     // + 4 converter warps
     static constexpr int TMA_BYTES = INK_ ? (A_BYTES + B_BYTES) : STAGE_BYTES;   // bytes the TMA lands per stage per CTA
-    static_assert(!INK_ || PASSES_ == 3, "in-kernel split only exists for TF32x3");
+    static_assert(!INK_ || (PASSES_ == 3 && !BF16_), "in-kernel split only exists for TF32x3");
+    static_assert(!BF16_ || PASSES_ == 3, "bf16 operands are only used by the x3 error-compensated mode");
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/;
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -177,9 +188,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 
 // D[tmem] (+)= A[smem desc] . B[smem desc]
-template <int CG>
+template <int CG, bool BF16 = false>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (CG == 1) {
+    if constexpr (BF16 && CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (BF16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+    } else if constexpr (CG == 1) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -242,8 +263,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // Instruction descriptor (32-bit): D=f32 (bits 4-5 =1), A=B=tf32 (bits 7-9, 10-12 =2), A K-major (bit 15 =0),
 // B MN-major (bit 16 =1), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+// kind::f16 uses the same fields with A=B=bf16 (format code 1).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool bf16 = false) {
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 
@@ -325,10 +348,10 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
                         if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
 #pragma unroll
-                        for (int j = 0; j < Cfg::BN_CTA / 32; j++) {
-                            tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
+                        for (int j = 0; j < Cfg::BN_CTA / Cfg::B_CHUNK_N; j++) {
+                            tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
                             if (PASSES == 3)
-                                tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * 4096, col0 + j * 32, k0, bb);
+                                tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -338,7 +361,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM * CG, BN);
+            constexpr uint32_t idesc = make_idesc_tf32(BM * CG, BN, Cfg::BF16);
+            constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
             for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
@@ -353,8 +377,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                             for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                 const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
-                                const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                                umma_tf32<CG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                umma_tf32<CG, Cfg::BF16>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
                             umma_commit<CG>(empty_bar(stage));
                             if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
@@ -385,20 +409,20 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                                    umma_tf32<CG>(d_cross, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                    umma_tf32<CG, Cfg::BF16>(d_cross, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                                    umma_tf32<CG>(d_cross, da, db, idesc, 1u);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                    umma_tf32<CG, Cfg::BF16>(d_cross, da, db, idesc, 1u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                                    umma_tf32<CG>(d_main, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                    umma_tf32<CG, Cfg::BF16>(d_main, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                                 }
                                 umma_commit<CG>(empty_bar(stage));
                                 if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(acc));
@@ -646,6 +670,62 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
     }
 }
 
+// ------------------------------------------------------------------ BF16 split pre-pass (BF16x3)
+// a = a1 + a2 + r with a1 = rn_bf16(a), a2 = rn_bf16(a - a1) (a - a1 is exact in fp32), |r| <= 2^-18 |a|.
+// The matrices are rewritten as packed bf16 [batch*rows][ld_out] (ld_out = cols rounded up to 8 so that every row
+// starts 16-byte aligned for the TMA); 4 B read + 4 B written per element, like the TF32 pre-pass.
+struct SplitSpan {
+    const float *in;
+    __nv_bfloat16 *hi, *lo;
+    int64_t rows_per, nrows, cols, ld_in, stride_in, ld_out;   // nrows = batch * rows_per
+    int64_t gpr, groups;                                        // 4-element groups per row / in total
+    int vec;                                                    // 16-byte aligned source rows
+};
+__device__ __forceinline__ void split_bf16(float a, __nv_bfloat16 &h, __nv_bfloat16 &l, int *nonfinite) {
+    uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) << 16;
+    const uint32_t ab = __float_as_uint(a);
+    if ((hb & 0x7FFFFFFFu) == 0x7F800000u) {
+        if ((ab & 0x7FFFFFFFu) == 0x7F800000u) {   // +-inf: no finite remainder, see the MMA issuer
+            *nonfinite = 1;
+            h = __ushort_as_bfloat16((unsigned short)(hb >> 16));
+            l = __ushort_as_bfloat16((unsigned short)0);
+            return;
+        }
+        hb = ab & 0xFFFF0000u;                     // finite value that rounds up to inf in bf16: truncate instead
+    }
+    h = __ushort_as_bfloat16((unsigned short)(hb >> 16));
+    l = __float2bfloat16_rn(a - __uint_as_float(hb));
+}
+__global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, const SplitSpan s1, int *__restrict__ nonfinite) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.groups + s1.groups; i += (int64_t)gridDim.x * 256) {
+        const bool second = i >= s0.groups;
+        const SplitSpan &s = second ? s1 : s0;
+        const int64_t j = second ? i - s0.groups : i;
+        const int64_t r = j / s.gpr, c = (j - r * s.gpr) << 2;
+        const int64_t b = r / s.rows_per, rr = r - b * s.rows_per;
+        const float *src = s.in + b * s.stride_in + rr * s.ld_in + c;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s.vec && c + 4 <= s.cols) {
+            const float4 a = ld_ew(reinterpret_cast<const float4 *>(src));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+            for (int e = 0; e < 4; e++) if (c + e < s.cols) v[e] = src[e];
+        }
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) split_bf16(v[e], h[e], l[e], nonfinite);
+        // ld_out is a multiple of 8 and c of 4: 8-byte aligned stores; columns in [cols, ld_out) receive zeros
+        const int64_t o = r * s.ld_out + c;
+        uint2 hv, lv;
+        hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+        hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+        lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+        lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        *reinterpret_cast<uint2 *>(s.hi + o) = hv;
+        *reinterpret_cast<uint2 *>(s.lo + o) = lv;
+    }
+}
+
 // ------------------------------------------------------------------ SIMT fp32 GEMM (small / unaligned shapes)
 // 64x64 tile, BK = 16, 256 threads x (4x4) micro-tile, fp32 FMA, k in increasing order.
 __global__ void __launch_bounds__(256) sgemm_simt_kernel(float *__restrict__ C, const float *__restrict__ A,
@@ -705,16 +785,18 @@ static EncodeTiledFn get_encode() {
 }
 
 // 3-D map over (inner, rows, batch) of a row-major fp32 matrix stack; box = (32, box_rows, 1), 128B swizzle.
-static int make_map(CUtensorMap *map, const float *base, int64_t inner, int64_t rows, int64_t ld, int64_t batch,
-                    int64_t batch_stride, int box_rows, CUtensorMapSwizzle swizzle) {
+static int make_map(CUtensorMap *map, const void *base, int64_t inner, int64_t rows, int64_t ld, int64_t batch,
+                    int64_t batch_stride, int box_rows, CUtensorMapSwizzle swizzle, bool bf16 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error(NB200_ECUDA, "cuTensorMapEncodeTiled unavailable");
     if (batch_stride == 0 || batch < 1) { batch = 1; batch_stride = rows * ld; }
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch_stride * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+    const cuuint64_t esz = bf16 ? 2 : 4;
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)batch_stride * esz};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows, 1};   // one 128-byte swizzle row
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(NB200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -731,14 +813,16 @@ template <class Cfg>
 static int launch_gemm(const GemmArgs &g) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    const CUtensorMapSwizzle SWA = CU_TENSOR_MAP_SWIZZLE_128B, SWB = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if ((rc = make_map(&ma_hi, g.A, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA)) != NB200_OK) return rc;
-    if ((rc = make_map(&mb_hi, g.B, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB)) != NB200_OK) return rc;
+    // g.A/A_lo/B/B_lo point at packed bf16 arrays (lda/ldb/sA/sB in bf16 elements) when Cfg::BF16
+    const CUtensorMapSwizzle SWA = CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle SWB = Cfg::BF16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if ((rc = make_map(&ma_hi, g.A, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA, Cfg::BF16)) != NB200_OK) return rc;
+    if ((rc = make_map(&mb_hi, g.B, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB, Cfg::BF16)) != NB200_OK) return rc;
     ma_lo = ma_hi;
     mb_lo = mb_hi;
     if (Cfg::PASSES == 3 && !Cfg::INK) {
-        if ((rc = make_map(&ma_lo, g.A_lo, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA)) != NB200_OK) return rc;
-        if ((rc = make_map(&mb_lo, g.B_lo, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB)) != NB200_OK) return rc;
+        if ((rc = make_map(&ma_lo, g.A_lo, g.K, g.M, g.lda, g.batch, g.sA, Cfg::BM, SWA, Cfg::BF16)) != NB200_OK) return rc;
+        if ((rc = make_map(&mb_lo, g.B_lo, g.N, g.K, g.ldb, g.batch, g.sB, Cfg::BK, SWB, Cfg::BF16)) != NB200_OK) return rc;
     }
     GemmParams p;
     p.C = g.C; p.M = g.M; p.N = g.N; p.K = g.K; p.ldc = g.ldc; p.strideC = g.sC; p.batch = g.batch;
@@ -831,6 +915,68 @@ static bool tensor_path_ok(const GemmArgs &g) {
            g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
 }
 
+static inline int64_t round8(int64_t x) { return (x + 7) & ~int64_t(7); }
+static SplitSpan make_span(const float *in, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t batch, int64_t rows, int64_t cols,
+                           int64_t ld_in, int64_t stride_in) {
+    SplitSpan s;
+    s.in = in; s.hi = hi; s.lo = lo;
+    s.rows_per = rows; s.nrows = batch * rows; s.cols = cols; s.ld_in = ld_in; s.stride_in = stride_in;
+    s.ld_out = round8(cols);
+    s.gpr = s.ld_out >> 2;
+    s.groups = s.nrows * s.gpr;
+    s.vec = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (ld_in % 4 == 0) && (stride_in % 4 == 0);
+    return s;
+}
+static int launch_split_bf16(const SplitSpan &s0, const SplitSpan &s1) {
+    const int64_t groups = s0.groups + s1.groups;
+    if (groups == 0) return NB200_OK;
+    int64_t blocks = (groups + 255) / 256;
+    if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0, s1, nonfinite_flag());
+    NB_LAUNCH_CHECK();
+    return NB200_OK;
+}
+
+// BF16x3: C = a1.b1 + (a2.b1 + a1.b2) with bf16 pairs (a1, a2), (b1, b2) from the pre-pass, same chunked kernel.
+// Dropped terms (a2.b2 and the two split remainders) are each <= 2^-18 |a||b| per product and zero-mean.
+static int gemm_bf16x3(const GemmArgs &g) {
+    const int64_t lda = round8(g.K), ldb = round8(g.N);
+    const int64_t per_a = g.M * lda, per_b = g.K * ldb;          // bf16 elements per matrix
+    int64_t chunk = g.batch;
+    const int64_t budget = (int64_t)4 << 30;
+    if (g.batch > 1) {
+        const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0));
+        if (per > 0 && per * chunk > budget) chunk = budget / per;
+        if (chunk < 1) chunk = 1;
+    }
+    { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
+    for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
+        const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
+        const int64_t na = (g.sA ? nb : 1) * per_a, nbb = (g.sB ? nb : 1) * per_b;
+        int rc = ensure_gemm_ws((na + nbb) * 4 + 1024);
+        if (rc != NB200_OK) return rc;
+        __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);
+        __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
+        const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
+        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is split once
+        SplitSpan sa = make_span(a_src, a_hi, a_lo, do_a ? (g.sA ? nb : 1) : 0, g.M, g.K, g.lda, g.sA);
+        SplitSpan sb = make_span(b_src, b_hi, b_lo, do_b ? (g.sB ? nb : 1) : 0, g.K, g.N, g.ldb, g.sB);
+        if ((rc = launch_split_bf16(sa, sb)) != NB200_OK) return rc;
+        GemmArgs c = g;
+        c.batch = nb;
+        c.A = reinterpret_cast<const float *>(a_hi); c.A_lo = reinterpret_cast<const float *>(a_lo);
+        c.B = reinterpret_cast<const float *>(b_hi); c.B_lo = reinterpret_cast<const float *>(b_lo);
+        c.lda = lda; c.ldb = ldb;
+        c.sA = g.sA ? per_a : 0; c.sB = g.sB ? per_b : 0;
+        c.C = g.C + b0 * g.sC;
+        const int v = gemm_variant();
+        const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
+        rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true>>(c);
+        if (rc != NB200_OK) return rc;
+    }
+    return NB200_OK;
+}
+
 static int gemm_impl(GemmArgs g, int precision) {
     if (g.batch == 0 || g.M == 0 || g.N == 0) return NB200_OK;
     if (g.K == 0) {
@@ -839,6 +985,9 @@ static int gemm_impl(GemmArgs g, int precision) {
                 NB_CUDA(cudaMemsetAsync(g.C + b * g.sC + r * g.ldc, 0, (size_t)g.N * 4, ctx().stream));
         return NB200_OK;
     }
+    // BF16x3 repacks its operands, so it has no alignment / leading-dimension requirements of its own
+    const bool bf16_ok = g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
+    if (precision == NB200_GEMM_BF16X3 && bf16_ok && !getenv("NB200_GEMM_FORCE_SIMT")) return gemm_bf16x3(g);
     if (!tensor_path_ok(g) || getenv("NB200_GEMM_FORCE_SIMT")) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
         if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
@@ -906,7 +1055,7 @@ extern "C" int nb200_sgemm_batched(float *C, const float *A, const float *B, int
     NB_READY();
     if (!C || !A || !B || batch < 0 || M < 0 || N < 0 || K < 0 || strideA < 0 || strideB < 0 || strideC < 0)
         return set_error(NB200_EINVAL, "nb200_sgemm_batched: bad argument");
-    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3)
+    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3 && precision != NB200_GEMM_BF16X3)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, batch, M, N, K, K, N, N, strideA, strideB, strideC};
     return gemm_impl(g, precision);
@@ -918,7 +1067,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
     if (!C || !A || !B || M < 0 || N < 0 || K < 0 || lda < K || ldb < N || ldc < N)
         return set_error(NB200_EINVAL, "Shape mismatch for matmul (M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
                          (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
-    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3)
+    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3 && precision != NB200_GEMM_BF16X3)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
     return gemm_impl(g, precision);
@@ -927,7 +1076,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
 extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes) {
     if (!bytes) return set_error(NB200_EINVAL, "null argument");
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
-    int64_t per = 4 * (round4(M * K) + round4(K * N));
+    int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024 : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = (int64_t)4 << 30;
     *bytes = (total > budget && batch > 1) ? (budget / per > 0 ? (budget / per) * per : per) : total;

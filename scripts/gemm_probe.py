@@ -13,6 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
+PNAME = {0: "x3", 1: "x1", 2: "bf16x3"}
 VARIANTS = {"cg1_bn256": 384, "cg1_bn128": 320, "cg2_bn256": 640, "cg2_bn128": 576}
 
 
@@ -32,7 +33,7 @@ def child(variant: str, precision: int, sizes):
         c = torch.full((M, N), float("nan"), device="cuda")
         rc = lib.nb200_sgemm(c.data_ptr(), a.data_ptr(), b.data_ptr(), M, N, K, K, N, N, precision)
         torch.cuda.synchronize()
-        rec = {"variant": variant, "precision": "x3" if precision == 0 else "x1", "M": M, "K": K, "N": N, "rc": rc}
+        rec = {"variant": variant, "precision": PNAME[precision], "M": M, "K": K, "N": N, "rc": rc}
         if rc != 0:
             rec["error"] = lib.nb200_last_error().decode()
             res.append(rec)
@@ -62,7 +63,7 @@ def child(variant: str, precision: int, sizes):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            rec.update(ms=ms, useful_tflops=2.0 * M * N * K / ms / 1e9, pipe_tflops=(3 if precision == 0 else 1) * 2.0 * M * N * K / ms / 1e9)
+            rec.update(ms=ms, useful_tflops=2.0 * M * N * K / ms / 1e9, pipe_tflops=(1 if precision == 1 else 3) * 2.0 * M * N * K / ms / 1e9)
         res.append(rec)
         print(json.dumps(rec), flush=True)
     return res
@@ -72,6 +73,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         sizes = [(256, 256, 256), (1024, 1024, 1024), (1000, 520, 776), (4096, 4096, 4096)]
+        if int(sys.argv[3]) == 2:
+            sizes = [(256, 256, 256), (333, 77, 129), (1000, 520, 776), (1024, 1024, 1024), (2048, 2048, 2048), (4096, 4096, 4096), (8192, 8192, 8192)]
         if len(sys.argv) > 4:
             sizes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[4:]]
         child(sys.argv[2], int(sys.argv[3]), sizes)
@@ -79,7 +82,7 @@ def main():
     variants = sys.argv[1:] or list(VARIANTS)
     with open(os.path.join(OUT, "gemm_probe.jsonl"), "a") as f:
         for v in variants:
-            for prec in (1, 0):
+            for prec in [int(x) for x in os.environ.get("PROBE_PRECISIONS", "1,0").split(",")]:
                 t0 = time.time()
                 try:
                     p = subprocess.run([sys.executable, __file__, "child", v, str(prec)], capture_output=True, text=True, timeout=240)
@@ -89,7 +92,7 @@ def main():
                 for line in out.splitlines():
                     if line.startswith("{"):
                         f.write(line + "\n")
-                f.write(json.dumps({"variant": v, "precision": "x3" if prec == 0 else "x1", "exit": code, "secs": round(time.time() - t0, 1),
+                f.write(json.dumps({"variant": v, "precision": PNAME[prec], "exit": code, "secs": round(time.time() - t0, 1),
                                     "stderr_tail": err if code != 0 else ""}) + "\n")
                 f.flush()
                 print(v, prec, "exit", code, flush=True)
