@@ -4,10 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N = 1 : workload = BASELINE.json configs[1] "nd::matmul 4096x4096 fp32 (tf32 tensor cores)": one step =
-        one nd::matmul through the C-ABI (nb200_sgemm, TF32x3 parity mode).  `value` = useful TFLOP/s with
+        one nd::matmul through the C-ABI (nb200_sgemm, NB200_GEMM_AUTO = the error-compensated BF16x3 mode on
+        tcgen05, max rel. error ~1e-6; TF32x3 and TF32x1 are reported in extras).  `value` = useful TFLOP/s with
         operands resident in HBM; `e2e` = same call fed from pinned HOST buffers (H2D of A,B and D2H of C
         inside the timed region).  `extras` reports the other single-GPU configs (a*b+c 8192^2 chain,
-        sum/argmax over 2^28, axis sums) as GB/s against the measured HBM roofline, and the TF32x1 fast mode.
+        sum/argmax over 2^28, axis sums) as GB/s against the measured HBM roofline.
 N > 1 : launched by torchrun, one rank per GPU: BASELINE.json configs[4] batched matmul, the batch dimension
         sharded with no data-path collective (128 matrices of 2048^2 per rank; N = 8 is exactly
         1024 x (2048x2048)).  weak scaling; value = total useful TFLOP/s over all ranks, max-over-ranks time.
@@ -32,7 +33,10 @@ sys.path.insert(0, ROOT)
 MATMUL_N = 4096
 SHARD_BATCH, SHARD_N = 128, 2048
 # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1b_ncu_gemm_ew.csv, profiles/r1_ncu_*.csv)
-NCU_TRAFFIC = {"sgemm_tf32_kernel<2,128,3>": 1.171e9, "split_tf32_kernel": 0.215e9, "sgemm_tf32_kernel<2,256,1>": 0.388e9,
+GEMM_AUTO = 3                      # include/nb200.h NB200_GEMM_AUTO
+NCU_PIPE_ACTIVE_BF16X3 = 86.2      # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, profiles/r1d_ncu_gemm_bf16x3.csv
+NCU_TRAFFIC = {"sgemm_tf32_kernel<2,128,3,bf16>": 0.562e9, "split_bf16_flat_kernel": 0.226e9,
+               "sgemm_tf32_kernel<2,128,3>": 1.171e9, "split_tf32_kernel": 0.215e9, "sgemm_tf32_kernel<2,256,1>": 0.388e9,
                "ew_flat_vec<3,MulAddOp>": 1.043e9, "ew_bcast2d<3,MulAddOp,4,1>": 0.489e9, "reduce_rows_kernel<0> 2^28": 1.077e9,
                "arg_rows_kernel<1> 2^28": 1.077e9, "reduce_cols_kernel<0,4,8,0>": 0.272e9}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
@@ -248,10 +252,19 @@ def run_single(args):
     launches0 = lib.nb200_launch_count()
     sampler = ClockSampler(0)
     sampler.start()
-    ms = B.time_steps(lambda: mm(0), args.steps, args.warmup)
+    ms = B.time_steps(lambda: mm(GEMM_AUTO), args.steps, args.warmup)      # AUTO -> BF16x3 at K = 4096 (what nd::matmul runs)
     launches = lib.nb200_launch_count() - launches0
     launches_timed = launches * args.steps // (args.steps + args.warmup)
+    ms_x3 = B.time_steps(lambda: mm(0), args.steps, args.warmup)
     ms_x1 = B.time_steps(lambda: mm(1), args.steps, args.warmup)
+    # accuracy of each mode against an fp64 product of 64 sampled rows (reported, the parity tests assert it)
+    rows = torch.randperm(n, device="cuda", generator=g)[:64]
+    truth = a[rows].double() @ b.double()
+    mode_err = {}
+    for name, prec in (("bf16x3", 2), ("tf32x3", 0), ("tf32x1", 1)):
+        mm(prec)
+        mode_err[name] = float(((c[rows].double() - truth) / truth).abs().max())
+    del truth
 
     # ---- e2e: pinned host buffers, H2D(A,B) + matmul + D2H(C) per step, through the C-ABI
     ha, hb, hc = (torch.empty(n, n, dtype=torch.float32).pin_memory() for _ in range(3))
@@ -260,7 +273,7 @@ def run_single(args):
 
     def e2e_step():
         # the public host-operand call: uploads B, streams row blocks of A in / C out around the tcgen05 GEMM
-        B.check(lib.nb200_sgemm_host(hc.data_ptr(), ha.data_ptr(), hb.data_ptr(), n, n, n, 0))
+        B.check(lib.nb200_sgemm_host(hc.data_ptr(), ha.data_ptr(), hb.data_ptr(), n, n, n, GEMM_AUTO))
 
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = B.time_steps(e2e_step, e2e_steps, 2)
@@ -272,7 +285,7 @@ def run_single(args):
     t_d2h = B.time_steps(lambda: pin.copy_(dbuf, non_blocking=True), 5, 2)
     pcie = {"h2d_GBps": pin.numel() * 4 / t_h2d / 1e6, "d2h_GBps": pin.numel() * 4 / t_d2h / 1e6}
     del pin, dbuf
-    mm(0)                                                            # resident TF32x3 result for comparison
+    mm(GEMM_AUTO)                                                    # resident result of the same mode for comparison
     torch.cuda.synchronize()
     e2e_err = float((hc.cuda() - c).abs().max() / c.abs().max())   # the host-operand call gives the same result
 
@@ -347,14 +360,19 @@ def run_single(args):
     cb = torch.empty(SHARD_BATCH, SHARD_N, SHARD_N, device="cuda")
     sn = SHARD_N
     t = B.time_steps(lambda: B.check(lib.nb200_sgemm_batched(cb.data_ptr(), ab.data_ptr(), bb_.data_ptr(), SHARD_BATCH, sn, sn, sn,
-                                                             sn * sn, sn * sn, sn * sn, 0)), 5, 3)
+                                                             sn * sn, sn * sn, sn * sn, GEMM_AUTO)), 5, 3)
     extras["batched_matmul_128x2048sq_1gpu"] = {"ms": t, "useful_tflops": SHARD_BATCH * 2.0 * sn ** 3 / t / 1e9,
                                                 "note": "same per-GPU workload as bench.py --gpus N (weak-scaling base; sustained, power-capped)"}
     del ab, bb_, cb
-    tf32_peak = peaks["bf16_tflops"] / 2.0   # tcgen05 kind::tf32 runs at half the bf16 rate
+    bf16_peak = peaks["bf16_tflops"]         # measured cuBLAS bf16 rate: the kind::f16 MMA ceiling
+    tf32_peak = bf16_peak / 2.0              # tcgen05 kind::tf32 runs at half the bf16 rate
     useful = flops / ms / 1e9
+    extras["matmul_4096_tf32x3"] = {"ms": ms_x3, "useful_tflops": flops / ms_x3 / 1e9, "pipe_frac_tf32_peak": 3 * flops / ms_x3 / 1e9 / tf32_peak,
+                                    "tensor_pipe_active_pct_ncu": 93.1, "max_rel_err_vs_fp64": mode_err["tf32x3"],
+                                    "note": "NB200_GEMM_TF32X3: three kind::tf32 MMAs per k-step (error bound 2^-21 per product)"}
     extras["matmul_4096_tf32x1"] = {"ms": ms_x1, "useful_tflops": flops / ms_x1 / 1e9, "frac_tf32_peak": flops / ms_x1 / 1e9 / tf32_peak,
-                                    "note": "single-pass TF32 fast mode (rel err ~1e-4 vs cblas_sgemm; not the parity mode)"}
+                                    "max_rel_err_vs_fp64": mode_err["tf32x1"],
+                                    "note": "single-pass TF32 fast mode (not a parity mode)"}
     cpu = cpu_baseline_matmul(n)
     try:
         extras["cpu_reference_hbm_configs"] = cpu_baseline_extras()
@@ -362,24 +380,27 @@ def run_single(args):
         extras["cpu_reference_hbm_configs"] = {"error": str(e)}
 
     line = {
-        "metric": "nd::matmul useful TFLOP/s (fp32 in/out, TF32 tensor cores)", "value": useful, "unit": "TFLOP/s",
+        "metric": "nd::matmul useful TFLOP/s (fp32 in/out)", "value": useful, "unit": "TFLOP/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 in/out, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": f"nd::matmul {n}x{n} fp32 (BASELINE configs[1]) via nb200_sgemm, TF32x3 parity mode",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32 in/out, operands split into 2 bf16 parts, 3 MMAs, fp32 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": f"nd::matmul {n}x{n} fp32 (BASELINE configs[1]) via nb200_sgemm, NB200_GEMM_AUTO (= BF16x3 for K >= 128), "
+                               f"max rel err vs fp64 {mode_err['bf16x3']:.2e} (tolerance 1e-5)",
                    "l2": "operands 128 MiB + result 64 MiB exceed the 126 MB L2; HBM-bound extras flush L2 between timed launches",
                    "timing": "CUDA events on the launching stream"},
-        "roofline": {"bound": "tensor", "achieved": useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": useful / tf32_peak,
-                     "traffic": NCU_TRAFFIC["sgemm_tf32_kernel<2,128,3>"] + NCU_TRAFFIC["split_tf32_kernel"],
+        "roofline": {"bound": "tensor", "achieved": useful, "peak": bf16_peak, "unit": "TFLOP/s", "frac": useful / bf16_peak,
+                     "traffic": NCU_TRAFFIC["sgemm_tf32_kernel<2,128,3,bf16>"] + NCU_TRAFFIC["split_bf16_flat_kernel"],
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as "
-                                       "profiles/r1b_ncu_gemm_ew.csv (GEMM kernel 1.171 GB + lo-split pre-pass 0.215 GB; algorithmic minimum "
-                                       "3 x 64 MiB = 0.201 GB: the GEMM is tensor-bound, its re-reads are L2-served at 70 % hit rate)",
-                     "tensor_pipe_active_pct_ncu": 93.1, "peak_source": peaks["_source"] + ": bf16_tflops / 2 (tf32 = half the bf16 MMA rate)",
-                     "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / tf32_peak,
-                     "note": "achieved counts the algorithmic 2*M*N*K flops; TF32x3 executes 3x that on the tensor pipe"},
+                                       "profiles/r1d_ncu_gemm_bf16x3.csv (GEMM kernel + bf16 split pre-pass; algorithmic minimum "
+                                       "3 x 64 MiB = 0.201 GB: the GEMM is tensor-bound, its re-reads are L2-served)",
+                     "tensor_pipe_active_pct_ncu": NCU_PIPE_ACTIVE_BF16X3, "peak_source": peaks["_source"] + ": bf16_tflops (cuBLAS bf16 8192^3)",
+                     "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / bf16_peak,
+                     "note": "achieved counts the algorithmic 2*M*N*K flops of the fp32 product; the error-compensated scheme executes 3x that "
+                             "on the tensor pipe (pipe_frac), so frac is bounded by 1/3"},
         "cpu_baseline": cpu,
         "e2e": {"value": flops / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": ms_e2e, "steps": e2e_steps, "api": "nb200_sgemm_host (pinned host buffers, pipelined H2D/compute/D2H)",
-                "max_rel_diff_vs_resident": e2e_err, "pcie_measured": pcie,
+                "max_rel_diff_vs_resident": e2e_err, "pcie_measured": pcie, "mode": "NB200_GEMM_AUTO (BF16x3)",
                 "pcie_bound_ms": 2 * nbytes / pcie["h2d_GBps"] / 1e6,
                 "note": "H2D of A and B (128 MiB) is the floor: D2H of C and the GEMM overlap it"},
         "gpu_launches": int(launches_timed),
@@ -407,7 +428,7 @@ def run_multi(args):
     flops_rank = nb_ * 2.0 * n ** 3
 
     def step():
-        B.check(lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), nb_, n, n, n, n * n, n * n, n * n, 0))
+        B.check(lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), nb_, n, n, n, n * n, n * n, n * n, GEMM_AUTO))
 
     for _ in range(args.warmup):
         step()
@@ -437,7 +458,7 @@ def run_multi(args):
     def e2e_step():
         B.check(lib.nb200_copy_h2d(a.data_ptr(), ha.data_ptr(), nbytes))
         B.check(lib.nb200_copy_h2d(b.data_ptr(), hb.data_ptr(), nbytes))
-        B.check(lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), e2e_batch, n, n, n, n * n, n * n, n * n, 0))
+        B.check(lib.nb200_sgemm_batched(c.data_ptr(), a.data_ptr(), b.data_ptr(), e2e_batch, n, n, n, n * n, n * n, n * n, GEMM_AUTO))
         B.check(lib.nb200_copy_d2h(hc.data_ptr(), c.data_ptr(), nbytes))
 
     e2e_step()
@@ -452,19 +473,20 @@ def run_multi(args):
     ms_e2e = float(t2.item())
 
     if rank == 0:
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        bf16_peak = peaks["bf16_tflops_sustained"]
         total = world * flops_rank / ms / 1e9
         per_gpu = flops_rank / ms / 1e9
         line = {
-            "metric": "nd::matmul useful TFLOP/s (fp32 in/out, TF32 tensor cores)", "value": total, "unit": "TFLOP/s",
+            "metric": "nd::matmul useful TFLOP/s (fp32 in/out)", "value": total, "unit": "TFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 in/out, fp32 accumulate)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32 in/out, operands split into 2 bf16 parts, 3 MMAs, fp32 accumulate)",
+            "data": "synthetic",
             "config": {"workload": f"batched nd::matmul, {nb_} x ({n}x{n}) per GPU, batch sharded across {world} GPUs "
                                    f"(N=8 is BASELINE configs[4] 1024x(2048x2048)); resident shards, no data-path collective",
                        "l2": f"per-rank operands {2 * nb_ * n * n * 4 >> 20} MiB exceed L2", "timing": "CUDA events, max over ranks (NCCL all-reduce of the times)"},
-            "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": tf32_peak, "unit": "TFLOP/s", "frac": per_gpu / tf32_peak,
-                         "traffic": None, "peak_source": peaks["_source"] + ": bf16_tflops_sustained / 2", "pipe_executed_tflops": 3 * per_gpu,
-                         "pipe_frac": 3 * per_gpu / tf32_peak, "note": "per-GPU figures"},
+            "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": bf16_peak, "unit": "TFLOP/s", "frac": per_gpu / bf16_peak,
+                         "traffic": None, "peak_source": peaks["_source"] + ": bf16_tflops_sustained", "pipe_executed_tflops": 3 * per_gpu,
+                         "pipe_frac": 3 * per_gpu / bf16_peak, "note": "per-GPU figures; frac counts the algorithmic flops (bounded by 1/3), pipe_frac the executed ones"},
             "e2e": {"value": world * e2e_batch * 2.0 * n ** 3 / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e, "note": f"{e2e_batch} matrices per rank per step, pinned host buffers, each rank over its own PCIe link"},
             "gpu_launches": int(launches),

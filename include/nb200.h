@@ -93,8 +93,9 @@ enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
  * TF32X1: single pass, fast mode (~7e-4);
  * BF16X3: operands split into two bfloat16 parts each, three kind::f16 MMAs per k-step at
  * twice the TF32 rate; per-product error <= 3*2^-18 (zero-mean), measured max rel. error
- * ~2e-6 vs cblas_sgemm for K >= 64.  Accepts any alignment / leading dimension. */
-enum nb200_gemm_precision { NB200_GEMM_TF32X3 = 0, NB200_GEMM_TF32X1 = 1, NB200_GEMM_BF16X3 = 2 };
+ * ~2e-6 vs cblas_sgemm for K >= 64.  Accepts any alignment / leading dimension.
+ * AUTO (what nd::matmul uses): BF16X3 when K >= 128, else TF32X3. */
+enum nb200_gemm_precision { NB200_GEMM_TF32X3 = 0, NB200_GEMM_TF32X1 = 1, NB200_GEMM_BF16X3 = 2, NB200_GEMM_AUTO = 3 };
 
 /* ---- context / device -------------------------------------------------------- */
 /* Replaces the process-global cudaSetDevice of NDArray::setDevice (numpower.c:615-635). */

@@ -137,9 +137,9 @@ NDArray *nb200_glue_matmul(NDArray *a, NDArray *b) {
     oshape[nd - 2] = M;
     oshape[nd - 1] = N;
     NDArray *r = gpu_result(oshape, nd);
-    int rc = batch == 1 ? nb200_sgemm(NDArray_FDATA(r), NDArray_FDATA(a), NDArray_FDATA(b), M, N, K, K, N, N, NB200_GEMM_TF32X3)
+    int rc = batch == 1 ? nb200_sgemm(NDArray_FDATA(r), NDArray_FDATA(a), NDArray_FDATA(b), M, N, K, K, N, N, NB200_GEMM_AUTO)
                         : nb200_sgemm_batched(NDArray_FDATA(r), NDArray_FDATA(a), NDArray_FDATA(b), batch, M, N, K, M * K, K * N, M * N,
-                                              NB200_GEMM_TF32X3);
+                                              NB200_GEMM_AUTO);
     if (rc != NB200_OK || nb200_synchronize() != NB200_OK) { glue_throw("nb200_sgemm"); NDArray_FREE(r); return NULL; }
     return r;
 }

@@ -41,6 +41,9 @@ int ensure_scratch(int64_t bytes);
 int ensure_gemm_ws(int64_t bytes);
 int gemm_split_operand(const float *in, float *lo, int64_t n);
 int gemm_reset_nonfinite();
+int gemm_bf16_split(const float *in, void *hi, void *lo, int64_t rows, int64_t cols);
+int gemm_bf16_presplit(float *C, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, int64_t M, int64_t N,
+                       int64_t K, int64_t ldc);
 int gemm_presplit(float *C, const float *A, const float *A_lo, const float *B, const float *B_lo, int64_t M, int64_t N,
                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int precision);
 

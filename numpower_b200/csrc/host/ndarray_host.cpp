@@ -359,7 +359,7 @@ NB_NDArray *NB_NDArray_Dot(NB_NDArray *a, NB_NDArray *b) {
         if (rc != NB200_OK) { NB_NDArray_FREE(r); return (NB_NDArray *)fail_backend("inner"); }
         return r;
     }
-    if (a->ndim == 2 && b->ndim == 2) return NB_NDArray_Matmul(a, b, NB200_GEMM_TF32X3);
+    if (a->ndim == 2 && b->ndim == 2) return NB_NDArray_Matmul(a, b, NB200_GEMM_AUTO);
     if (a->ndim == 0 || b->ndim == 0) return NB_NDArray_Multiply_Float(a, b);
     if (a->ndim > 0 && b->ndim == 1) {
         if (a->device != NB_DEVICE_GPU) return (NB_NDArray *)fail("NDArray is on the CPU: this backend computes on the GPU only");

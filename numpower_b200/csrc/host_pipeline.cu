@@ -40,7 +40,8 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
                                 int precision) {
     NB_READY();
     if (!C_host || !A_host || !B_host || M < 0 || N < 0 || K < 0) return set_error(NB200_EINVAL, "nb200_sgemm_host: bad argument");
-    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3) return set_error(NB200_EINVAL, "unknown precision %d", precision);
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_AUTO) return set_error(NB200_EINVAL, "unknown precision %d", precision);
+    if (precision == NB200_GEMM_AUTO) precision = K >= 128 ? NB200_GEMM_BF16X3 : NB200_GEMM_TF32X3;
     if (M == 0 || N == 0) return NB200_OK;
     Pipe &P = g_pipe;
     Ctx &c = ctx();
@@ -78,6 +79,13 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
     }
     // lo parts come from the pre-pass (B once, A per row block) unless NB200_GEMM_INKERNEL=1 selects the in-kernel split
     const bool x3 = precision == NB200_GEMM_TF32X3 && getenv("NB200_GEMM_INKERNEL") == nullptr;
+    const bool b3 = precision == NB200_GEMM_BF16X3;
+    const int64_t Kp = (K + 7) & ~int64_t(7), Np = (N + 7) & ~int64_t(7);   // packed bf16 leading dimensions
+    uint16_t *ah = nullptr, *al = nullptr, *bh = nullptr, *bl = nullptr;
+    if (b3) {
+        if ((rc = ensure_gemm_ws((M * Kp + K * Np) * 4 + 1024)) != NB200_OK) return rc;
+        ah = static_cast<uint16_t *>(c.gemm_ws); al = ah + M * Kp; bh = al + M * Kp; bl = bh + K * Np;
+    }
     if (x3) {
         if ((rc = ensure_gemm_ws((M * K + K * N) * 4 + 256)) != NB200_OK) return rc;
         P.dAlo = static_cast<float *>(c.gemm_ws);
@@ -95,13 +103,17 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
         NB_CUDA(cudaEventRecord(P.ev_in[i], P.s_in));
     }
     NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_b, 0));
-    if (x3 && (rc = gemm_reset_nonfinite()) != NB200_OK) return rc;
+    if ((x3 || b3) && (rc = gemm_reset_nonfinite()) != NB200_OK) return rc;
     if (x3 && (rc = gemm_split_operand(P.dB, P.dBlo, K * N)) != NB200_OK) return rc;
+    if (b3 && (rc = gemm_bf16_split(P.dB, bh, bl, K, N)) != NB200_OK) return rc;
     for (int64_t i = 0; i < nblk; i++) {
         const int64_t r0 = i * rb, rows = (r0 + rb <= M) ? rb : M - r0;
         NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_in[i], 0));
         if (x3 && (rc = gemm_split_operand(P.dA + r0 * K, P.dAlo + r0 * K, rows * K)) != NB200_OK) return rc;
-        if ((rc = gemm_presplit(P.dC + r0 * N, P.dA + r0 * K, x3 ? P.dAlo + r0 * K : nullptr, P.dB, x3 ? P.dBlo : nullptr, rows, N, K,
+        if (b3) {
+            if ((rc = gemm_bf16_split(P.dA + r0 * K, ah + r0 * Kp, al + r0 * Kp, rows, K)) != NB200_OK) return rc;
+            if ((rc = gemm_bf16_presplit(P.dC + r0 * N, ah + r0 * Kp, al + r0 * Kp, bh, bl, rows, N, K, N)) != NB200_OK) return rc;
+        } else if ((rc = gemm_presplit(P.dC + r0 * N, P.dA + r0 * K, x3 ? P.dAlo + r0 * K : nullptr, P.dB, x3 ? P.dBlo : nullptr, rows, N, K,
                                 K, N, N, precision)) != NB200_OK)
             return rc;
         NB_CUDA(cudaEventRecord(P.ev_done[i], c.stream));

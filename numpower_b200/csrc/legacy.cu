@@ -230,7 +230,7 @@ int nb200_shim_cublasSgemm(void *, int transa, int transb, int m, int n, int k, 
         return 1;
     }
     enter();
-    int rc = nb200_sgemm(C, B, A, n, m, k, ldb, lda, ldc, NB200_GEMM_TF32X3);
+    int rc = nb200_sgemm(C, B, A, n, m, k, ldb, lda, ldc, NB200_GEMM_AUTO);
     leave(rc, "cublasSgemm (nb200_sgemm)");
     return rc == NB200_OK ? 0 : 1;
 }

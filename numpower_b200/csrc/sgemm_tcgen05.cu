@@ -680,6 +680,7 @@ struct SplitSpan {
     int64_t rows_per, nrows, cols, ld_in, stride_in, ld_out;   // nrows = batch * rows_per
     int64_t gpr, groups;                                        // 4-element groups per row / in total
     int vec;                                                    // 16-byte aligned source rows
+    int flat;                                                   // contiguous, cols % 8 == 0: output index == input index
 };
 __device__ __forceinline__ void split_bf16(float a, __nv_bfloat16 &h, __nv_bfloat16 &l, int *nonfinite) {
     uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) << 16;
@@ -695,6 +696,49 @@ __device__ __forceinline__ void split_bf16(float a, __nv_bfloat16 &h, __nv_bfloa
     }
     h = __ushort_as_bfloat16((unsigned short)(hb >> 16));
     l = __float2bfloat16_rn(a - __uint_as_float(hb));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// Contiguous operands whose row length is a multiple of 8 keep their flat indexing (ld_out == cols): 8 elements per
+// thread, 2 x 16-byte loads and 2 x 16-byte stores, one group per thread, no index arithmetic.
+__global__ void __launch_bounds__(256) split_bf16_flat_kernel(const float *__restrict__ in0, __nv_bfloat16 *__restrict__ hi0,
+                                                              __nv_bfloat16 *__restrict__ lo0, int64_t g0,
+                                                              const float *__restrict__ in1, __nv_bfloat16 *__restrict__ hi1,
+                                                              __nv_bfloat16 *__restrict__ lo1, int64_t g1,
+                                                              int *__restrict__ nonfinite) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
+        const bool second = i >= g0;
+        const int64_t j = second ? i - g0 : i;
+        const float4 *src = reinterpret_cast<const float4 *>(second ? in1 : in0) + 2 * j;
+        const float4 a = ld_ew(src), b = ld_ew(src + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t hp[4], lp[4], any = 0;
+        // fast path, two elements per cvt: h = rn_bf16(v), l = rn_bf16(v - h).  A remainder with an all-ones exponent
+        // (h overflowed to inf, or v is inf/NaN) sends the whole group through the careful per-element path.
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            hp[q] = *reinterpret_cast<const uint32_t *>(&h2);
+            const float r0 = v[2 * q] - __uint_as_float(hp[q] << 16), r1 = v[2 * q + 1] - __uint_as_float(hp[q] & 0xFFFF0000u);
+            any |= __float_as_uint(r0) | __float_as_uint(r1);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+            lp[q] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        if ((any & 0x7F800000u) == 0x7F800000u) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[2 * q], h0, l0, nonfinite);
+                split_bf16(v[2 * q + 1], h1, l1, nonfinite);
+                hp[q] = pack_bf16(h0, h1);
+                lp[q] = pack_bf16(l0, l1);
+            }
+        }
+        const uint4 hv = make_uint4(hp[0], hp[1], hp[2], hp[3]), lv = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        reinterpret_cast<uint4 *>(second ? hi1 : hi0)[j] = hv;
+        reinterpret_cast<uint4 *>(second ? lo1 : lo0)[j] = lv;
+    }
 }
 __global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, const SplitSpan s1, int *__restrict__ nonfinite) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.groups + s1.groups; i += (int64_t)gridDim.x * 256) {
@@ -717,10 +761,8 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, con
         // ld_out is a multiple of 8 and c of 4: 8-byte aligned stores; columns in [cols, ld_out) receive zeros
         const int64_t o = r * s.ld_out + c;
         uint2 hv, lv;
-        hv.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-        hv.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-        lv.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-        lv.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        hv.x = pack_bf16(h[0], h[1]); hv.y = pack_bf16(h[2], h[3]);
+        lv.x = pack_bf16(l[0], l[1]); lv.y = pack_bf16(l[2], l[3]);
         *reinterpret_cast<uint2 *>(s.hi + o) = hv;
         *reinterpret_cast<uint2 *>(s.lo + o) = lv;
     }
@@ -925,11 +967,20 @@ static SplitSpan make_span(const float *in, __nv_bfloat16 *hi, __nv_bfloat16 *lo
     s.gpr = s.ld_out >> 2;
     s.groups = s.nrows * s.gpr;
     s.vec = ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (ld_in % 4 == 0) && (stride_in % 4 == 0);
+    s.flat = s.vec && cols % 8 == 0 && ld_in == cols && (batch <= 1 || stride_in == rows * cols);
     return s;
 }
 static int launch_split_bf16(const SplitSpan &s0, const SplitSpan &s1) {
     const int64_t groups = s0.groups + s1.groups;
     if (groups == 0) return NB200_OK;
+    if ((s0.flat || s0.groups == 0) && (s1.flat || s1.groups == 0)) {
+        const int64_t g0 = s0.groups >> 1, g1 = s1.groups >> 1;   // 8-element groups
+        int64_t blocks = (g0 + g1 + 255) / 256;
+        if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+        split_bf16_flat_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0.in, s0.hi, s0.lo, g0, s1.in, s1.hi, s1.lo, g1, nonfinite_flag());
+        NB_LAUNCH_CHECK();
+        return NB200_OK;
+    }
     int64_t blocks = (groups + 255) / 256;
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
     split_bf16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0, s1, nonfinite_flag());
@@ -985,9 +1036,13 @@ static int gemm_impl(GemmArgs g, int precision) {
                 NB_CUDA(cudaMemsetAsync(g.C + b * g.sC + r * g.ldc, 0, (size_t)g.N * 4, ctx().stream));
         return NB200_OK;
     }
+    // AUTO = the fastest mode that meets 1e-5 against cblas_sgemm: BF16x3 once K is long enough for its zero-mean
+    // split remainders to average out (and for the GEMM to be compute-bound at all), TF32x3 (bound 2^-21) below.
+    if (precision == NB200_GEMM_AUTO) precision = g.K >= 128 ? NB200_GEMM_BF16X3 : NB200_GEMM_TF32X3;
     // BF16x3 repacks its operands, so it has no alignment / leading-dimension requirements of its own
     const bool bf16_ok = g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
     if (precision == NB200_GEMM_BF16X3 && bf16_ok && !getenv("NB200_GEMM_FORCE_SIMT")) return gemm_bf16x3(g);
+    if (precision == NB200_GEMM_BF16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || getenv("NB200_GEMM_FORCE_SIMT")) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
         if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
@@ -1039,6 +1094,20 @@ static int gemm_impl(GemmArgs g, int precision) {
 
 // ---- internal hooks for the host-buffer pipeline (host_pipeline.cu): split one operand / run with given lo parts
 int gemm_split_operand(const float *in, float *lo, int64_t n) { return launch_split(in, lo, n, nullptr, nullptr, 0); }
+// BF16x3 flavour of the two hooks: packed bf16 operand pairs (leading dimension = cols rounded up to 8)
+int gemm_bf16_split(const float *in, void *hi, void *lo, int64_t rows, int64_t cols) {
+    SplitSpan s = make_span(in, static_cast<__nv_bfloat16 *>(hi), static_cast<__nv_bfloat16 *>(lo), 1, rows, cols, cols, 0);
+    SplitSpan none = make_span(nullptr, nullptr, nullptr, 0, 0, 0, 0, 0);
+    return launch_split_bf16(s, none);
+}
+int gemm_bf16_presplit(float *C, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, int64_t M, int64_t N,
+                       int64_t K, int64_t ldc) {
+    GemmArgs g{C, static_cast<const float *>(a_hi), static_cast<const float *>(b_hi), static_cast<const float *>(a_lo),
+               static_cast<const float *>(b_lo), 1, M, N, K, round8(K), round8(N), ldc, 0, 0, 0};
+    const int v = gemm_variant();
+    const int cg = v ? (v >> 8) : (M > 128 ? 2 : 1);
+    return cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true>>(g) : launch_gemm<GemmCfg<1, 128, 3, false, true>>(g);
+}
 int gemm_presplit(float *C, const float *A, const float *A_lo, const float *B, const float *B_lo, int64_t M, int64_t N,
                   int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int precision) {
     GemmArgs g{C, A, B, A_lo, B_lo, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
@@ -1055,7 +1124,7 @@ extern "C" int nb200_sgemm_batched(float *C, const float *A, const float *B, int
     NB_READY();
     if (!C || !A || !B || batch < 0 || M < 0 || N < 0 || K < 0 || strideA < 0 || strideB < 0 || strideC < 0)
         return set_error(NB200_EINVAL, "nb200_sgemm_batched: bad argument");
-    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3 && precision != NB200_GEMM_BF16X3)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_AUTO)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, batch, M, N, K, K, N, N, strideA, strideB, strideC};
     return gemm_impl(g, precision);
@@ -1067,7 +1136,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
     if (!C || !A || !B || M < 0 || N < 0 || K < 0 || lda < K || ldb < N || ldc < N)
         return set_error(NB200_EINVAL, "Shape mismatch for matmul (M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
                          (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
-    if (precision != NB200_GEMM_TF32X1 && precision != NB200_GEMM_TF32X3 && precision != NB200_GEMM_BF16X3)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_AUTO)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
     return gemm_impl(g, precision);
@@ -1076,6 +1145,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
 extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes) {
     if (!bytes) return set_error(NB200_EINVAL, "null argument");
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
+    if (precision == NB200_GEMM_AUTO) precision = K >= 128 ? NB200_GEMM_BF16X3 : NB200_GEMM_TF32X3;
     int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024 : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = (int64_t)4 << 30;

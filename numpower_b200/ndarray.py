@@ -23,7 +23,7 @@ UN = {
     "positive": 31, "sign": 32, "reciprocal": 33, "rsqrt": 34, "clip": 35, "round": 36, "square": 37,
 }
 RED = {"sum": 0, "prod": 1, "min": 2, "max": 3}
-TF32X3, TF32X1 = 0, 1
+TF32X3, TF32X1, BF16X3, GEMM_AUTO = 0, 1, 2, 3   # include/nb200.h nb200_gemm_precision
 ORDER_TREE, ORDER_SEQUENTIAL = 0, 1
 
 
@@ -268,7 +268,7 @@ class nd:
     def argmin(a, axis=None, keepdims=False): return nd._arg(a, axis, keepdims, False)
 
     @staticmethod
-    def matmul(a, b, precision: int = TF32X3) -> NDArray:
+    def matmul(a, b, precision: int = GEMM_AUTO) -> NDArray:
         a, b = nd._a(a), nd._a(b)
         return NDArray(L.check_ptr(L.lib().NB_NDArray_Matmul(a._h, b._h, precision)))
 

@@ -322,6 +322,38 @@ def test_matmul_tf32x3_vs_cblas_sgemm(nb, mkn):
     _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.TF32X3, RTOL)
 
 
+@pytest.mark.parametrize("mkn", [(128, 128, 256), (256, 512, 256), (384, 1024, 640), (1000, 520, 776), (1024, 1024, 1024),
+                                 (130, 36, 260), (333, 77, 129), (257, 1001, 67), (2048, 2048, 512)])
+def test_matmul_bf16x3_vs_cblas_sgemm(nb, mkn):
+    """BF16x3 (two bf16 parts per operand, three kind::f16 MMAs): positive inputs, per-element relative error <= 1e-5
+    against cblas_sgemm, including K and N that are not multiples of 8 (the pre-pass repacks with padded rows)."""
+    m, k, n = mkn
+    r = _rng(m + k + n)
+    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.BF16X3, RTOL)
+
+
+def test_matmul_auto_picks_bf16x3_for_long_k_and_tf32x3_below(nb):
+    """AUTO (nd::matmul's default) == BF16X3 bit for bit when K >= 128, == TF32X3 bit for bit below."""
+    r = _rng(77)
+    for (m, k, n) in ((256, 512, 256), (256, 96, 256)):
+        a, b = r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32)
+        A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
+        auto = nb.nd.matmul(A, B).toArray()
+        same = nb.nd.matmul(A, B, nb.BF16X3 if k >= 128 else nb.TF32X3).toArray()
+        np.testing.assert_array_equal(auto, same)
+
+
+@pytest.mark.parametrize("prec", ["TF32X3", "BF16X3"])
+def test_matmul_signed_inputs_normwise_per_mode(nb, prec):
+    r = _rng(13)
+    a = (r.random((640, 1024), dtype=np.float32) * 2 - 1).astype(np.float32)
+    b = (r.random((1024, 512), dtype=np.float32) * 2 - 1).astype(np.float32)
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), getattr(nb, prec)).toArray()
+    exp = ORACLE.matmul(a, b)
+    scale = (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)).max()
+    assert np.abs(got.astype(np.float64) - exp).max() / scale <= RTOL
+
+
 def test_matmul_signed_inputs_normwise(nb):
     """Signed inputs: per-element relative error is ill-posed under cancellation; use the norm-wise
     metric of SURVEY §8 d: max|G-R| / max_ij (|A|.|B|)_ij <= 1e-5."""
@@ -446,7 +478,7 @@ def test_sgemm_leading_dimensions_and_ragged_edges(nb):
     abuf, bbuf = r.random((M, lda), dtype=np.float32), r.random((K, ldb), dtype=np.float32)
     cbuf = np.full((M, ldc), -1.0, np.float32)
     da, db, dc = _dev(nb, abuf), _dev(nb, bbuf), _dev(nb, cbuf)
-    for prec, tol in ((0, RTOL), (1, 2e-3)):
+    for prec, tol in ((0, RTOL), (1, 2e-3), (2, RTOL), (3, RTOL)):
         assert lib.nb200_sgemm(dc, da, db, M, N, K, lda, ldb, ldc, prec) == 0, lib.nb200_last_error()
         got = _fetch(nb, dc, (M, ldc))
         exp = ORACLE.matmul(np.ascontiguousarray(abuf[:, :K]), np.ascontiguousarray(bbuf[:, :N]))
@@ -464,10 +496,12 @@ def test_sgemm_batched_shared_operand_and_many_batches(nb):
     a, b = r.random((batch, M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
     da, db = _dev(nb, a), _dev(nb, b)
     dc = _dev(nb, np.zeros((batch, M, N), np.float32))
-    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, 0) == 0, lib.nb200_last_error()
-    got = _fetch(nb, dc, (batch, M, N))
-    for i in range(batch):
-        assert rel_err(got[i], ORACLE.matmul(a[i], b)).max() <= RTOL
+    for prec in (0, 2):
+        assert lib.nb200_copy_h2d(dc, np.zeros((batch, M, N), np.float32).ctypes.data, batch * M * N * 4) == 0
+        assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, prec) == 0, lib.nb200_last_error()
+        got = _fetch(nb, dc, (batch, M, N))
+        for i in range(batch):
+            assert rel_err(got[i], ORACLE.matmul(a[i], b)).max() <= RTOL
     for p in (da, db, dc):
         lib.nb200_free(p)
 
@@ -481,10 +515,12 @@ def test_sgemm_host_pipeline_matches_resident_call(nb, mkn):
     r = _rng(M)
     a, b = r.random((M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
     c = np.empty((M, N), np.float32)
-    assert lib.nb200_sgemm_host(c.ctypes.data, a.ctypes.data, b.ctypes.data, M, N, K, 0) == 0, lib.nb200_last_error()
-    assert rel_err(c, ORACLE.matmul(a, b)).max() <= RTOL
-    resident = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
-    assert rel_err(c, resident).max() <= 2e-6
+    for prec in (0, 2, 3):
+        c[:] = -1.0
+        assert lib.nb200_sgemm_host(c.ctypes.data, a.ctypes.data, b.ctypes.data, M, N, K, prec) == 0, lib.nb200_last_error()
+        assert rel_err(c, ORACLE.matmul(a, b)).max() <= RTOL
+        resident = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), prec).toArray()
+        assert rel_err(c, resident).max() <= 2e-6
 
 
 # --------------------------------------------------------------------- comparisons (SURVEY §8 f, N2)
@@ -597,17 +633,24 @@ def test_matmul_inf_nan_propagation_and_dynamic_range(nb):
     a[100, 5] = -np.inf
     b[9, 200] = np.nan
     b[7, 50] = 0.0          # inf * 0 -> NaN in row 3, column 50
-    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
     exp = ORACLE.matmul(a, b)
-    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
-    np.testing.assert_array_equal(np.isposinf(got), np.isposinf(exp))
-    np.testing.assert_array_equal(np.isneginf(got), np.isneginf(exp))
     fin = np.isfinite(exp)
-    assert rel_err(got[fin], exp[fin]).max() <= 2e-3      # a flagged call runs at TF32x1 accuracy (documented)
+    for prec, tol in ((nb.TF32X3, 2e-3), (nb.BF16X3, 2e-2)):   # a flagged call runs at single-pass accuracy (documented)
+        got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), prec).toArray()
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+        np.testing.assert_array_equal(np.isposinf(got), np.isposinf(exp))
+        np.testing.assert_array_equal(np.isneginf(got), np.isneginf(exp))
+        assert rel_err(got[fin], exp[fin]).max() <= tol
     # wide dynamic range, finite: every row scaled by 2^k, k in [-60, 60]
     a2 = (r.random((256, 160), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(256, 1))).astype(np.float32)).astype(np.float32)
     b2 = (r.random((160, 128), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(1, 128))).astype(np.float32)).astype(np.float32)
-    got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu()).toArray()
     exp2 = ORACLE.matmul(a2, b2)
     ok = np.isfinite(exp2) & (np.abs(exp2) > 1e-30)
-    assert rel_err(got2[ok], exp2[ok]).max() <= RTOL
+    for prec in (nb.TF32X3, nb.BF16X3):
+        got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu(), prec).toArray()
+        assert rel_err(got2[ok], exp2[ok]).max() <= RTOL
+    # values next to FLT_MAX round up to inf in bf16: the split must truncate instead (finite result expected)
+    a3 = np.full((128, 128), 3.4e38, np.float32)
+    b3 = np.full((128, 128), 2.0 ** -10, np.float32)
+    got3 = nb.nd.matmul(nb.NDArray.array(a3).gpu(), nb.NDArray.array(b3).gpu(), nb.BF16X3).toArray()
+    assert np.isfinite(got3).all() and rel_err(got3, ORACLE.matmul(a3, b3)).max() <= RTOL
