@@ -88,6 +88,7 @@ struct GemmParams {
     int64_t M, N, K, ldc, strideC;
     int64_t batch;
     int tiles_m, tiles_n;      // tiles per matrix
+    int group_m;               // tile raster: row-tiles per band (0 = plain m-fastest order)
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
     int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
@@ -270,6 +271,20 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool bf16 =
            ((uint32_t)(M >> 4) << 24);
 }
 
+// Tile order within one matrix: bands of `group_m` row-tiles, inside a band m fastest.  The tiles in flight at any time
+// (one per CTA pair) then cover ~group_m x (clusters / group_m) tiles: every A row-block and B column-block they touch is
+// shared by several of them while it is still in L2, and consecutive waves of a band reuse the band's A rows.
+__device__ __forceinline__ void tile_coords(int64_t r, const GemmParams &p, int &m_tile, int &n_tile) {
+    const int gm = p.group_m;
+    if (gm <= 0 || gm >= p.tiles_m) { m_tile = (int)(r % p.tiles_m); n_tile = (int)(r / p.tiles_m); return; }
+    const int64_t per_band = (int64_t)gm * p.tiles_n;
+    const int band = (int)(r / per_band);
+    const int within = (int)(r - band * per_band);
+    const int rows = (p.tiles_m - band * gm) < gm ? (p.tiles_m - band * gm) : gm;   // last band may be short
+    m_tile = band * gm + within % rows;
+    n_tile = within / rows;
+}
+
 // ------------------------------------------------------------------ the kernel
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
@@ -329,7 +344,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             uint32_t phase = 0;
             for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
                 const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
-                const int m_tile = (int)(r % p.tiles_m), n_tile = (int)(r / p.tiles_m);
+                int m_tile, n_tile;
+                tile_coords(r, p, m_tile, n_tile);
                 const int row0 = m_tile * BM * CG + (int)rank * BM;
                 const int col0 = n_tile * BN + (int)rank * Cfg::BN_CTA;
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
@@ -481,7 +497,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
             const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
-            const int m_tile = (int)(r % p.tiles_m), n_tile = (int)(r / p.tiles_m);
+            int m_tile, n_tile;
+                tile_coords(r, p, m_tile, n_tile);
             const int64_t row = (int64_t)m_tile * BM * CG + (int64_t)rank * BM + quarter * 32 + lane;
             const int64_t col0 = (int64_t)n_tile * BN;
             float *crow = p.C + b * p.strideC + row * p.ldc;
@@ -871,6 +888,9 @@ static int launch_gemm(const GemmArgs &g) {
     p.tiles_m = (int)((g.M + Cfg::BM * Cfg::CG - 1) / (Cfg::BM * Cfg::CG));
     p.tiles_n = (int)((g.N + Cfg::BN - 1) / Cfg::BN);
     p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * g.batch;
+    // measured on B200 (BF16x3): 4096^3 0.308 -> 0.300 ms, 8192^3 2.40 -> 2.22 ms against the plain m-fastest order
+    static const int group_m = getenv("NB200_GEMM_GROUP_M") ? atoi(getenv("NB200_GEMM_GROUP_M")) : 8;
+    p.group_m = group_m;
     static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
     p.early_cross = early;
     p.nonfinite = nonfinite_flag();
