@@ -35,8 +35,13 @@
 namespace nb200 {
 
 // ------------------------------------------------------------------ configuration
-template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false>
+template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false, bool MERGED_ = false>
 struct GemmCfg {
+    // MERGED (BF16x3, BN = 256): all three products of a chunk accumulate into ONE 256-column TMEM accumulator (2-deep
+    // ring = all 512 columns) and the running total lives in the registers of eight epilogue warps.  Twice the flops
+    // per staged byte and no cross-accumulator hand-off between tiles; costs 48 instead of 32 truncating accumulation
+    // steps per (256-long) chunk.
+    static constexpr bool MERGED = MERGED_;
     // BF16 (x3 only): operands are pre-split into two bfloat16 arrays each and multiplied with kind::f16 MMAs at twice
     // the TF32 rate; everything else (ring, chunked accumulation, epilogue) is shared with TF32x3.
     static constexpr bool BF16 = BF16_;
@@ -70,11 +75,13 @@ struct GemmCfg {
     // (tcgen05.ld / FADD / tcgen05.st), and (b) keeps the 2^-11-smaller cross terms in their own
     // accumulator.  TMEM columns: [0,BN) [BN,2BN) main ring | [2BN,3BN) cross terms | [3BN,4BN) running total.
     static constexpr bool CHUNKED = PASSES == 3;
-    static constexpr int KC = BF16_ ? 512 : 256;         // K elements per accumulation chunk (32 MMA k-steps either way)
+    static constexpr int KC = (BF16_ && !MERGED_) ? 512 : 256;   // K elements per accumulation chunk (32 MMA k-steps; MERGED: 16 x 3 products)
     static constexpr int KB_PER_CHUNK = KC / BK;
-    static constexpr int TMEM_COLS = CHUNKED ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
-    static_assert(!CHUNKED || BN == 128, "chunked TF32x3 uses 128-column tiles (4 x 128 TMEM columns)");
-    static constexpr int THREADS = INK_ ? 320 : 192;     // + 4 converter warps
+    static constexpr int TMEM_COLS = (CHUNKED && !MERGED_) ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
+    static_assert(!CHUNKED || MERGED_ || BN == 128, "chunked x3 uses 128-column tiles (4 x 128 TMEM columns)");
+    static_assert(!MERGED_ || (BF16_ && BN == 256 && PASSES_ == 3), "merged accumulation exists for BF16x3 with 256-column tiles");
+    static constexpr int EPI_WARPS = MERGED_ ? 8 : 4;
+    static constexpr int THREADS = (INK_ || MERGED_) ? 320 : 192;     // + 4 converter warps / + 4 more epilogue warps
     static constexpr int TMA_BYTES = INK_ ? (A_BYTES + B_BYTES) : STAGE_BYTES;   // bytes the TMA lands per stage per CTA
     static_assert(!INK_ || (PASSES_ == 3 && !BF16_), "in-kernel split only exists for TF32x3");
     static_assert(!BF16_ || PASSES_ == 3, "bf16 operands are only used by the x3 error-compensated mode");
@@ -235,6 +242,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -323,7 +338,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), Cfg::EPI_WARPS * CG); }
         mbar_init(cross_empty_bar, 4 * CG);
         if (Cfg::INK) for (int s = 0; s < STAGES; s++) mbar_init(conv_bar(s), 4 * CG);
         fence_barrier_init();
@@ -405,7 +420,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
                 } else {
                     // cross-term accumulator of the previous tile must have been read out
-                    mbar_wait(cross_empty_bar, tile_phase ^ 1u, p.debug, 0x500u);
+                    if constexpr (!Cfg::MERGED) mbar_wait(cross_empty_bar, tile_phase ^ 1u, p.debug, 0x500u);
                     // An operand with +-inf: a_hi = inf times b_lo = 0 would turn cblas_sgemm's inf into NaN.  The pre-pass
                     // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
                     // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
@@ -415,6 +430,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
                         tc_fence_after();
                         const uint32_t d_main = tmem_base + (uint32_t)(acc * BN);
+                        const uint32_t d_x = Cfg::MERGED ? d_main : d_cross;   // where the cross products go
                         const int kb1 = kb0 + Cfg::KB_PER_CHUNK < num_kb ? kb0 + Cfg::KB_PER_CHUNK : num_kb;
                         for (int kb = kb0; kb < kb1; kb++) {
                             if (Cfg::INK) mbar_wait(conv_bar(stage), phase, p.debug, 0x600u + stage);
@@ -426,19 +442,19 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_cross, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_cross, da, db, idesc, 1u);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, 1u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_main, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                                    umma_tf32<CG, Cfg::BF16>(d_main, da, db, idesc, (Cfg::MERGED || kb != kb0 || k != 0) ? 1u : 0u);
                                 }
                                 umma_commit<CG>(empty_bar(stage));
                                 if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(acc));
@@ -488,8 +504,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp >= 2 && warp < 6) {
-        // ===================== epilogue (warps 2..5) =====================
+    } else if (warp >= 2 && warp < 2 + Cfg::EPI_WARPS) {
+        // ===================== epilogue (warps 2..5; MERGED: 2..9, warps 6..9 take the upper 128 columns) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -518,7 +534,45 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     }
                 }
             };
-            if constexpr (!Cfg::CHUNKED) {
+            if constexpr (Cfg::MERGED) {
+                // running total of this thread's row (128 of the tile's 256 columns) in registers, chunks added round-to-nearest
+                const int half = (warp - 2) >> 2;
+                float tot[128];
+                for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
+                    const bool first = kb0 == 0, last = kb0 + Cfg::KB_PER_CHUNK >= num_kb;
+                    mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
+                    tc_fence_after();
+                    const uint32_t t_main = tmem_base + lane_sel + (uint32_t)(acc * BN + half * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {   // 16 columns at a time: 128 totals + 16 in flight fit the 168-register budget
+                        uint32_t v[16];
+                        tmem_ld_32x16(t_main + (uint32_t)(c * 16), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 16; q++)
+                            tot[c * 16 + q] = first ? __uint_as_float(v[q]) : __fadd_rn(tot[c * 16 + q], __uint_as_float(v[q]));
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
+                        else mbar_arrive_local(tempty_bar(acc));
+                    }
+                    if (last && row < p.M) {
+                        const int64_t colh = col0 + half * 128;
+                        if (vec_ok && colh + 128 <= p.N) {
+                            float4 *dst = reinterpret_cast<float4 *>(crow + colh);
+#pragma unroll
+                            for (int q = 0; q < 32; q++) dst[q] = make_float4(tot[4 * q], tot[4 * q + 1], tot[4 * q + 2], tot[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 128; q++)
+                                if (colh + q < p.N) crow[colh + q] = tot[q];
+                        }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+            } else if constexpr (!Cfg::CHUNKED) {
                 mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
                 tc_fence_after();
                 const uint32_t taddr0 = tmem_base + lane_sel + (uint32_t)(acc * BN);
@@ -1008,6 +1062,20 @@ static int launch_split_bf16(const SplitSpan &s0, const SplitSpan &s1) {
     return NB200_OK;
 }
 
+// BF16x3 tile choice for CTA pairs.  Measured on B200: the merged 256x256 tile is ~7.5 % faster per flop than 256x128
+// (8192^3: 2.06 vs 2.21 ms) but has half as many tiles, so it loses when the last wave over the 74 CTA pairs is poorly
+// filled (4096^3: 256 tiles = 3.46 waves, 0.308 vs 0.297 ms).  Pick by wave-quantisation efficiency.
+static int bf16_pair_bn(int64_t batch, int64_t M, int64_t N) {
+    if (N <= 128) return 128;
+    const int64_t clusters = ctx().num_sms / 2 > 0 ? ctx().num_sms / 2 : 1;
+    auto eff = [&](int bn) {
+        const int64_t tiles = batch * ((M + 255) / 256) * ((N + bn - 1) / bn);
+        const int64_t waves = (tiles + clusters - 1) / clusters;
+        return (double)tiles / (double)(waves * clusters);
+    };
+    return eff(256) * 1.07 > eff(128) ? 256 : 128;
+}
+
 // BF16x3: C = a1.b1 + (a2.b1 + a1.b2) with bf16 pairs (a1, a2), (b1, b2) from the pre-pass, same chunked kernel.
 // Dropped terms (a2.b2 and the two split remainders) are each <= 2^-18 |a||b| per product and zero-mean.
 static int gemm_bf16x3(const GemmArgs &g) {
@@ -1042,7 +1110,10 @@ static int gemm_bf16x3(const GemmArgs &g) {
         c.C = g.C + b0 * g.sC;
         const int v = gemm_variant();
         const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
-        rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true>>(c);
+        // NB200_GEMM_VARIANT: CG << 8 | BN / 2; default = CTA pairs with merged accumulation (BN = 256) once N > 128
+        const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? bf16_pair_bn(nb, g.M, g.N) : 128);
+        if (cg == 2 && bn == 256) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true>>(c);
+        else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true>>(c);
         if (rc != NB200_OK) return rc;
     }
     return NB200_OK;
@@ -1126,6 +1197,8 @@ int gemm_bf16_presplit(float *C, const void *a_hi, const void *a_lo, const void 
                static_cast<const float *>(b_lo), 1, M, N, K, round8(K), round8(N), ldc, 0, 0, 0};
     const int v = gemm_variant();
     const int cg = v ? (v >> 8) : (M > 128 ? 2 : 1);
+    const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? bf16_pair_bn(1, M, N) : 128);
+    if (cg == 2 && bn == 256) return launch_gemm<GemmCfg<2, 256, 3, false, true, true>>(g);
     return cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true>>(g) : launch_gemm<GemmCfg<1, 128, 3, false, true>>(g);
 }
 int gemm_presplit(float *C, const float *A, const float *A_lo, const float *B, const float *B_lo, int64_t M, int64_t N,
