@@ -96,6 +96,7 @@ struct GemmParams {
     int64_t batch;
     int tiles_m, tiles_n;      // tiles per matrix
     int group_m;               // tile raster: row-tiles per band (0 = plain m-fastest order)
+    int64_t full_items;        // MERGED: work items >= full_items are half tiles (128 of the 256 columns), two per tile
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
     int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
@@ -358,11 +359,15 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
-                const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
+                // work item -> tile (+ which half of it when the last wave is split, see launch_gemm)
+                const bool half_tile = Cfg::MERGED && t >= p.full_items;
+                const int64_t tt = half_tile ? p.full_items + ((t - p.full_items) >> 1) : t;
+                const int ncols_cta = half_tile ? Cfg::BN_CTA / 2 : Cfg::BN_CTA;   // B columns this CTA stages
+                const int64_t b = tt / tiles_per_mat, r = tt % tiles_per_mat;
                 int m_tile, n_tile;
                 tile_coords(r, p, m_tile, n_tile);
                 const int row0 = m_tile * BM * CG + (int)rank * BM;
-                const int col0 = n_tile * BN + (int)rank * Cfg::BN_CTA;
+                const int col0 = n_tile * BN + (half_tile ? (int)((t - p.full_items) & 1) * (BN / 2) : 0) + (int)rank * ncols_cta;
                 const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
                 for (int kb = 0; kb < num_kb; kb++) {
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.debug, 0x100u + stage);
@@ -375,11 +380,12 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         for (int j = 0; j < Cfg::BN_CTA / 32; j++)
                             tma_load_3d<1>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
                     } else {
-                        if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::STAGE_BYTES * CG);
+                        if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(NPART * (Cfg::A_BYTES + ncols_cta * BK * Cfg::ESZ)) * CG);
                         tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
                         if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
 #pragma unroll
                         for (int j = 0; j < Cfg::BN_CTA / Cfg::B_CHUNK_N; j++) {
+                            if (j * Cfg::B_CHUNK_N >= ncols_cta) break;
                             tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
                             if (PASSES == 3)
                                 tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
@@ -392,11 +398,13 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM * CG, BN, Cfg::BF16);
+            constexpr uint32_t idesc_full = make_idesc_tf32(BM * CG, BN, Cfg::BF16);
+            constexpr uint32_t idesc_half = make_idesc_tf32(BM * CG, BN / 2, Cfg::BF16);
             constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
             for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                const uint32_t idesc = (Cfg::MERGED && t >= p.full_items) ? idesc_half : idesc_full;
                 if constexpr (!Cfg::CHUNKED) {
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
                     tc_fence_after();
@@ -512,11 +520,13 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
-            const int64_t b = t / tiles_per_mat, r = t % tiles_per_mat;
+            const bool half_tile = Cfg::MERGED && t >= p.full_items;
+            const int64_t tt = half_tile ? p.full_items + ((t - p.full_items) >> 1) : t;
+            const int64_t b = tt / tiles_per_mat, r = tt % tiles_per_mat;
             int m_tile, n_tile;
-                tile_coords(r, p, m_tile, n_tile);
+            tile_coords(r, p, m_tile, n_tile);
             const int64_t row = (int64_t)m_tile * BM * CG + (int64_t)rank * BM + quarter * 32 + lane;
-            const int64_t col0 = (int64_t)n_tile * BN;
+            const int64_t col0 = (int64_t)n_tile * BN + (half_tile ? (int64_t)((t - p.full_items) & 1) * (BN / 2) : 0);
             float *crow = p.C + b * p.strideC + row * p.ldc;
             auto store_row = [&](int c, const uint32_t (&v)[32]) {
                 const int64_t col = col0 + c * 32;
@@ -537,20 +547,23 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             if constexpr (Cfg::MERGED) {
                 // running total of this thread's row (128 of the tile's 256 columns) in registers, chunks added round-to-nearest
                 const int half = (warp - 2) >> 2;
+                const bool idle = half_tile && half == 1;   // half tiles only have the lower 128 accumulator columns
                 float tot[128];
                 for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
                     const bool first = kb0 == 0, last = kb0 + Cfg::KB_PER_CHUNK >= num_kb;
                     mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
                     tc_fence_after();
                     const uint32_t t_main = tmem_base + lane_sel + (uint32_t)(acc * BN + half * 128);
+                    if (!idle) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {   // 16 columns at a time: 128 totals + 16 in flight fit the 168-register budget
-                        uint32_t v[16];
-                        tmem_ld_32x16(t_main + (uint32_t)(c * 16), v);
-                        tmem_ld_wait();
+                        for (int c = 0; c < 8; c++) {   // 16 columns at a time: 128 totals + 16 in flight fit the 168-register budget
+                            uint32_t v[16];
+                            tmem_ld_32x16(t_main + (uint32_t)(c * 16), v);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int q = 0; q < 16; q++)
-                            tot[c * 16 + q] = first ? __uint_as_float(v[q]) : __fadd_rn(tot[c * 16 + q], __uint_as_float(v[q]));
+                            for (int q = 0; q < 16; q++)
+                                tot[c * 16 + q] = first ? __uint_as_float(v[q]) : __fadd_rn(tot[c * 16 + q], __uint_as_float(v[q]));
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -558,7 +571,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                         if (CG == 2) mbar_arrive_leader(tempty_bar(acc));
                         else mbar_arrive_local(tempty_bar(acc));
                     }
-                    if (last && row < p.M) {
+                    if (last && row < p.M && !idle) {
                         const int64_t colh = col0 + half * 128;
                         if (vec_ok && colh + 128 <= p.N) {
                             float4 *dst = reinterpret_cast<float4 *>(crow + colh);
@@ -943,6 +956,19 @@ static int launch_gemm(const GemmArgs &g) {
     p.tiles_n = (int)((g.N + Cfg::BN - 1) / Cfg::BN);
     p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * g.batch;
     // measured on B200 (BF16x3): 4096^3 0.308 -> 0.300 ms, 8192^3 2.40 -> 2.22 ms against the plain m-fastest order
+    p.full_items = p.total_tiles;
+    if (Cfg::MERGED) {
+        // Last wave poorly filled (at most half of the CTA pairs busy): split its tiles into two 128-column halves each, so
+        // that wave keeps (nearly) every pair busy for half a tile time.  4096^3: 256 tiles on 74 pairs = 3.46 -> 3.5 waves
+        // instead of 4.
+        const int64_t pairs = ctx().num_sms / Cfg::CG;
+        const int64_t rem = p.total_tiles % pairs;
+        static const bool split_tail = getenv("NB200_GEMM_NO_SPLIT_TAIL") == nullptr;
+        if (split_tail && rem > 0 && 2 * rem <= pairs && g.N % Cfg::BN == 0) {   // (ragged last n-tile: keep whole tiles)
+            p.full_items = p.total_tiles - rem;
+            p.total_tiles = p.full_items + 2 * rem;
+        }
+    }
     static const int group_m = getenv("NB200_GEMM_GROUP_M") ? atoi(getenv("NB200_GEMM_GROUP_M")) : 8;
     p.group_m = group_m;
     static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
@@ -1070,8 +1096,10 @@ static int bf16_pair_bn(int64_t batch, int64_t M, int64_t N) {
     const int64_t clusters = ctx().num_sms / 2 > 0 ? ctx().num_sms / 2 : 1;
     auto eff = [&](int bn) {
         const int64_t tiles = batch * ((M + 255) / 256) * ((N + bn - 1) / bn);
-        const int64_t waves = (tiles + clusters - 1) / clusters;
-        return (double)tiles / (double)(waves * clusters);
+        const int64_t rem = tiles % clusters;
+        double waves = (double)(tiles / clusters);
+        if (rem) waves += (bn == 256 && 2 * rem <= clusters && N % 256 == 0) ? 0.5 : 1.0;   // the merged kernel splits a thin last wave
+        return (double)tiles / (waves * (double)clusters);
     };
     return eff(256) * 1.07 > eff(128) ? 256 : 128;
 }
