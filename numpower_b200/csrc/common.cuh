@@ -29,6 +29,7 @@ struct Ctx {
     int *domain_flag = nullptr;           // sticky math-domain flag (device)
     float *host_result = nullptr;         // pinned 64-byte result slot
     float *dev_result = nullptr;          // device result slot
+    int nonfinite_gen = 0;                // tag of the current x3 GEMM call (sgemm_tcgen05.cu, gemm_reset_nonfinite)
     int64_t live_allocs = 0;
     int64_t live_bytes = 0;
     int64_t launches = 0;

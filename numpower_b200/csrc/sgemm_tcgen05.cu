@@ -100,7 +100,8 @@ struct GemmParams {
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
     int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
-    const int *nonfinite;      // TF32x3: set by the split pre-pass when an operand holds +-inf (see lo_part)
+    const int *nonfinite;      // x3 modes: the split pre-pass stores nonfinite_gen here when an operand holds +-inf (see lo_part)
+    int nonfinite_gen;         // this call's tag (a fresh value per call instead of a memset per call)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
 };
 
@@ -432,7 +433,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     // An operand with +-inf: a_hi = inf times b_lo = 0 would turn cblas_sgemm's inf into NaN.  The pre-pass
                     // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
                     // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
-                    const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite)) ? 1 : 0;
+                    const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite) == p.nonfinite_gen) ? 1 : 0;
                     const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
                     for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
                         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
@@ -722,21 +723,24 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// device flag "an operand of the current TF32x3 call contains +-inf" (reset by gemm_reset_nonfinite before each call)
+// Device word "an operand of call #gen contains +-inf".  Every x3 call gets a fresh tag (gemm_reset_nonfinite), the split
+// kernels store the tag when they meet an inf and the GEMM compares against it: no per-call memset on the stream.
 static int *nonfinite_flag() { return reinterpret_cast<int *>(ctx().dev_result) + 8; }
 int gemm_reset_nonfinite() {
-    NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, sizeof(int), ctx().stream));
+    int &gen = ctx().nonfinite_gen;   // lives in the context: a re-initialised context starts from a cleared word again
+    if (gen == 0) NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, sizeof(int), ctx().stream));   // once: defined start value
+    if (++gen == 0x7FFFFFFF) gen = 1;
     return NB200_OK;
 }
 // +-inf has no finite remainder (inf - inf = NaN): its lo part is 0 and the call is flagged, see the MMA issuer.
-__device__ __forceinline__ float lo_part(float a, int *nonfinite) {
-    if (fabsf(a) == CUDART_INF_F) { *nonfinite = 1; return 0.f; }
+__device__ __forceinline__ float lo_part(float a, int *nonfinite, int gen) {
+    if (fabsf(a) == CUDART_INF_F) { *nonfinite = gen; return 0.f; }
     const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
     return to_tf32(a - hi);
 }
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
                                                          const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
-                                                         int *__restrict__ nonfinite) {
+                                                         int *__restrict__ nonfinite, int gen) {
     const int64_t g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;   // 4-element groups (spans are padded to a multiple of 4)
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= g0;
@@ -746,10 +750,10 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
         const int64_t n = second ? n1 : n0;
         if ((j << 2) + 4 <= n) {
             float4 a = ld_ew(reinterpret_cast<const float4 *>(in) + j), l;
-            l.x = lo_part(a.x, nonfinite); l.y = lo_part(a.y, nonfinite); l.z = lo_part(a.z, nonfinite); l.w = lo_part(a.w, nonfinite);
+            l.x = lo_part(a.x, nonfinite, gen); l.y = lo_part(a.y, nonfinite, gen); l.z = lo_part(a.z, nonfinite, gen); l.w = lo_part(a.w, nonfinite, gen);
             reinterpret_cast<float4 *>(lo)[j] = l;
         } else {
-            for (int64_t e = j << 2; e < n; e++) lo[e] = lo_part(in[e], nonfinite);
+            for (int64_t e = j << 2; e < n; e++) lo[e] = lo_part(in[e], nonfinite, gen);
         }
     }
 }
@@ -766,12 +770,12 @@ struct SplitSpan {
     int vec;                                                    // 16-byte aligned source rows
     int flat;                                                   // contiguous, cols % 8 == 0: output index == input index
 };
-__device__ __forceinline__ void split_bf16(float a, __nv_bfloat16 &h, __nv_bfloat16 &l, int *nonfinite) {
+__device__ __forceinline__ void split_bf16(float a, __nv_bfloat16 &h, __nv_bfloat16 &l, int *nonfinite, int gen) {
     uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) << 16;
     const uint32_t ab = __float_as_uint(a);
     if ((hb & 0x7FFFFFFFu) == 0x7F800000u) {
         if ((ab & 0x7FFFFFFFu) == 0x7F800000u) {   // +-inf: no finite remainder, see the MMA issuer
-            *nonfinite = 1;
+            *nonfinite = gen;
             h = __ushort_as_bfloat16((unsigned short)(hb >> 16));
             l = __ushort_as_bfloat16((unsigned short)0);
             return;
@@ -790,7 +794,7 @@ __global__ void __launch_bounds__(256) split_bf16_flat_kernel(const float *__res
                                                               __nv_bfloat16 *__restrict__ lo0, int64_t g0,
                                                               const float *__restrict__ in1, __nv_bfloat16 *__restrict__ hi1,
                                                               __nv_bfloat16 *__restrict__ lo1, int64_t g1,
-                                                              int *__restrict__ nonfinite) {
+                                                              int *__restrict__ nonfinite, int gen) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= g0;
         const int64_t j = second ? i - g0 : i;
@@ -813,8 +817,8 @@ __global__ void __launch_bounds__(256) split_bf16_flat_kernel(const float *__res
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(v[2 * q], h0, l0, nonfinite);
-                split_bf16(v[2 * q + 1], h1, l1, nonfinite);
+                split_bf16(v[2 * q], h0, l0, nonfinite, gen);
+                split_bf16(v[2 * q + 1], h1, l1, nonfinite, gen);
                 hp[q] = pack_bf16(h0, h1);
                 lp[q] = pack_bf16(l0, l1);
             }
@@ -824,7 +828,7 @@ __global__ void __launch_bounds__(256) split_bf16_flat_kernel(const float *__res
         reinterpret_cast<uint4 *>(second ? lo1 : lo0)[j] = lv;
     }
 }
-__global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, const SplitSpan s1, int *__restrict__ nonfinite) {
+__global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, const SplitSpan s1, int *__restrict__ nonfinite, int gen) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.groups + s1.groups; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= s0.groups;
         const SplitSpan &s = second ? s1 : s0;
@@ -841,7 +845,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, con
         }
         __nv_bfloat16 h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) split_bf16(v[e], h[e], l[e], nonfinite);
+        for (int e = 0; e < 4; e++) split_bf16(v[e], h[e], l[e], nonfinite, gen);
         // ld_out is a multiple of 8 and c of 4: 8-byte aligned stores; columns in [cols, ld_out) receive zeros
         const int64_t o = r * s.ld_out + c;
         uint2 hv, lv;
@@ -974,6 +978,7 @@ static int launch_gemm(const GemmArgs &g) {
     static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
     p.early_cross = early;
     p.nonfinite = nonfinite_flag();
+    p.nonfinite_gen = ctx().nonfinite_gen;
     p.a_batched = g.sA != 0;
     p.b_batched = g.sB != 0;
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
@@ -1008,7 +1013,7 @@ static int launch_split(const float *in0, float *lo0, int64_t n0, const float *i
     if (groups == 0) return NB200_OK;
     int64_t blocks = (groups + 255) / 256;   // one 4-element group per thread, non-persistent (see common.cuh)
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag());
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag(), ctx().nonfinite_gen);
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }
@@ -1077,13 +1082,13 @@ static int launch_split_bf16(const SplitSpan &s0, const SplitSpan &s1) {
         const int64_t g0 = s0.groups >> 1, g1 = s1.groups >> 1;   // 8-element groups
         int64_t blocks = (g0 + g1 + 255) / 256;
         if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-        split_bf16_flat_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0.in, s0.hi, s0.lo, g0, s1.in, s1.hi, s1.lo, g1, nonfinite_flag());
+        split_bf16_flat_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0.in, s0.hi, s0.lo, g0, s1.in, s1.hi, s1.lo, g1, nonfinite_flag(), ctx().nonfinite_gen);
         NB_LAUNCH_CHECK();
         return NB200_OK;
     }
     int64_t blocks = (groups + 255) / 256;
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-    split_bf16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0, s1, nonfinite_flag());
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(s0, s1, nonfinite_flag(), ctx().nonfinite_gen);
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }
