@@ -34,8 +34,8 @@ MATMUL_N = 4096
 SHARD_BATCH, SHARD_N = 128, 2048
 # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1b_ncu_gemm_ew.csv, profiles/r1_ncu_*.csv)
 GEMM_AUTO = 3                      # include/nb200.h NB200_GEMM_AUTO
-NCU_PIPE_ACTIVE_BF16X3 = 86.2      # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, profiles/r1d_ncu_gemm_bf16x3.csv
-NCU_TRAFFIC = {"sgemm_tf32_kernel<2,128,3,bf16>": 0.562e9, "split_bf16_flat_kernel": 0.226e9,
+NCU_PIPE_ACTIVE_BF16X3 = 85.8      # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, profiles/r1e_ncu_gemm_bf16x3_merged.csv
+NCU_TRAFFIC = {"sgemm_tf32_kernel<2,256,3,bf16,merged>": 0.351e9, "split_bf16_flat_kernel": 0.215e9,
                "sgemm_tf32_kernel<2,128,3>": 1.171e9, "split_tf32_kernel": 0.215e9, "sgemm_tf32_kernel<2,256,1>": 0.388e9,
                "ew_flat_vec<3,MulAddOp>": 1.043e9, "ew_bcast2d<3,MulAddOp,4,1>": 0.489e9, "reduce_rows_kernel<0> 2^28": 1.077e9,
                "arg_rows_kernel<1> 2^28": 1.077e9, "reduce_cols_kernel<0,4,8,0>": 0.272e9}
@@ -389,9 +389,9 @@ def run_single(args):
                    "l2": "operands 128 MiB + result 64 MiB exceed the 126 MB L2; HBM-bound extras flush L2 between timed launches",
                    "timing": "CUDA events on the launching stream"},
         "roofline": {"bound": "tensor", "achieved": useful, "peak": bf16_peak, "unit": "TFLOP/s", "frac": useful / bf16_peak,
-                     "traffic": NCU_TRAFFIC["sgemm_tf32_kernel<2,128,3,bf16>"] + NCU_TRAFFIC["split_bf16_flat_kernel"],
+                     "traffic": NCU_TRAFFIC["sgemm_tf32_kernel<2,256,3,bf16,merged>"] + NCU_TRAFFIC["split_bf16_flat_kernel"],
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as "
-                                       "profiles/r1d_ncu_gemm_bf16x3.csv (GEMM kernel + bf16 split pre-pass; algorithmic minimum "
+                                       "profiles/r1e_ncu_gemm_bf16x3_merged.csv (GEMM kernel 0.351 GB + bf16 split pre-pass 0.215 GB; algorithmic minimum "
                                        "3 x 64 MiB = 0.201 GB: the GEMM is tensor-bound, its re-reads are L2-served)",
                      "tensor_pipe_active_pct_ncu": NCU_PIPE_ACTIVE_BF16X3, "peak_source": peaks["_source"] + ": bf16_tflops (cuBLAS bf16 8192^3)",
                      "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / bf16_peak,
