@@ -144,7 +144,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -407,7 +407,7 @@ def run_single(args):
         "clocks": clocks,
         "extras": extras,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -492,12 +492,32 @@ def run_multi(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries that write to file descriptor 1 (NCCL prints its
+    version banner there when NCCL_DEBUG is set on the box) are diverted to stderr; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
