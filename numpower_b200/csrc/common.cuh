@@ -42,6 +42,7 @@ int ensure_scratch(int64_t bytes);
 int ensure_gemm_ws(int64_t bytes);
 int gemm_split_operand(const float *in, float *lo, int64_t n);
 int gemm_reset_nonfinite();
+int gemm_resolve_precision(int precision, int64_t K);   // NB200_GEMM_AUTO -> concrete mode
 int gemm_bf16_split(const float *in, void *hi, void *lo, int64_t rows, int64_t cols);
 int gemm_bf16_presplit(float *C, const void *a_hi, const void *a_lo, const void *b_hi, const void *b_lo, int64_t M, int64_t N,
                        int64_t K, int64_t ldc);

@@ -1,0 +1,127 @@
+"""CPU model of the two error-compensated GEMM modes (numpower_b200/csrc/sgemm_tcgen05.cu): the operand splits and the
+three retained products are restated in numpy with exact (fp64) accumulation, so what remains is the algorithmic error of
+the split itself — the part the kernels cannot do better than.  Checks the bounds DESIGN.md §5 quotes:
+
+  TF32x3:  a = hi + lo, hi = trunc_tf32(a), lo = rna_tf32(a - hi); |lo| <= 2^-10 |a|, remainder <= 2^-21 |a|;
+           dropped lo.lo (<= 2^-20) and the two remainders                       -> <= 2^-19 per product: GUARANTEES 1e-5
+  BF16x3:  a = a1 + a2 + r, a1 = rn_bf16(a), a2 = rn_bf16(a - a1); |a2| <= 2^-8 |a|, |r| <= 2^-17 |a|;
+           dropped a2.b2 (<= 2^-16) and the two remainders                       -> <= 2^-15 per product, zero-mean:
+           averages out over K on random data, adds up coherently on constant matrices -> opt-in mode, not NB200_GEMM_AUTO
+"""
+import numpy as np
+import pytest
+
+
+def _bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def rn_bf16(x):
+    """round-to-nearest-even to bfloat16, returned as float32 (cvt.rn.bf16.f32)."""
+    b = _bits(x).astype(np.uint64)
+    r = ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return r.view(np.float32)
+
+
+def trunc_tf32(x):
+    return (_bits(x) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def rna_tf32(x):
+    """round-to-nearest, ties away from zero, to TF32 (cvt.rna.tf32.f32)."""
+    b = _bits(x).astype(np.uint64)
+    return ((b + 0x1000) & 0xFFFFE000).astype(np.uint32).view(np.float32)
+
+
+def split_bf16(a):
+    a1 = rn_bf16(a)
+    a2 = rn_bf16((a - a1).astype(np.float32))      # a - a1 is exact in fp32
+    return a1, a2
+
+
+def split_tf32(a):
+    hi = trunc_tf32(a)
+    return hi, rna_tf32((a - hi).astype(np.float32))
+
+
+def three_products(ah, al, bh, bl):
+    d = np.float64
+    return ah.astype(d) @ bh.astype(d) + ah.astype(d) @ bl.astype(d) + al.astype(d) @ bh.astype(d)
+
+
+def test_bf16_split_remainder_bound():
+    r = np.random.default_rng(0)
+    a = (r.random(1 << 16, dtype=np.float32) * 2 - 1) * np.exp2(r.integers(-20, 20, 1 << 16)).astype(np.float32)
+    a1, a2 = split_bf16(a)
+    assert ((a - a1).astype(np.float32).astype(np.float64) == a.astype(np.float64) - a1.astype(np.float64)).all()   # exact subtraction
+    rem = np.abs(a.astype(np.float64) - a1.astype(np.float64) - a2.astype(np.float64))
+    assert (rem <= np.abs(a) * 2.0 ** -17).all()
+    assert (np.abs(a2) <= np.abs(a) * 2.0 ** -8).all()
+    # both parts really are bf16 values
+    assert ((_bits(a1) & 0xFFFF) == 0).all() and ((_bits(a2) & 0xFFFF) == 0).all()
+
+
+def test_tf32_split_remainder_bound():
+    r = np.random.default_rng(1)
+    a = (r.random(1 << 16, dtype=np.float32) * 2 - 1) * np.exp2(r.integers(-20, 20, 1 << 16)).astype(np.float32)
+    hi, lo = split_tf32(a)
+    rem = np.abs(a.astype(np.float64) - hi.astype(np.float64) - lo.astype(np.float64))
+    assert (rem <= np.abs(a) * 2.0 ** -21).all()
+    assert (np.abs(lo) <= np.abs(a) * 2.0 ** -10).all()
+    assert ((_bits(hi) & 0x1FFF) == 0).all() and ((_bits(lo) & 0x1FFF) == 0).all()
+
+
+@pytest.mark.parametrize("k", [1, 8, 128, 1024])
+def test_bf16x3_algorithmic_error_random_data(k):
+    """Per product up to 2^-16 + 2 * 2^-17 = 2^-15; zero-mean, so on random data it shrinks along K."""
+    r = np.random.default_rng(k)
+    a, b = r.random((96, k), dtype=np.float32), r.random((k, 80), dtype=np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    a1, a2 = split_bf16(a)
+    b1, b2 = split_bf16(b)
+    signed = (three_products(a1, a2, b1, b2) - exact) / exact
+    assert np.abs(signed).max() <= 2.0 ** -15
+    if k >= 128:
+        assert np.abs(signed).max() <= 3e-6      # what the GPU measurements show as well (1.2-2.5e-6 incl. accumulation)
+    assert abs(signed.mean()) <= 2e-6
+
+
+def test_bf16x3_coherent_inputs_break_1e5_and_tf32x3_does_not():
+    """A constant-matrix GEMM is one product repeated K times: its split error does not average out.  This is the reason
+    NB200_GEMM_AUTO resolves to TF32x3 (include/nb200.h) and BF16x3 is opt-in."""
+    r = np.random.default_rng(7)
+    n = 200_000
+    a = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
+    b = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
+    d = np.float64
+    exact = a.astype(d) * b.astype(d)
+    a1, a2 = split_bf16(a)
+    b1, b2 = split_bf16(b)
+    e_bf16 = np.abs(a1.astype(d) * b1 + a1.astype(d) * b2 + a2.astype(d) * b1 - exact) / exact
+    ah, al = split_tf32(a)
+    bh, bl = split_tf32(b)
+    e_tf32 = np.abs(ah.astype(d) * bh + ah.astype(d) * bl + al.astype(d) * bh - exact) / exact
+    assert e_tf32.max() <= 2.0 ** -19 < 1e-5          # guaranteed
+    assert e_bf16.max() <= 2.0 ** -15
+    assert e_bf16.max() > 1e-5 and 0.01 < (e_bf16 > 1e-5).mean() < 0.2   # a few per cent of constant pairs violate 1e-5
+
+
+@pytest.mark.parametrize("k", [1, 8, 1024])
+def test_tf32x3_algorithmic_error(k):
+    r = np.random.default_rng(100 + k)
+    a, b = r.random((96, k), dtype=np.float32), r.random((k, 80), dtype=np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    ah, al = split_tf32(a)
+    bh, bl = split_tf32(b)
+    err = np.abs(three_products(ah, al, bh, bl) - exact) / exact
+    assert err.max() <= 2.0 ** -19
+
+
+def test_bf16_split_special_values_match_the_kernel_rules():
+    """split_bf16() in sgemm_tcgen05.cu: +-inf -> (inf, 0); finite values that would round up to inf are truncated."""
+    big = np.array([3.4e38, -3.4e38], np.float32)
+    assert np.isinf(rn_bf16(big)).all()                      # plain rounding overflows ...
+    trunc = (_bits(big) & np.uint32(0xFFFF0000)).view(np.float32)
+    assert np.isfinite(trunc).all()                          # ... truncation (what the kernel does) does not
+    lo = rn_bf16((big - trunc).astype(np.float32))
+    assert (np.abs(big.astype(np.float64) - trunc.astype(np.float64) - lo.astype(np.float64)) <= np.abs(big) * 2.0 ** -16).all()
