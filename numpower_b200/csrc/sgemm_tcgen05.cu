@@ -32,12 +32,18 @@
 #include <cstring>
 #include <math_constants.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace nb200 {
 
 // ------------------------------------------------------------------ configuration
-template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false, bool MERGED_ = false>
+template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false, bool MERGED_ = false, bool SCALED_ = false>
 struct GemmCfg {
+    // SCALED (FP16x3): the 16-bit operand parts are IEEE half (11-bit significands, TF32x3-class split error) of
+    // A scaled per row and B scaled per column by powers of two (so that every row / column uses the top of fp16's
+    // exponent range); the epilogue undoes the scaling with one exact scalbnf per output element.
+    static constexpr bool SCALED = SCALED_;
+    static_assert(!SCALED_ || BF16_, "scaled mode uses the 16-bit operand path");
     // MERGED (BF16x3, BN = 256): all three products of a chunk accumulate into ONE 256-column TMEM accumulator (2-deep
     // ring = all 512 columns) and the running total lives in the registers of eight epilogue warps.  Twice the flops
     // per staged byte and no cross-accumulator hand-off between tiles; costs 48 instead of 32 truncating accumulation
@@ -101,6 +107,7 @@ struct GemmParams {
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
     int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
+    const unsigned int *row_max, *col_max;   // SCALED: |max| bit patterns per row of A / column of B (see scale_exp)
     const int *nonfinite;      // x3 modes: the split pre-pass stores nonfinite_gen here when an operand holds +-inf (see lo_part)
     int nonfinite_gen;         // this call's tag (a fresh value per call instead of a memset per call)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
@@ -283,10 +290,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // Instruction descriptor (32-bit): D=f32 (bits 4-5 =1), A=B=tf32 (bits 7-9, 10-12 =2), A K-major (bit 15 =0),
 // B MN-major (bit 16 =1), N>>3 at bits 17-22, M>>4 at bits 24-28.
 // kind::f16 uses the same fields with A=B=bf16 (format code 1).
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool bf16 = false) {
-    const uint32_t fmt = bf16 ? 1u : 2u;
+// fmt: 0 = f16, 1 = bf16 (both kind::f16), 2 = tf32.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, uint32_t fmt = 2u) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
+}
+
+// FP16x3 scaling: the power of two that brings a row's / column's largest finite magnitude (given as its bit pattern,
+// collected by absmax_*_kernel) into [2^14, 2^15), the top binade below fp16's 65504.  0 for empty / all-zero vectors.
+// The exponent is clamped to +-100 so that a row and a column exponent always combine into two representable power-of-two
+// factors (vectors whose largest magnitude is below 2^-86 are simply not brought all the way up).
+__device__ __forceinline__ int scale_exp(unsigned int max_bits) {
+    if (max_bits == 0u || max_bits >= 0x7F800000u) return 0;
+    const int e = 14 - ((int)(max_bits >> 23) - 127);          // subnormal maxima read as 2^-127: clamped below anyway
+    return e > 100 ? 100 : (e < -100 ? -100 : e);
+}
+// x * 2^e, |e| <= 200, as two exact multiplications (2^e itself may not be representable)
+__device__ __forceinline__ float scale_pow2(float x, int e) {
+    const int e1 = e / 2, e2 = e - e1;
+    return x * __int_as_float((e1 + 127) << 23) * __int_as_float((e2 + 127) << 23);
 }
 
 // Tile order within one matrix: bands of `group_m` row-tiles, inside a band m fastest.  The tiles in flight at any time
@@ -400,8 +422,9 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
-            constexpr uint32_t idesc_full = make_idesc_tf32(BM * CG, BN, Cfg::BF16);
-            constexpr uint32_t idesc_half = make_idesc_tf32(BM * CG, BN / 2, Cfg::BF16);
+            constexpr uint32_t FMT = Cfg::SCALED ? 0u : (Cfg::BF16 ? 1u : 2u);
+            constexpr uint32_t idesc_full = make_idesc_tf32(BM * CG, BN, FMT);
+            constexpr uint32_t idesc_half = make_idesc_tf32(BM * CG, BN / 2, FMT);
             constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
@@ -530,10 +553,21 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             const int64_t row = (int64_t)m_tile * BM * CG + (int64_t)rank * BM + quarter * 32 + lane;
             const int64_t col0 = (int64_t)n_tile * BN + (half_tile ? (int64_t)((t - p.full_items) & 1) * (BN / 2) : 0);
             float *crow = p.C + b * p.strideC + row * p.ldc;
+            // SCALED: C = acc * 2^-(row exponent + column exponent), one exact scalbnf per element
+            int e_row = 0;
+            const unsigned int *cmax = nullptr;
+            if constexpr (Cfg::SCALED) {
+                if (row < p.M) e_row = scale_exp(p.row_max[(p.a_batched ? b : 0) * p.M + row]);
+                cmax = p.col_max + (p.b_batched ? b : 0) * p.N;
+            }
             auto store_row = [&](int c, const uint32_t (&v)[32]) {
                 const int64_t col = col0 + c * 32;
                 if (row < p.M) {
-                    if (vec_ok && col + 32 <= p.N) {
+                    if constexpr (Cfg::SCALED) {
+#pragma unroll
+                        for (int q = 0; q < 32; q++)
+                            if (col + q < p.N) crow[col + q] = scale_pow2(__uint_as_float(v[q]), -(e_row + scale_exp(cmax[col + q])));
+                    } else if (vec_ok && col + 32 <= p.N) {
                         float4 *dst = reinterpret_cast<float4 *>(crow + col);
 #pragma unroll
                         for (int q = 0; q < 8; q++)
@@ -575,6 +609,11 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     }
                     if (last && row < p.M && !idle) {
                         const int64_t colh = col0 + half * 128;
+                        if constexpr (Cfg::SCALED) {
+#pragma unroll
+                            for (int q = 0; q < 128; q++)
+                                if (colh + q < p.N) tot[q] = scale_pow2(tot[q], -(e_row + scale_exp(cmax[colh + q])));
+                        }
                         if (vec_ok && colh + 128 <= p.N) {
                             float4 *dst = reinterpret_cast<float4 *>(crow + colh);
 #pragma unroll
@@ -857,6 +896,99 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, con
     }
 }
 
+// ------------------------------------------------------------------ FP16x3 pre-pass: per-row / per-column |max|, scaled half split
+// Largest FINITE magnitude of every row of A and every column of B, as fp32 bit patterns (monotonic as unsigned ints),
+// combined with atomicMax into zero-initialised arrays.  +-inf / NaN are skipped here; the split flags them.
+__device__ __forceinline__ unsigned int finite_abs_bits(float v) {
+    const unsigned int b = __float_as_uint(v) & 0x7FFFFFFFu;
+    return b < 0x7F800000u ? b : 0u;
+}
+// one warp per row; rows = batch * rows_per
+__global__ void __launch_bounds__(256) absmax_rows_kernel(const float *__restrict__ in, int64_t rows_per, int64_t nrows, int64_t cols,
+                                                          int64_t ld_in, int64_t stride_in, unsigned int *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < nrows; r += (int64_t)gridDim.x * 8) {
+        const int64_t b = r / rows_per, rr = r - b * rows_per;
+        const float *src = in + b * stride_in + rr * ld_in;
+        unsigned int m = 0;
+        if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (cols & 3) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            for (int64_t c = lane; c < (cols >> 2); c += 32) {
+                const float4 v = ldg_stream(s4 + c);
+                m = max(max(m, finite_abs_bits(v.x)), max(finite_abs_bits(v.y), max(finite_abs_bits(v.z), finite_abs_bits(v.w))));
+            }
+        } else {
+            for (int64_t c = lane; c < cols; c += 32) m = max(m, finite_abs_bits(ldg_stream(src + c)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if (lane == 0) out[r] = m;
+    }
+}
+// threads along the contiguous columns, blockIdx.y splits the rows, blockIdx.z = batch
+__global__ void __launch_bounds__(256) absmax_cols_kernel(const float *__restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                                                          int64_t stride_in, unsigned int *__restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= cols) return;
+    const float *src = in + (int64_t)blockIdx.z * stride_in + c;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    unsigned int m = 0;
+    for (int64_t r = r0; r < r1; r++) m = max(m, finite_abs_bits(ldg_stream(src + r * ld_in)));
+    if (m) atomicMax(out + (int64_t)blockIdx.z * cols + c, m);
+}
+// a' = a * 2^e (e from the row or column |max|), hi = rn_f16(a'), lo = rn_f16(a' - hi); |a'| < 2^15, so nothing overflows.
+// Remainder <= 2^-22 |a'| for |a'| >= 2^-3 (normal lo part), <= 2^-25 absolute below (subnormal spacing).
+__device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, unsigned short &l, int *nonfinite, int gen) {
+    const unsigned int ab = __float_as_uint(a) & 0x7FFFFFFFu;
+    if (ab >= 0x7F800000u) {                       // +-inf (flag: see the MMA issuer) or NaN: hi carries it, lo = 0
+        if (ab == 0x7F800000u) *nonfinite = gen;
+        h = __half_as_ushort(__float2half_rn(a));
+        l = 0;
+        return;
+    }
+    const float x = scale_pow2(a, e);
+    const __half hh = __float2half_rn(x);
+    h = __half_as_ushort(hh);
+    l = __half_as_ushort(__float2half_rn(x - __half2float(hh)));
+}
+struct SplitSpanF16 {
+    SplitSpan s;
+    const unsigned int *max_bits;   // per row (by_col == 0: index = output row) or per column (index = batch * cols + column)
+    int by_col;
+};
+__global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int *__restrict__ nonfinite, int gen) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.s.groups + s1.s.groups; i += (int64_t)gridDim.x * 256) {
+        const bool second = i >= s0.s.groups;
+        const SplitSpanF16 &sp = second ? s1 : s0;
+        const SplitSpan &s = sp.s;
+        const int64_t j = second ? i - s0.s.groups : i;
+        const int64_t r = j / s.gpr, c = (j - r * s.gpr) << 2;
+        const int64_t b = r / s.rows_per, rr = r - b * s.rows_per;
+        const float *src = s.in + b * s.stride_in + rr * s.ld_in + c;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s.vec && c + 4 <= s.cols) {
+            const float4 a = ld_ew(reinterpret_cast<const float4 *>(src));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else {
+            for (int e = 0; e < 4; e++) if (c + e < s.cols) v[e] = src[e];
+        }
+        const int e_row = sp.by_col ? 0 : scale_exp(sp.max_bits[r]);
+        unsigned short h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int ex = sp.by_col ? (c + e < s.cols ? scale_exp(sp.max_bits[b * s.cols + c + e]) : 0) : e_row;
+            split_f16(v[e], ex, h[e], l[e], nonfinite, gen);
+        }
+        const int64_t o = r * s.ld_out + c;
+        uint2 hv, lv;
+        hv.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16); hv.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+        lv.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); lv.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+        *reinterpret_cast<uint2 *>(s.hi + o) = hv;
+        *reinterpret_cast<uint2 *>(s.lo + o) = lv;
+    }
+}
+
 // ------------------------------------------------------------------ SIMT fp32 GEMM (small / unaligned shapes)
 // 64x64 tile, BK = 16, 256 threads x (4x4) micro-tile, fp32 FMA, k in increasing order.
 __global__ void __launch_bounds__(256) sgemm_simt_kernel(float *__restrict__ C, const float *__restrict__ A,
@@ -938,6 +1070,7 @@ struct GemmArgs {
     float *C;
     const float *A, *B, *A_lo, *B_lo;   // A/B are the "hi" (or raw) operands
     int64_t batch, M, N, K, lda, ldb, ldc, sA, sB, sC;
+    const unsigned int *row_max = nullptr, *col_max = nullptr;   // FP16x3 scaling inputs (GemmCfg::SCALED)
 };
 
 template <class Cfg>
@@ -978,6 +1111,7 @@ static int launch_gemm(const GemmArgs &g) {
     p.group_m = group_m;
     static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
     p.early_cross = early;
+    p.row_max = g.row_max; p.col_max = g.col_max;
     p.nonfinite = nonfinite_flag();
     p.nonfinite_gen = ctx().nonfinite_gen;
     p.a_batched = g.sA != 0;
@@ -1064,6 +1198,13 @@ static bool tensor_path_ok(const GemmArgs &g) {
 }
 
 static inline int64_t round8(int64_t x) { return (x + 7) & ~int64_t(7); }
+// Batched x3 calls process the batch in chunks whose operand parts fit this much workspace (default 4 GiB;
+// NB200_GEMM_WS_BUDGET_MB overrides it, read per call so that tests can force several chunks on small problems).
+static int64_t gemm_ws_budget() {
+    const char *e = getenv("NB200_GEMM_WS_BUDGET_MB");
+    const int64_t mb = e ? atoll(e) : 0;
+    return mb > 0 ? mb << 20 : (int64_t)4 << 30;
+}
 static SplitSpan make_span(const float *in, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t batch, int64_t rows, int64_t cols,
                            int64_t ld_in, int64_t stride_in) {
     SplitSpan s;
@@ -1116,7 +1257,7 @@ static int gemm_bf16x3(const GemmArgs &g) {
     const int64_t lda = round8(g.K), ldb = round8(g.N);
     const int64_t per_a = g.M * lda, per_b = g.K * ldb;          // bf16 elements per matrix
     int64_t chunk = g.batch;
-    const int64_t budget = (int64_t)4 << 30;
+    const int64_t budget = gemm_ws_budget();
     if (g.batch > 1) {
         const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0));
         if (per > 0 && per * chunk > budget) chunk = budget / per;
@@ -1125,7 +1266,9 @@ static int gemm_bf16x3(const GemmArgs &g) {
     { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
-        const int64_t na = (g.sA ? nb : 1) * per_a, nbb = (g.sB ? nb : 1) * per_b;
+        // workspace offsets follow the FULL chunk size: a shared operand, split with the first chunk, must stay where it is
+        // when the last chunk is shorter
+        const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
         int rc = ensure_gemm_ws((na + nbb) * 4 + 1024);
         if (rc != NB200_OK) return rc;
         __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);
@@ -1153,6 +1296,83 @@ static int gemm_bf16x3(const GemmArgs &g) {
     return NB200_OK;
 }
 
+// FP16x3: the BF16x3 pipeline with IEEE-half parts of row-scaled A / column-scaled B (see GemmCfg::SCALED).
+// Pre-pass = |max| per row of A and per column of B (two read-only passes), then the scaled split; workspace layout:
+// [a_hi | a_lo | b_hi | b_lo | row_max (u32 per row) | col_max (u32 per column)].
+static int gemm_fp16x3(const GemmArgs &g) {
+    const int64_t lda = round8(g.K), ldb = round8(g.N);
+    const int64_t per_a = g.M * lda, per_b = g.K * ldb;          // 16-bit elements per matrix
+    int64_t chunk = g.batch;
+    const int64_t budget = gemm_ws_budget();
+    if (g.batch > 1) {
+        const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0));
+        if (per > 0 && per * chunk > budget) chunk = budget / per;
+        if (chunk < 1) chunk = 1;
+        if (chunk > 65535) chunk = 65535;                        // absmax_cols_kernel puts the batch on gridDim.z
+    }
+    { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
+    for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
+        const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
+        const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;   // matrices of each operand in this chunk
+        const int64_t n_rows = ba * g.M, n_cols = bb * g.N;
+        // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
+        const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
+        const int64_t rows_layout = (g.sA ? chunk : 1) * g.M, cols_layout = (g.sB ? chunk : 1) * g.N;
+        int rc = ensure_gemm_ws((na + nbb) * 4 + (rows_layout + cols_layout) * 4 + 1024);
+        if (rc != NB200_OK) return rc;
+        __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);   // (16-bit storage; the contents are IEEE half)
+        __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
+        unsigned int *row_max = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);
+        unsigned int *col_max = row_max + rows_layout;
+        const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
+        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once
+        if (do_a) {
+            int64_t blocks = (n_rows + 7) / 8;
+            if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+            absmax_rows_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(a_src, g.M, n_rows, g.K, g.lda, g.sA, row_max);
+            NB_LAUNCH_CHECK();
+        }
+        if (do_b) {
+            NB_CUDA(cudaMemsetAsync(col_max, 0, (size_t)n_cols * 4, ctx().stream));
+            // enough row segments to fill the machine: columns / 256 blocks wide
+            const int64_t bx = (g.N + 255) / 256;
+            int64_t by = (4 * ctx().num_sms + bx * bb - 1) / (bx * bb);
+            if (by < 1) by = 1;
+            if (by > g.K) by = g.K;
+            if (by > 65535) by = 65535;
+            absmax_cols_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
+            NB_LAUNCH_CHECK();
+        }
+        SplitSpanF16 sa, sb;
+        sa.s = make_span(a_src, a_hi, a_lo, do_a ? ba : 0, g.M, g.K, g.lda, g.sA);
+        sa.max_bits = row_max; sa.by_col = 0;
+        sb.s = make_span(b_src, b_hi, b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
+        sb.max_bits = col_max; sb.by_col = 1;
+        const int64_t groups = sa.s.groups + sb.s.groups;
+        if (groups > 0) {
+            int64_t blocks = (groups + 255) / 256;
+            if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+            split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
+            NB_LAUNCH_CHECK();
+        }
+        GemmArgs c = g;
+        c.batch = nb;
+        c.A = reinterpret_cast<const float *>(a_hi); c.A_lo = reinterpret_cast<const float *>(a_lo);
+        c.B = reinterpret_cast<const float *>(b_hi); c.B_lo = reinterpret_cast<const float *>(b_lo);
+        c.lda = lda; c.ldb = ldb;
+        c.sA = g.sA ? per_a : 0; c.sB = g.sB ? per_b : 0;
+        c.C = g.C + b0 * g.sC;
+        c.row_max = row_max; c.col_max = col_max;
+        const int v = gemm_variant();
+        const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
+        const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? bf16_pair_bn(nb, g.M, g.N) : 128);
+        if (cg == 2 && bn == 256) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
+        else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
+        if (rc != NB200_OK) return rc;
+    }
+    return NB200_OK;
+}
+
 // AUTO = the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every input: TF32x3 (<= 3 * 2^-22 per
 // product plus the chunked accumulation, measured 1.8e-6).  BF16x3 is twice as fast on the tensor pipe but its bound is
 // only statistical: each product may be off by up to 2^-16 + 2 * 2^-17 (dropped a2.b2 and the split remainders) — zero-mean,
@@ -1161,8 +1381,10 @@ static int gemm_bf16x3(const GemmArgs &g) {
 // precision = NB200_GEMM_BF16X3 per call, or NB200_GEMM_AUTO_MODE=bf16x3 in the environment to let AUTO use it for K >= 128.
 int gemm_resolve_precision(int precision, int64_t K) {
     if (precision != NB200_GEMM_AUTO) return precision;
-    static const bool auto_bf16 = getenv("NB200_GEMM_AUTO_MODE") && strcmp(getenv("NB200_GEMM_AUTO_MODE"), "bf16x3") == 0;
-    return (auto_bf16 && K >= 128) ? NB200_GEMM_BF16X3 : NB200_GEMM_TF32X3;
+    static const char *mode = getenv("NB200_GEMM_AUTO_MODE");
+    static const int fast = !mode ? NB200_GEMM_TF32X3 : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
+                                  : strcmp(mode, "fp16x3") == 0 ? NB200_GEMM_FP16X3 : NB200_GEMM_TF32X3;
+    return K >= 128 ? fast : NB200_GEMM_TF32X3;
 }
 
 static int gemm_impl(GemmArgs g, int precision) {
@@ -1178,7 +1400,8 @@ static int gemm_impl(GemmArgs g, int precision) {
     const bool bf16_ok = g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
     static const bool force_simt = getenv("NB200_GEMM_FORCE_SIMT") != nullptr;   // debugging switch, read once
     if (precision == NB200_GEMM_BF16X3 && bf16_ok && !force_simt) return gemm_bf16x3(g);
-    if (precision == NB200_GEMM_BF16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
+    if (precision == NB200_GEMM_FP16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g);
+    if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
         if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
@@ -1199,7 +1422,7 @@ static int gemm_impl(GemmArgs g, int precision) {
     }
     // ---- TF32x3 with the lo-part pre-pass into the context workspace, batch processed in chunks
     int64_t chunk = g.batch;
-    const int64_t budget = (int64_t)4 << 30;  // at most 4 GiB of workspace per chunk
+    const int64_t budget = gemm_ws_budget();
     if (g.batch > 1) {
         int64_t per = 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0));
         if (per > 0 && per * chunk > budget) chunk = budget / per;
@@ -1209,7 +1432,8 @@ static int gemm_impl(GemmArgs g, int precision) {
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t sa = span(g.sA ? nb : 1, g.sA, g.M, g.lda, g.K), sb = span(g.sB ? nb : 1, g.sB, g.K, g.ldb, g.N);
-        const int64_t na = round4(sa), nbb = round4(sb);
+        // workspace offsets follow the FULL chunk size (a shared operand split with the first chunk must not move)
+        const int64_t na = round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)), nbb = round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N));
         int rc = ensure_gemm_ws((na + nbb) * 4 + 256);
         if (rc != NB200_OK) return rc;
         float *ws = static_cast<float *>(ctx().gemm_ws);
@@ -1262,7 +1486,7 @@ extern "C" int nb200_sgemm_batched(float *C, const float *A, const float *B, int
     NB_READY();
     if (!C || !A || !B || batch < 0 || M < 0 || N < 0 || K < 0 || strideA < 0 || strideB < 0 || strideC < 0)
         return set_error(NB200_EINVAL, "nb200_sgemm_batched: bad argument");
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_AUTO)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, batch, M, N, K, K, N, N, strideA, strideB, strideC};
     return gemm_impl(g, precision);
@@ -1274,7 +1498,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
     if (!C || !A || !B || M < 0 || N < 0 || K < 0 || lda < K || ldb < N || ldc < N)
         return set_error(NB200_EINVAL, "Shape mismatch for matmul (M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
                          (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_AUTO)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
     return gemm_impl(g, precision);
@@ -1284,9 +1508,11 @@ extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, 
     if (!bytes) return set_error(NB200_EINVAL, "null argument");
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
     precision = gemm_resolve_precision(precision, K);
-    int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024 : 4 * (round4(M * K) + round4(K * N));
+    int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024
+                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * (M + N) + 1024
+                                                 : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
-    const int64_t budget = (int64_t)4 << 30;
+    const int64_t budget = gemm_ws_budget();
     *bytes = (total > budget && batch > 1) ? (budget / per > 0 ? (budget / per) * per : per) : total;
     return NB200_OK;
 }

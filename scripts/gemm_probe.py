@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
-PNAME = {0: "x3", 1: "x1", 2: "bf16x3"}
+PNAME = {0: "x3", 1: "x1", 2: "bf16x3", 4: "fp16x3"}
 VARIANTS = {"cg1_bn256": 384, "cg1_bn128": 320, "cg2_bn256": 640, "cg2_bn128": 576}
 
 
@@ -73,7 +73,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         sizes = [(256, 256, 256), (1024, 1024, 1024), (1000, 520, 776), (4096, 4096, 4096)]
-        if int(sys.argv[3]) == 2:
+        if int(sys.argv[3]) in (2, 4):
             sizes = [(256, 256, 256), (333, 77, 129), (1000, 520, 776), (1024, 1024, 1024), (2048, 2048, 2048), (4096, 4096, 4096), (8192, 8192, 8192)]
         if len(sys.argv) > 4:
             sizes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[4:]]

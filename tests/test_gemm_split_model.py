@@ -125,3 +125,67 @@ def test_bf16_split_special_values_match_the_kernel_rules():
     assert np.isfinite(trunc).all()                          # ... truncation (what the kernel does) does not
     lo = rn_bf16((big - trunc).astype(np.float32))
     assert (np.abs(big.astype(np.float64) - trunc.astype(np.float64) - lo.astype(np.float64)) <= np.abs(big) * 2.0 ** -16).all()
+
+
+# ------------------------------------------------------------------ FP16x3 (scaled half parts), numpy restatement
+def scale_exp(max_abs):
+    """sgemm_tcgen05.cu scale_exp(): power of two bringing the largest finite magnitude into [2^14, 2^15)."""
+    m = np.asarray(max_abs, dtype=np.float64)
+    e = np.zeros(m.shape, dtype=np.int64)
+    ok = (m > 0) & np.isfinite(m)
+    e[ok] = 14 - np.floor(np.log2(m[ok])).astype(np.int64)
+    return e
+
+
+def split_f16_scaled(x, e):
+    """x * 2^e -> (hi, lo) IEEE half values (returned as float64 for exact arithmetic)."""
+    xs = np.ldexp(x.astype(np.float64), e)                 # exact
+    hi = xs.astype(np.float32).astype(np.float16)          # cvt.rn.f16.f32
+    lo = (xs - hi.astype(np.float64)).astype(np.float32).astype(np.float16)
+    return hi.astype(np.float64), lo.astype(np.float64)
+
+
+def fp16x3_model(a, b):
+    ea = scale_exp(np.abs(a).max(axis=1))[:, None]
+    eb = scale_exp(np.abs(b).max(axis=0))[None, :]
+    ah, al = split_f16_scaled(a, ea)
+    bh, bl = split_f16_scaled(b, eb)
+    assert np.abs(ah).max() <= 32768 and np.abs(bh).max() <= 32768      # never overflows fp16
+    acc = ah @ bh + ah @ bl + al @ bh
+    return np.ldexp(acc, -(ea + eb))
+
+
+def test_fp16x3_coherent_inputs_stay_inside_1e5():
+    """The case that breaks BF16x3 (one product repeated): 11-bit parts keep it at TF32x3 level."""
+    r = np.random.default_rng(7)
+    n = 100_000
+    a = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
+    b = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
+    exact = a.astype(np.float64) * b.astype(np.float64)
+    got = np.array([fp16x3_model(a[i:i + 1, None], b[None, i:i + 1])[0, 0] for i in range(0, n, 50)])
+    err = np.abs(got - exact[::50]) / exact[::50]
+    assert err.max() <= 2.0 ** -20
+
+
+@pytest.mark.parametrize("k", [8, 256])
+def test_fp16x3_random_and_wide_dynamic_range(k):
+    r = np.random.default_rng(k)
+    a, b = r.random((64, k), dtype=np.float32), r.random((k, 48), dtype=np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    assert (np.abs(fp16x3_model(a, b) - exact) / exact).max() <= 2.0 ** -20
+    # rows of A / columns of B scaled by 2^-60 .. 2^60: the per-row / per-column exponents absorb it exactly
+    a2 = (a * np.exp2(r.integers(-60, 61, size=(64, 1))).astype(np.float32)).astype(np.float32)
+    b2 = (b * np.exp2(r.integers(-60, 61, size=(1, 48))).astype(np.float32)).astype(np.float32)
+    exact2 = a2.astype(np.float64) @ b2.astype(np.float64)
+    assert (np.abs(fp16x3_model(a2, b2) - exact2) / np.abs(exact2)).max() <= 2.0 ** -20
+
+
+def test_fp16x3_intra_row_dynamic_range_is_normwise():
+    """Elements more than 2^-18 below their row's maximum lose relative precision (fp16 subnormal spacing), but only by
+    2^-39 of that maximum: the error stays far below 1e-5 of (|A||B|)_ij."""
+    r = np.random.default_rng(3)
+    a = (r.random((32, 128), dtype=np.float32) * np.exp2(r.integers(-30, 1, size=(32, 128))).astype(np.float32)).astype(np.float32)
+    b = r.random((128, 40), dtype=np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    norm = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    assert (np.abs(fp16x3_model(a, b) - exact) / norm).max() <= 2.0 ** -20

@@ -349,6 +349,57 @@ def test_matmul_auto_is_the_guaranteed_mode(nb):
     assert rel_err(nb.nd.matmul(A, B, nb.BF16X3).toArray(), exp).max() <= 5e-5    # documented statistical mode
 
 
+@pytest.mark.parametrize("mkn", [(128, 128, 256), (384, 1024, 640), (1000, 520, 776), (333, 77, 129), (257, 1001, 67), (2048, 2048, 512)])
+def test_matmul_fp16x3_vs_cblas_sgemm(nb, mkn):
+    """FP16x3 (half parts of row-scaled A / column-scaled B): positive inputs, per-element relative error <= 1e-5."""
+    m, k, n = mkn
+    r = _rng(m + k + n + 1)
+    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.FP16X3, RTOL)
+
+
+def test_matmul_fp16x3_coherent_inputs_dynamic_range_and_specials(nb):
+    # the constant pair that costs BF16x3 1.5e-5
+    a = np.full((256, 512), 1.00390613, np.float32)
+    b = np.full((512, 256), 1.00390613, np.float32)
+    got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), nb.FP16X3).toArray()
+    assert rel_err(got, ORACLE.matmul(a, b)).max() <= RTOL
+    # rows / columns scaled by 2^-60 .. 2^60
+    r = _rng(42)
+    a2 = (r.random((256, 160), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(256, 1))).astype(np.float32)).astype(np.float32)
+    b2 = (r.random((160, 128), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(1, 128))).astype(np.float32)).astype(np.float32)
+    exp2 = ORACLE.matmul(a2, b2)
+    ok = np.isfinite(exp2) & (np.abs(exp2) > 1e-30)
+    got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu(), nb.FP16X3).toArray()
+    assert rel_err(got2[ok], exp2[ok]).max() <= RTOL
+    # inf / NaN propagate like cblas_sgemm
+    a3 = r.random((256, 128), dtype=np.float32)
+    b3 = r.random((128, 256), dtype=np.float32)
+    a3[3, 7] = np.inf; a3[100, 5] = -np.inf; b3[9, 200] = np.nan; b3[7, 50] = 0.0
+    exp3 = ORACLE.matmul(a3, b3)
+    got3 = nb.nd.matmul(nb.NDArray.array(a3).gpu(), nb.NDArray.array(b3).gpu(), nb.FP16X3).toArray()
+    np.testing.assert_array_equal(np.isnan(got3), np.isnan(exp3))
+    np.testing.assert_array_equal(np.isposinf(got3), np.isposinf(exp3))
+    np.testing.assert_array_equal(np.isneginf(got3), np.isneginf(exp3))
+    fin = np.isfinite(exp3)
+    assert rel_err(got3[fin], exp3[fin]).max() <= 2e-3
+    # signed inputs, norm-wise; batched with a shared B through the C-ABI
+    a4 = (r.random((640, 1024), dtype=np.float32) * 2 - 1).astype(np.float32)
+    b4 = (r.random((1024, 512), dtype=np.float32) * 2 - 1).astype(np.float32)
+    got4 = nb.nd.matmul(nb.NDArray.array(a4).gpu(), nb.NDArray.array(b4).gpu(), nb.FP16X3).toArray()
+    scale = (np.abs(a4).astype(np.float64) @ np.abs(b4).astype(np.float64)).max()
+    assert np.abs(got4.astype(np.float64) - ORACLE.matmul(a4, b4)).max() / scale <= RTOL
+    lib = nb.lib()
+    batch, M, N, K = 5, 256, 136, 200
+    a5, b5 = r.random((batch, M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
+    da, db, dc = _dev(nb, a5), _dev(nb, b5), _dev(nb, np.zeros((batch, M, N), np.float32))
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, 4) == 0, lib.nb200_last_error()
+    got5 = _fetch(nb, dc, (batch, M, N))
+    for i in range(batch):
+        assert rel_err(got5[i], ORACLE.matmul(a5[i], b5)).max() <= RTOL
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
 @pytest.mark.parametrize("prec", ["TF32X3", "BF16X3"])
 def test_matmul_signed_inputs_normwise_per_mode(nb, prec):
     r = _rng(13)
@@ -508,6 +559,25 @@ def test_sgemm_batched_shared_operand_and_many_batches(nb):
         got = _fetch(nb, dc, (batch, M, N))
         for i in range(batch):
             assert rel_err(got[i], ORACLE.matmul(a[i], b)).max() <= RTOL
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
+@pytest.mark.parametrize("prec", [0, 2, 4])
+def test_sgemm_batched_in_several_workspace_chunks(nb, prec, monkeypatch):
+    """A workspace budget of 1 MiB forces chunks of 2 + 2 + 1 matrices; B is shared (stride 0), i.e. split once with the
+    first chunk and reused by the shorter last one."""
+    lib = nb.lib()
+    r = _rng(33)
+    batch, M, N, K = 5, 256, 128, 512
+    a, b = r.random((batch, M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
+    da, db = _dev(nb, a), _dev(nb, b)
+    dc = _dev(nb, np.zeros((batch, M, N), np.float32))
+    monkeypatch.setenv("NB200_GEMM_WS_BUDGET_MB", "1")
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, prec) == 0, lib.nb200_last_error()
+    got = _fetch(nb, dc, (batch, M, N))
+    for i in range(batch):
+        assert rel_err(got[i], ORACLE.matmul(a[i], b)).max() <= RTOL
     for p in (da, db, dc):
         lib.nb200_free(p)
 
