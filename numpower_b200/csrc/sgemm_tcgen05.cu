@@ -298,14 +298,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, uint32_t fm
 
 // FP16x3 scaling: the power of two that brings a row's / column's largest finite magnitude (given as its bit pattern,
 // collected by absmax_*_kernel) into [2^14, 2^15), the top binade below fp16's 65504.  0 for empty / all-zero vectors.
-// The exponent is clamped to +-100 so that a row and a column exponent always combine into two representable power-of-two
-// factors (vectors whose largest magnitude is below 2^-86 are simply not brought all the way up).
+// The exponent lies in [-113, 100]: scaling UP is capped (vectors whose largest magnitude is below 2^-86 are simply not brought
+// all the way up) so that a row and a column exponent always combine into two representable power-of-two factors.
 __device__ __forceinline__ int scale_exp(unsigned int max_bits) {
     if (max_bits == 0u || max_bits >= 0x7F800000u) return 0;
-    const int e = 14 - ((int)(max_bits >> 23) - 127);          // subnormal maxima read as 2^-127: clamped below anyway
-    return e > 100 ? 100 : (e < -100 ? -100 : e);
+    const int e = 14 - ((int)(max_bits >> 23) - 127);          // >= -113; subnormal maxima read as 2^-127 and hit the cap
+    return e > 100 ? 100 : e;
 }
-// x * 2^e, |e| <= 200, as two exact multiplications (2^e itself may not be representable)
+// x * 2^e, -226 <= e <= 226, as two exact multiplications (2^e itself may not be representable)
 __device__ __forceinline__ float scale_pow2(float x, int e) {
     const int e1 = e / 2, e2 = e - e1;
     return x * __int_as_float((e1 + 127) << 23) * __int_as_float((e2 + 127) << 23);

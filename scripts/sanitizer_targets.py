@@ -37,5 +37,12 @@ m1, m2 = A(r.random((300, 136), dtype=np.float32)).gpu(), A(r.random((136, 200),
 nd.matmul(m1, m2).toArray(); nd.matmul(m1, m2, nb.TF32X1).toArray()            # tcgen05 path, ragged tiles
 nd.matmul(A(r.random((3, 130, 64), dtype=np.float32)).gpu(), A(r.random((3, 64, 260), dtype=np.float32)).gpu()).toArray()
 nd.matmul(A(r.random((5, 7), dtype=np.float32)).gpu(), A(r.random((7, 3), dtype=np.float32)).gpu()).toArray()   # SIMT path
+if os.environ.get("SANITIZE_16BIT", "1") == "1":
+    # 16-bit operand modes: odd K / N (repacking split), merged 256-column tile incl. the split tail, scaled half mode
+    m3, m4 = A(r.random((300, 137), dtype=np.float32)).gpu(), A(r.random((137, 201), dtype=np.float32)).gpu()
+    for prec in (nb.BF16X3, nb.FP16X3):
+        nd.matmul(m1, m2, prec).toArray(); nd.matmul(m3, m4, prec).toArray()
+        nd.matmul(A(r.random((512, 160), dtype=np.float32)).gpu(), A(r.random((160, 512), dtype=np.float32)).gpu(), prec).toArray()
+        nd.matmul(A(r.random((3, 260, 72), dtype=np.float32)).gpu(), A(r.random((3, 72, 264), dtype=np.float32)).gpu(), prec).toArray()
 nd.dot(m1, A(r.random(136, dtype=np.float32)).gpu()).toArray()
 print("sanitizer targets done;", nb.lib().nb200_launch_count(), "launches")
