@@ -43,7 +43,10 @@ struct GemmCfg {
     // A scaled per row and B scaled per column by powers of two (so that every row / column uses the top of fp16's
     // exponent range); the epilogue undoes the scaling with one exact scalbnf per output element.
     static constexpr bool SCALED = SCALED_;
-    static_assert(!SCALED_ || BF16_, "scaled mode uses the 16-bit operand path");
+    static_assert(!SCALED_ || (BF16_ && !MERGED_), "scaled mode: 16-bit operands, separate cross-term accumulator");
+    // SCALED stores the lo parts times 2^11 (so that they use the same fp16 binades as the hi parts); the cross-term
+    // accumulator is therefore 2^11 too large and is scaled back (exactly) when it is folded into the total.
+    static constexpr float CROSS_SCALE = SCALED_ ? 1.0f / 2048.0f : 1.0f;
     // MERGED (BF16x3, BN = 256): all three products of a chunk accumulate into ONE 256-column TMEM accumulator (2-deep
     // ring = all 512 columns) and the running total lives in the registers of eight epilogue warps.  Twice the flops
     // per staged byte and no cross-accumulator hand-off between tiles; costs 48 instead of 32 truncating accumulation
@@ -107,6 +110,10 @@ struct GemmParams {
     int64_t total_tiles;
     int a_batched, b_batched;  // 0: operand shared across the batch (coordinate 0)
     int early_cross;           // chunked epilogue: release the cross accumulator before writing C (A/B switch)
+    // Device-side gate: the kernel returns at once unless (*gate == gate_gen) == (gate_want != 0).  Lets the host enqueue both
+    // the FP16x3 product and its TF32x3 fallback and have the split pre-pass decide, without a host round trip.
+    const int *gate;
+    int gate_gen, gate_want;
     const unsigned int *row_max, *col_max;   // SCALED: |max| bit patterns per row of A / column of B (see scale_exp)
     const int *nonfinite;      // x3 modes: the split pre-pass stores nonfinite_gen here when an operand holds +-inf (see lo_part)
     int nonfinite_gen;         // this call's tag (a fresh value per call instead of a memset per call)
@@ -333,6 +340,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   const GemmParams p) {
     constexpr int CG = Cfg::CG, BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
     constexpr int PASSES = Cfg::PASSES, NPART = Cfg::NPART;
+    if (p.gate != nullptr && ((*reinterpret_cast<const volatile int *>(p.gate) == p.gate_gen) != (p.gate_want != 0))) return;   // uniform over the grid
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -688,7 +696,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             tmem_ld_32x32(t_cross + (uint32_t)(c * 32), x);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(m[q]), __uint_as_float(x[q])));
+                            for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(m[q]), __uint_as_float(x[q]) * Cfg::CROSS_SCALE));
                             store_row(c, m);
                         }
                         tc_fence_before();
@@ -706,6 +714,10 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             tmem_ld_32x32(t_cross + (uint32_t)(c * 32), m);
                             if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
                             tmem_ld_wait();
+                            if constexpr (Cfg::SCALED) {   // the lo parts are stored times 2^11 (exact power-of-two factor)
+#pragma unroll
+                                for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__uint_as_float(m[q]) * Cfg::CROSS_SCALE);
+                            }
                             if (!first) {
 #pragma unroll
                                 for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__fadd_rn(__uint_as_float(x[q]), __uint_as_float(m[q])));
@@ -768,7 +780,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 static int *nonfinite_flag() { return reinterpret_cast<int *>(ctx().dev_result) + 8; }
 int gemm_reset_nonfinite() {
     int &gen = ctx().nonfinite_gen;   // lives in the context: a re-initialised context starts from a cleared word again
-    if (gen == 0) NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, sizeof(int), ctx().stream));   // once: defined start value
+    if (gen == 0) NB_CUDA(cudaMemsetAsync(nonfinite_flag(), 0, 2 * sizeof(int), ctx().stream));   // once: defined start values ([1] = FP16x3 eligibility)
     if (++gen == 0x7FFFFFFF) gen = 1;
     return NB200_OK;
 }
@@ -780,7 +792,8 @@ __device__ __forceinline__ float lo_part(float a, int *nonfinite, int gen) {
 }
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
                                                          const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
-                                                         int *__restrict__ nonfinite, int gen) {
+                                                         int *__restrict__ nonfinite, int gen, const int *gate, int gate_want) {
+    if (gate != nullptr && ((*reinterpret_cast<const volatile int *>(gate) == gen) != (gate_want != 0))) return;   // see GemmParams::gate
     const int64_t g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;   // 4-element groups (spans are padded to a multiple of 4)
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= g0;
@@ -937,8 +950,11 @@ __global__ void __launch_bounds__(256) absmax_cols_kernel(const float *__restric
     for (int64_t r = r0; r < r1; r++) m = max(m, finite_abs_bits(ldg_stream(src + r * ld_in)));
     if (m) atomicMax(out + (int64_t)blockIdx.z * cols + c, m);
 }
-// a' = a * 2^e (e from the row or column |max|), hi = rn_f16(a'), lo = rn_f16(a' - hi); |a'| < 2^15, so nothing overflows.
-// Remainder <= 2^-22 |a'| for |a'| >= 2^-3 (normal lo part), <= 2^-25 absolute below (subnormal spacing).
+// a' = a * 2^e (e from the row or column |max|), hi = rn_f16(a'), lo = rn_f16((a' - hi) * 2^11); |a'| < 2^15 and
+// |a' - hi| * 2^11 <= 2^15, so nothing overflows.  As long as hi is a NORMAL half (|a'| >= 2^-14, i.e. the element lies within
+// 2^-28 of its row / column maximum) the remainder a' - hi - lo * 2^-11 is <= 2^-22 |a'|: the same class as TF32x3.  A
+// non-zero element below that (or a subnormal fp32) marks the call INELIGIBLE: nonfinite[1] = gen, and the gated TF32x3
+// fallback produces the result instead (see gemm_fp16x3).
 __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, unsigned short &l, int *nonfinite, int gen) {
     const unsigned int ab = __float_as_uint(a) & 0x7FFFFFFFu;
     if (ab >= 0x7F800000u) {                       // +-inf (flag: see the MMA issuer) or NaN: hi carries it, lo = 0
@@ -948,9 +964,10 @@ __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, uns
         return;
     }
     const float x = scale_pow2(a, e);
+    if (ab != 0u && fabsf(x) < 6.103515625e-05f) nonfinite[1] = gen;   // below 2^-14: hi would be a subnormal half
     const __half hh = __float2half_rn(x);
     h = __half_as_ushort(hh);
-    l = __half_as_ushort(__float2half_rn(x - __half2float(hh)));
+    l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.0f));
 }
 struct SplitSpanF16 {
     SplitSpan s;
@@ -1071,6 +1088,7 @@ struct GemmArgs {
     const float *A, *B, *A_lo, *B_lo;   // A/B are the "hi" (or raw) operands
     int64_t batch, M, N, K, lda, ldb, ldc, sA, sB, sC;
     const unsigned int *row_max = nullptr, *col_max = nullptr;   // FP16x3 scaling inputs (GemmCfg::SCALED)
+    int gate_want = -1;   // -1: ungated; 0: run unless the call was marked ineligible for FP16x3; 1: run only if it was
 };
 
 template <class Cfg>
@@ -1112,6 +1130,9 @@ static int launch_gemm(const GemmArgs &g) {
     static const int early = getenv("NB200_GEMM_EARLY_CROSS") ? atoi(getenv("NB200_GEMM_EARLY_CROSS")) : 1;
     p.early_cross = early;
     p.row_max = g.row_max; p.col_max = g.col_max;
+    p.gate = g.gate_want >= 0 ? nonfinite_flag() + 1 : nullptr;
+    p.gate_gen = ctx().nonfinite_gen;
+    p.gate_want = g.gate_want > 0 ? 1 : 0;
     p.nonfinite = nonfinite_flag();
     p.nonfinite_gen = ctx().nonfinite_gen;
     p.a_batched = g.sA != 0;
@@ -1143,12 +1164,14 @@ static int launch_gemm(const GemmArgs &g) {
     return NB200_OK;
 }
 
-static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1) {
+// gate: run only if the FP16x3 split of the same call marked it ineligible (nonfinite_flag()[1] == gen)
+static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1, bool gate = false) {
     int64_t groups = ((n0 + 3) >> 2) + ((n1 + 3) >> 2);
     if (groups == 0) return NB200_OK;
     int64_t blocks = (groups + 255) / 256;   // one 4-element group per thread, non-persistent (see common.cuh)
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag(), ctx().nonfinite_gen);
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag(), ctx().nonfinite_gen,
+                                                                  gate ? nonfinite_flag() + 1 : nullptr, 1);
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }
@@ -1296,34 +1319,40 @@ static int gemm_bf16x3(const GemmArgs &g) {
     return NB200_OK;
 }
 
-// FP16x3: the BF16x3 pipeline with IEEE-half parts of row-scaled A / column-scaled B (see GemmCfg::SCALED).
-// Pre-pass = |max| per row of A and per column of B (two read-only passes), then the scaled split; workspace layout:
-// [a_hi | a_lo | b_hi | b_lo | row_max (u32 per row) | col_max (u32 per column)].
+// FP16x3: the BF16x3 pipeline (256x128 pair tiles: separate cross-term accumulator) with IEEE-half parts of row-scaled A /
+// column-scaled B (GemmCfg::SCALED).  11-bit parts give the TF32x3 error class at the kind::f16 rate — provided every
+// non-zero element lies within 2^-28 of its row / column maximum (split_f16).  That is decided ON THE DEVICE by the split
+// pre-pass; the host enqueues both the gated FP16x3 GEMM and the gated TF32x3 fallback (lo-split + GEMM on the raw operands),
+// exactly one of which does the work.  Requires operands the TF32 path can read (tensor_path_ok).
+// Workspace: [a_hi | a_lo | b_hi | b_lo (half) | row_max | col_max (u32) | a_lo32 | b_lo32 (fp32 lo parts of the fallback)].
 static int gemm_fp16x3(const GemmArgs &g) {
     const int64_t lda = round8(g.K), ldb = round8(g.N);
     const int64_t per_a = g.M * lda, per_b = g.K * ldb;          // 16-bit elements per matrix
     int64_t chunk = g.batch;
     const int64_t budget = gemm_ws_budget();
     if (g.batch > 1) {
-        const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0));
+        const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0)) + 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0));
         if (per > 0 && per * chunk > budget) chunk = budget / per;
         if (chunk < 1) chunk = 1;
         if (chunk > 65535) chunk = 65535;                        // absmax_cols_kernel puts the batch on gridDim.z
     }
     { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
+    // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
+    const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
+    const int64_t rows_layout = (g.sA ? chunk : 1) * g.M, cols_layout = (g.sB ? chunk : 1) * g.N;
+    const int64_t na32 = round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)), nb32 = round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N));
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;   // matrices of each operand in this chunk
-        const int64_t n_rows = ba * g.M, n_cols = bb * g.N;
-        // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
-        const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
-        const int64_t rows_layout = (g.sA ? chunk : 1) * g.M, cols_layout = (g.sB ? chunk : 1) * g.N;
-        int rc = ensure_gemm_ws((na + nbb) * 4 + (rows_layout + cols_layout) * 4 + 1024);
+        const int64_t n_rows = ba * g.M;
+        int rc = ensure_gemm_ws((na + nbb) * 4 + (rows_layout + cols_layout) * 4 + (na32 + nb32) * 4 + 1024);
         if (rc != NB200_OK) return rc;
         __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);   // (16-bit storage; the contents are IEEE half)
         __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
         unsigned int *row_max = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);
         unsigned int *col_max = row_max + rows_layout;
+        float *a_lo32 = reinterpret_cast<float *>(col_max + cols_layout + ((4 - ((rows_layout + cols_layout) & 3)) & 3));   // keep 16-byte alignment
+        float *b_lo32 = a_lo32 + na32;
         const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
         const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once
         if (do_a) {
@@ -1333,9 +1362,8 @@ static int gemm_fp16x3(const GemmArgs &g) {
             NB_LAUNCH_CHECK();
         }
         if (do_b) {
-            NB_CUDA(cudaMemsetAsync(col_max, 0, (size_t)n_cols * 4, ctx().stream));
-            // enough row segments to fill the machine: columns / 256 blocks wide
-            const int64_t bx = (g.N + 255) / 256;
+            NB_CUDA(cudaMemsetAsync(col_max, 0, (size_t)(bb * g.N) * 4, ctx().stream));
+            const int64_t bx = (g.N + 255) / 256;                // row segments: enough blocks to fill the machine
             int64_t by = (4 * ctx().num_sms + bx * bb - 1) / (bx * bb);
             if (by < 1) by = 1;
             if (by > g.K) by = g.K;
@@ -1348,13 +1376,15 @@ static int gemm_fp16x3(const GemmArgs &g) {
         sa.max_bits = row_max; sa.by_col = 0;
         sb.s = make_span(b_src, b_hi, b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
         sb.max_bits = col_max; sb.by_col = 1;
-        const int64_t groups = sa.s.groups + sb.s.groups;
-        if (groups > 0) {
-            int64_t blocks = (groups + 255) / 256;
+        if (sa.s.groups + sb.s.groups > 0) {
+            int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
             if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
             split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
             NB_LAUNCH_CHECK();
         }
+        const int v = gemm_variant();
+        const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
+        // (1) FP16x3 product, runs unless the split marked the call ineligible
         GemmArgs c = g;
         c.batch = nb;
         c.A = reinterpret_cast<const float *>(a_hi); c.A_lo = reinterpret_cast<const float *>(a_lo);
@@ -1363,12 +1393,18 @@ static int gemm_fp16x3(const GemmArgs &g) {
         c.sA = g.sA ? per_a : 0; c.sB = g.sB ? per_b : 0;
         c.C = g.C + b0 * g.sC;
         c.row_max = row_max; c.col_max = col_max;
-        const int v = gemm_variant();
-        const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
-        const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? bf16_pair_bn(nb, g.M, g.N) : 128);
-        if (cg == 2 && bn == 256) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
-        else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
+        c.gate_want = 0;
+        rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
         if (rc != NB200_OK) return rc;
+        // (2) TF32x3 fallback on the raw operands, runs only if it did
+        const int64_t s_a = span(ba, g.sA, g.M, g.lda, g.K), s_b = span(bb, g.sB, g.K, g.ldb, g.N);
+        if ((rc = launch_split(a_src, a_lo32, do_a ? s_a : 0, b_src, b_lo32, do_b ? s_b : 0, true)) != NB200_OK) return rc;
+        GemmArgs f = g;
+        f.batch = nb;
+        f.A = a_src; f.A_lo = a_lo32; f.B = b_src; f.B_lo = b_lo32;
+        f.C = g.C + b0 * g.sC;
+        f.gate_want = 1;
+        if ((rc = dispatch_cfg<3>(f)) != NB200_OK) return rc;
     }
     return NB200_OK;
 }
@@ -1400,7 +1436,7 @@ static int gemm_impl(GemmArgs g, int precision) {
     const bool bf16_ok = g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
     static const bool force_simt = getenv("NB200_GEMM_FORCE_SIMT") != nullptr;   // debugging switch, read once
     if (precision == NB200_GEMM_BF16X3 && bf16_ok && !force_simt) return gemm_bf16x3(g);
-    if (precision == NB200_GEMM_FP16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g);
+    if (precision == NB200_GEMM_FP16X3 && bf16_ok && tensor_path_ok(g) && !force_simt) return gemm_fp16x3(g);
     if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);

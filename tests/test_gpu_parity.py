@@ -400,6 +400,36 @@ def test_matmul_fp16x3_coherent_inputs_dynamic_range_and_specials(nb):
         lib.nb200_free(p)
 
 
+def test_matmul_fp16x3_device_side_fallback_and_gather(nb):
+    """FP16x3 needs every non-zero element within 2^-28 of its row (A) / column (B) maximum; the split pre-pass decides on
+    the device and the gated TF32x3 fallback produces the result otherwise — bit-identical to a plain TF32X3 call."""
+    r = _rng(55)
+    a = r.random((384, 256), dtype=np.float32) + 0.25
+    b = r.random((256, 320), dtype=np.float32) + 0.25
+    A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
+    strict = nb.nd.matmul(A, B, nb.TF32X3).toArray()
+    fast = nb.nd.matmul(A, B, nb.FP16X3).toArray()
+    assert rel_err(fast, ORACLE.matmul(a, b)).max() <= RTOL
+    assert not np.array_equal(fast, strict)                  # eligible data really took the FP16 path
+    a_bad = a.copy()
+    a_bad[17, 5] = a_bad[17].max() * np.float32(2.0 ** -40)  # one element far below its row's maximum
+    Ab = nb.NDArray.array(a_bad).gpu()
+    np.testing.assert_array_equal(nb.nd.matmul(Ab, B, nb.FP16X3).toArray(), nb.nd.matmul(Ab, B, nb.TF32X3).toArray())
+    b_bad = b.copy()
+    b_bad[100, 7] = np.float32(1e-42)                        # subnormal fp32 in B
+    Bb = nb.NDArray.array(b_bad).gpu()
+    np.testing.assert_array_equal(nb.nd.matmul(A, Bb, nb.FP16X3).toArray(), nb.nd.matmul(A, Bb, nb.TF32X3).toArray())
+    # the next (eligible) call is not affected by the previous call's flag
+    np.testing.assert_array_equal(nb.nd.matmul(A, B, nb.FP16X3).toArray(), fast)
+    # gather through a permutation matrix: every output IS one input element, also the ones 2^-20 below their row maximum
+    g = (r.random((256, 256), dtype=np.float32) + 0.5) * np.exp2(r.integers(-20, 1, size=(256, 256))).astype(np.float32)
+    perm = r.permutation(256)
+    pm = np.zeros((256, 256), np.float32)
+    pm[perm, np.arange(256)] = 1.0
+    got = nb.nd.matmul(nb.NDArray.array(g.astype(np.float32)).gpu(), nb.NDArray.array(pm).gpu(), nb.FP16X3).toArray()
+    assert rel_err(got, g.astype(np.float32)[:, perm]).max() <= 2.0 ** -20
+
+
 @pytest.mark.parametrize("prec", ["TF32X3", "BF16X3"])
 def test_matmul_signed_inputs_normwise_per_mode(nb, prec):
     r = _rng(13)
