@@ -34,6 +34,13 @@ MATMUL_N = 4096
 SHARD_BATCH, SHARD_N = 128, 2048
 # DRAM traffic per launch from the committed ncu --set full captures (profiles/r1b_ncu_gemm_ew.csv, profiles/r1_ncu_*.csv)
 GEMM_AUTO = 3                      # include/nb200.h NB200_GEMM_AUTO
+# what NB200_GEMM_AUTO can resolve to (nb200_gemm_resolve_precision): name, dtype string, MMA kind of the roofline peak
+MODES = {
+    0: ("tf32x3", "tf32x3 (fp32 in/out, error-compensated 3-pass TF32, fp32 accumulate)", "tf32"),
+    2: ("bf16x3", "bf16x3 (fp32 in/out, operands split into 2 bf16 parts, 3 MMAs, fp32 accumulate)", "bf16"),
+    4: ("fp16x3", "fp16x3 (fp32 in/out, row/column-scaled operands split into 2 half parts, 3 MMAs, fp32 accumulate; "
+                  "TF32x3 fallback decided on the device)", "bf16"),
+}
 NCU_PIPE_ACTIVE_BF16X3 = 85.8      # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, profiles/r1e_ncu_gemm_bf16x3_merged.csv
 NCU_TRAFFIC = {"sgemm_tf32_kernel<2,256,3,bf16,merged>": 0.351e9, "split_bf16_flat_kernel": 0.215e9,
                "sgemm_tf32_kernel<2,128,3>": 1.171e9, "split_tf32_kernel": 0.215e9, "sgemm_tf32_kernel<2,256,1>": 0.388e9,
@@ -252,16 +259,20 @@ def run_single(args):
     launches0 = lib.nb200_launch_count()
     sampler = ClockSampler(0)
     sampler.start()
-    ms = B.time_steps(lambda: mm(GEMM_AUTO), args.steps, args.warmup)      # AUTO = TF32x3, the guaranteed-accuracy mode nd::matmul runs
+    auto_mode = int(lib.nb200_gemm_resolve_precision(GEMM_AUTO, n))        # the mode nd::matmul runs at this K
+    auto_name, auto_dtype, auto_kind = MODES[auto_mode]
+    ms = B.time_steps(lambda: mm(GEMM_AUTO), args.steps, args.warmup)
     launches = lib.nb200_launch_count() - launches0
     launches_timed = launches * args.steps // (args.steps + args.warmup)
-    ms_b3 = B.time_steps(lambda: mm(2), args.steps, args.warmup)           # opt-in BF16x3
-    ms_x1 = B.time_steps(lambda: mm(1), args.steps, args.warmup)
+    mode_ms = {auto_name: ms}
+    for name, prec in (("tf32x3", 0), ("bf16x3", 2), ("fp16x3", 4), ("tf32x1", 1)):
+        if name not in mode_ms:
+            mode_ms[name] = B.time_steps(lambda: mm(prec), args.steps, args.warmup)
     # accuracy of each mode against an fp64 product of 64 sampled rows (reported, the parity tests assert it)
     rows = torch.randperm(n, device="cuda", generator=g)[:64]
     truth = a[rows].double() @ b.double()
     mode_err = {}
-    for name, prec in (("bf16x3", 2), ("tf32x3", 0), ("tf32x1", 1)):
+    for name, prec in (("tf32x3", 0), ("bf16x3", 2), ("fp16x3", 4), ("tf32x1", 1)):
         mm(prec)
         mode_err[name] = float(((c[rows].double() - truth) / truth).abs().max())
     del truth
@@ -366,17 +377,27 @@ def run_single(args):
     del ab, bb_, cb
     bf16_peak = peaks["bf16_tflops"]         # measured cuBLAS bf16 rate: the kind::f16 MMA ceiling
     tf32_peak = bf16_peak / 2.0              # tcgen05 kind::tf32 runs at half the bf16 rate
+    auto_peak = tf32_peak if auto_kind == "tf32" else bf16_peak
     useful = flops / ms / 1e9
-    extras["matmul_4096_bf16x3_opt_in"] = {
-        "ms": ms_b3, "useful_tflops": flops / ms_b3 / 1e9, "pipe_executed_tflops": 3 * flops / ms_b3 / 1e9,
-        "pipe_frac_bf16_peak": 3 * flops / ms_b3 / 1e9 / bf16_peak, "tensor_pipe_active_pct_ncu": NCU_PIPE_ACTIVE_BF16X3,
-        "max_rel_err_vs_fp64": mode_err["bf16x3"],
-        "ncu_dram_traffic_bytes": NCU_TRAFFIC["sgemm_tf32_kernel<2,256,3,bf16,merged>"] + NCU_TRAFFIC["split_bf16_flat_kernel"],
-        "note": "NB200_GEMM_BF16X3 (per call, or NB200_GEMM_AUTO_MODE=bf16x3): two bf16 parts per operand, three kind::f16 MMAs; "
-                "statistical accuracy (zero-mean split error: fine on random data, up to ~3e-5 on coherent inputs), hence not the default"}
-    extras["matmul_4096_tf32x1"] = {"ms": ms_x1, "useful_tflops": flops / ms_x1 / 1e9, "frac_tf32_peak": flops / ms_x1 / 1e9 / tf32_peak,
-                                    "max_rel_err_vs_fp64": mode_err["tf32x1"],
+    mode_notes = {
+        "tf32x3": ("NB200_GEMM_TF32X3: three kind::tf32 MMAs per k-step, guaranteed bound (2^-19 per product); ncu tensor pipe active 93.1 %", tf32_peak),
+        "bf16x3": ("NB200_GEMM_BF16X3 (opt-in): two bf16 parts per operand, three kind::f16 MMAs; statistical accuracy (zero-mean split "
+                   "error: fine on random data, up to ~3e-5 on coherent inputs); ncu tensor pipe active 85.8 %, GEMM kernel 1686 TFLOP/s executed", bf16_peak),
+        "fp16x3": ("NB200_GEMM_FP16X3: half parts of row/column-scaled operands (22-bit elements inside a 2^28 window, TF32x3-class "
+                   "guaranteed bound), eligibility decided on the device by the split pre-pass, gated TF32x3 fallback otherwise", bf16_peak),
+    }
+    for name, (note, pk) in mode_notes.items():
+        t = mode_ms[name]
+        extras["matmul_4096_" + name] = {"ms": t, "useful_tflops": flops / t / 1e9, "pipe_executed_tflops": 3 * flops / t / 1e9,
+                                         "pipe_frac": 3 * flops / t / 1e9 / pk, "max_rel_err_vs_fp64": mode_err[name],
+                                         "is_auto": name == auto_name, "note": note}
+    extras["matmul_4096_tf32x1"] = {"ms": mode_ms["tf32x1"], "useful_tflops": flops / mode_ms["tf32x1"] / 1e9,
+                                    "frac_tf32_peak": flops / mode_ms["tf32x1"] / 1e9 / tf32_peak, "max_rel_err_vs_fp64": mode_err["tf32x1"],
                                     "note": "single-pass TF32 fast mode (not a parity mode)"}
+    traffic = {"tf32x3": NCU_TRAFFIC["sgemm_tf32_kernel<2,128,3>"] + NCU_TRAFFIC["split_tf32_kernel"],
+               "bf16x3": NCU_TRAFFIC["sgemm_tf32_kernel<2,256,3,bf16,merged>"] + NCU_TRAFFIC["split_bf16_flat_kernel"],
+               "fp16x3": None}[auto_name]
+    pipe_active = {"tf32x3": 93.1, "bf16x3": NCU_PIPE_ACTIVE_BF16X3, "fp16x3": None}[auto_name]
     cpu = cpu_baseline_matmul(n)
     try:
         extras["cpu_reference_hbm_configs"] = cpu_baseline_extras()
@@ -386,25 +407,26 @@ def run_single(args):
     line = {
         "metric": "nd::matmul useful TFLOP/s (fp32 in/out)", "value": useful, "unit": "TFLOP/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 in/out, error-compensated 3-pass TF32, fp32 accumulate)",
+        "scaling": "weak", "vs_baseline": None, "dtype": auto_dtype,
         "data": "synthetic",
-        "config": {"workload": f"nd::matmul {n}x{n} fp32 (BASELINE configs[1]) via nb200_sgemm, NB200_GEMM_AUTO (= TF32x3, guaranteed bound), "
-                               f"max rel err vs fp64 {mode_err['tf32x3']:.2e} (tolerance 1e-5)",
+        "config": {"workload": f"nd::matmul {n}x{n} fp32 (BASELINE configs[1]) via nb200_sgemm, NB200_GEMM_AUTO (= {auto_name}), "
+                               f"max rel err vs fp64 {mode_err[auto_name]:.2e} (tolerance 1e-5)",
                    "l2": "operands 128 MiB + result 64 MiB exceed the 126 MB L2; HBM-bound extras flush L2 between timed launches",
                    "timing": "CUDA events on the launching stream"},
-        "roofline": {"bound": "tensor", "achieved": useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": useful / tf32_peak,
-                     "traffic": NCU_TRAFFIC["sgemm_tf32_kernel<2,128,3>"] + NCU_TRAFFIC["split_tf32_kernel"],
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture committed as "
-                                       "profiles/r1b_ncu_gemm_ew.csv (GEMM kernel 1.171 GB + lo-split pre-pass 0.215 GB, measured before the "
-                                       "banded tile raster; algorithmic minimum 3 x 64 MiB = 0.201 GB: the GEMM is tensor-bound, re-reads are L2-served)",
-                     "tensor_pipe_active_pct_ncu": 93.1, "peak_source": peaks["_source"] + ": bf16_tflops / 2 (tf32 = half the bf16 MMA rate)",
-                     "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / tf32_peak,
+        "roofline": {"bound": "tensor", "achieved": useful, "peak": auto_peak, "unit": "TFLOP/s", "frac": useful / auto_peak,
+                     "traffic": traffic,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch (GEMM kernel + split pre-pass) from the ncu --set full "
+                                       "captures under profiles/ (r1b_ncu_gemm_ew.csv for TF32x3, r1e_ncu_gemm_bf16x3_merged.csv for BF16x3; the FP16x3 "
+                                       "pipeline has no capture yet: null); algorithmic minimum 3 x 64 MiB = 0.201 GB: the GEMM is tensor-bound, re-reads are L2-served",
+                     "tensor_pipe_active_pct_ncu": pipe_active,
+                     "peak_source": peaks["_source"] + (": bf16_tflops / 2 (tf32 = half the bf16 MMA rate)" if auto_kind == "tf32" else ": bf16_tflops (cuBLAS bf16 8192^3)"),
+                     "pipe_executed_tflops": 3 * useful, "pipe_frac": 3 * useful / auto_peak,
                      "note": "achieved counts the algorithmic 2*M*N*K flops of the fp32 product; the error-compensated scheme executes 3x that "
                              "on the tensor pipe (pipe_frac), so frac is bounded by 1/3"},
         "cpu_baseline": cpu,
         "e2e": {"value": flops / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": ms_e2e, "steps": e2e_steps, "api": "nb200_sgemm_host (pinned host buffers, pipelined H2D/compute/D2H)",
-                "max_rel_diff_vs_resident": e2e_err, "pcie_measured": pcie, "mode": "NB200_GEMM_AUTO (TF32x3)",
+                "max_rel_diff_vs_resident": e2e_err, "pcie_measured": pcie, "mode": "NB200_GEMM_AUTO (" + ("tf32x3: the host pipeline keeps the TF32x3 kernels" if auto_name == "fp16x3" else auto_name) + ")",
                 "pcie_bound_ms": 2 * nbytes / pcie["h2d_GBps"] / 1e6,
                 "note": "H2D of A and B (128 MiB) is the floor: D2H of C and the GEMM overlap it"},
         "gpu_launches": int(launches_timed),
@@ -477,19 +499,20 @@ def run_multi(args):
     ms_e2e = float(t2.item())
 
     if rank == 0:
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        auto_name, auto_dtype, auto_kind = MODES[int(lib.nb200_gemm_resolve_precision(GEMM_AUTO, n))]
+        tf32_peak = peaks["bf16_tflops_sustained"] / (2.0 if auto_kind == "tf32" else 1.0)
         total = world * flops_rank / ms / 1e9
         per_gpu = flops_rank / ms / 1e9
         line = {
             "metric": "nd::matmul useful TFLOP/s (fp32 in/out)", "value": total, "unit": "TFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32 in/out, error-compensated 3-pass TF32, fp32 accumulate)",
+            "scaling": "weak", "vs_baseline": None, "dtype": auto_dtype,
             "data": "synthetic",
             "config": {"workload": f"batched nd::matmul, {nb_} x ({n}x{n}) per GPU, batch sharded across {world} GPUs "
                                    f"(N=8 is BASELINE configs[4] 1024x(2048x2048)); resident shards, no data-path collective",
                        "l2": f"per-rank operands {2 * nb_ * n * n * 4 >> 20} MiB exceed L2", "timing": "CUDA events, max over ranks (NCCL all-reduce of the times)"},
             "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": tf32_peak, "unit": "TFLOP/s", "frac": per_gpu / tf32_peak,
-                         "traffic": None, "peak_source": peaks["_source"] + ": bf16_tflops_sustained / 2", "pipe_executed_tflops": 3 * per_gpu,
+                         "traffic": None, "peak_source": peaks["_source"] + (": bf16_tflops_sustained / 2" if auto_kind == "tf32" else ": bf16_tflops_sustained"), "pipe_executed_tflops": 3 * per_gpu,
                          "pipe_frac": 3 * per_gpu / tf32_peak, "note": "per-GPU figures; frac counts the algorithmic flops (bounded by 1/3), pipe_frac the executed ones"},
             "e2e": {"value": world * e2e_batch * 2.0 * n ** 3 / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes,
                     "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e, "note": f"{e2e_batch} matrices per rank per step, pinned host buffers, each rank over its own PCIe link"},

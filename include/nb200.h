@@ -188,6 +188,9 @@ int nb200_sgemm_host(float *C_host, const float *A_host, const float *B_host, in
 /* scratch the 3xTF32 split needs for an (M,N,K,batch) problem; allocated lazily from the
  * context and reused (bytes reported for capacity planning). */
 int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes);
+/* The concrete mode NB200_GEMM_AUTO (or any other value, returned unchanged) stands for at inner dimension K
+ * (default policy, NB200_GEMM_AUTO_MODE override).  Shapes / alignments a mode cannot serve still fall back to TF32X3. */
+int nb200_gemm_resolve_precision(int precision, int64_t K);
 /* y[rows] = A[rows,cols]·x[cols] — replaces cuda_float_multiply_matrix_vector (cuda_math.h:62). */
 int nb200_gemv(float *y, const float *A, const float *x, int64_t rows, int64_t cols);
 /* out[cols,rows] = in[rows,cols]^T, out != in — replaces cuda_float_transpose (cuda_math.h:77). */

@@ -916,6 +916,9 @@ __device__ __forceinline__ unsigned int finite_abs_bits(float v) {
     const unsigned int b = __float_as_uint(v) & 0x7FFFFFFFu;
     return b < 0x7F800000u ? b : 0u;
 }
+__device__ __forceinline__ unsigned int abs4_bits(const float4 &v) {
+    return max(max(finite_abs_bits(v.x), finite_abs_bits(v.y)), max(finite_abs_bits(v.z), finite_abs_bits(v.w)));
+}
 // one warp per row; rows = batch * rows_per
 __global__ void __launch_bounds__(256) absmax_rows_kernel(const float *__restrict__ in, int64_t rows_per, int64_t nrows, int64_t cols,
                                                           int64_t ld_in, int64_t stride_in, unsigned int *__restrict__ out) {
@@ -926,10 +929,13 @@ __global__ void __launch_bounds__(256) absmax_rows_kernel(const float *__restric
         unsigned int m = 0;
         if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (cols & 3) == 0) {
             const float4 *s4 = reinterpret_cast<const float4 *>(src);
-            for (int64_t c = lane; c < (cols >> 2); c += 32) {
-                const float4 v = ldg_stream(s4 + c);
-                m = max(max(m, finite_abs_bits(v.x)), max(finite_abs_bits(v.y), max(finite_abs_bits(v.z), finite_abs_bits(v.w))));
+            const int64_t n4 = cols >> 2;
+            int64_t c = lane;
+            for (; c + 96 < n4; c += 128) {   // four independent 16-byte loads in flight per lane
+                const float4 v0 = ldg_stream(s4 + c), v1 = ldg_stream(s4 + c + 32), v2 = ldg_stream(s4 + c + 64), v3 = ldg_stream(s4 + c + 96);
+                m = max(m, max(max(abs4_bits(v0), abs4_bits(v1)), max(abs4_bits(v2), abs4_bits(v3))));
             }
+            for (; c < n4; c += 32) m = max(m, abs4_bits(ldg_stream(s4 + c)));
         } else {
             for (int64_t c = lane; c < cols; c += 32) m = max(m, finite_abs_bits(ldg_stream(src + c)));
         }
@@ -949,6 +955,35 @@ __global__ void __launch_bounds__(256) absmax_cols_kernel(const float *__restric
     unsigned int m = 0;
     for (int64_t r = r0; r < r1; r++) m = max(m, finite_abs_bits(ldg_stream(src + r * ld_in)));
     if (m) atomicMax(out + (int64_t)blockIdx.z * cols + c, m);
+}
+// same, four adjacent columns per thread with 16-byte loads (needs 16-byte aligned rows: ld % 4 == 0, cols % 4 == 0)
+__global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                                                           int64_t stride_in, unsigned int *__restrict__ out) {
+    const int64_t c4 = (int64_t)blockIdx.x * 256 + threadIdx.x;   // column group
+    if (c4 * 4 >= cols) return;
+    const float4 *src = reinterpret_cast<const float4 *>(in + (int64_t)blockIdx.z * stride_in) + c4;
+    const int64_t ld4 = ld_in >> 2;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+    unsigned int mx = 0, my = 0, mz = 0, mw = 0;
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {   // four independent 16-byte loads in flight per thread
+        const float4 v0 = ldg_stream(src + r * ld4), v1 = ldg_stream(src + (r + 1) * ld4), v2 = ldg_stream(src + (r + 2) * ld4),
+                     v3 = ldg_stream(src + (r + 3) * ld4);
+        mx = max(mx, max(max(finite_abs_bits(v0.x), finite_abs_bits(v1.x)), max(finite_abs_bits(v2.x), finite_abs_bits(v3.x))));
+        my = max(my, max(max(finite_abs_bits(v0.y), finite_abs_bits(v1.y)), max(finite_abs_bits(v2.y), finite_abs_bits(v3.y))));
+        mz = max(mz, max(max(finite_abs_bits(v0.z), finite_abs_bits(v1.z)), max(finite_abs_bits(v2.z), finite_abs_bits(v3.z))));
+        mw = max(mw, max(max(finite_abs_bits(v0.w), finite_abs_bits(v1.w)), max(finite_abs_bits(v2.w), finite_abs_bits(v3.w))));
+    }
+    for (; r < r1; r++) {
+        const float4 v = ldg_stream(src + r * ld4);
+        mx = max(mx, finite_abs_bits(v.x)); my = max(my, finite_abs_bits(v.y)); mz = max(mz, finite_abs_bits(v.z)); mw = max(mw, finite_abs_bits(v.w));
+    }
+    unsigned int *o = out + (int64_t)blockIdx.z * cols + c4 * 4;
+    if (mx) atomicMax(o, mx);
+    if (my) atomicMax(o + 1, my);
+    if (mz) atomicMax(o + 2, mz);
+    if (mw) atomicMax(o + 3, mw);
 }
 // a' = a * 2^e (e from the row or column |max|), hi = rn_f16(a'), lo = rn_f16((a' - hi) * 2^11); |a'| < 2^15 and
 // |a' - hi| * 2^11 <= 2^15, so nothing overflows.  As long as hi is a NORMAL half (|a'| >= 2^-14, i.e. the element lies within
@@ -1003,6 +1038,61 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, c
         lv.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16); lv.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
         *reinterpret_cast<uint2 *>(s.hi + o) = hv;
         *reinterpret_cast<uint2 *>(s.lo + o) = lv;
+    }
+}
+
+// Contiguous operands with cols % 8 == 0: eight elements per thread, 2 x 16-byte loads, 2 x 16-byte stores, packed conversions;
+// any +-inf / NaN in the group sends it through the careful per-element path.
+__global__ void __launch_bounds__(256) split_f16_flat_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int64_t g0, int64_t g1,
+                                                             int *__restrict__ nonfinite, int gen) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
+        const bool second = i >= g0;
+        const SplitSpanF16 &sp = second ? s1 : s0;
+        const int64_t j = second ? i - g0 : i;
+        const int64_t gpr8 = sp.s.cols >> 3;                    // 8-element groups per row
+        const int64_t r = j / gpr8, c = (j - r * gpr8) << 3;   // global row (over the batch), first column
+        const float4 *src = reinterpret_cast<const float4 *>(sp.s.in) + 2 * j;
+        const float4 a = ld_ew(src), b = ld_ew(src + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        int ex[8];
+        if (sp.by_col) {
+            const uint4 *mb = reinterpret_cast<const uint4 *>(sp.max_bits + (r / sp.s.rows_per) * sp.s.cols + c);
+            const uint4 m0 = mb[0], m1 = mb[1];
+            ex[0] = scale_exp(m0.x); ex[1] = scale_exp(m0.y); ex[2] = scale_exp(m0.z); ex[3] = scale_exp(m0.w);
+            ex[4] = scale_exp(m1.x); ex[5] = scale_exp(m1.y); ex[6] = scale_exp(m1.z); ex[7] = scale_exp(m1.w);
+        } else {
+            const int e = scale_exp(sp.max_bits[r]);
+#pragma unroll
+            for (int q = 0; q < 8; q++) ex[q] = e;
+        }
+        uint32_t hp[4], lp[4], special = 0;
+        bool small = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float x0 = scale_pow2(v[2 * q], ex[2 * q]), x1 = scale_pow2(v[2 * q + 1], ex[2 * q + 1]);
+            special |= (uint32_t)((__float_as_uint(v[2 * q]) & 0x7F800000u) == 0x7F800000u) |
+                       (uint32_t)((__float_as_uint(v[2 * q + 1]) & 0x7F800000u) == 0x7F800000u);   // inf / NaN in the group?
+            small |= (x0 != 0.f && fabsf(x0) < 6.103515625e-05f) | (x1 != 0.f && fabsf(x1) < 6.103515625e-05f);
+            const __half2 h2 = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+            hp[q] = *reinterpret_cast<const uint32_t *>(&h2);
+            lp[q] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        if (special) {                                   // careful per-element path (flags +-inf, keeps NaN)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                unsigned short h0, l0, h1, l1;
+                split_f16(v[2 * q], ex[2 * q], h0, l0, nonfinite, gen);
+                split_f16(v[2 * q + 1], ex[2 * q + 1], h1, l1, nonfinite, gen);
+                hp[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                lp[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+        } else if (small) {
+            nonfinite[1] = gen;                          // a non-zero element below the FP16x3 window: the fallback will run
+        }
+        reinterpret_cast<uint4 *>(sp.s.hi)[j] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        reinterpret_cast<uint4 *>(sp.s.lo)[j] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
 }
 
@@ -1170,6 +1260,7 @@ static int launch_split(const float *in0, float *lo0, int64_t n0, const float *i
     if (groups == 0) return NB200_OK;
     int64_t blocks = (groups + 255) / 256;   // one 4-element group per thread, non-persistent (see common.cuh)
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+    if (gate && blocks > (int64_t)ctx().num_sms * 16) blocks = (int64_t)ctx().num_sms * 16;   // normally exits at once: keep the launch small (grid-stride loop)
     split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag(), ctx().nonfinite_gen,
                                                                   gate ? nonfinite_flag() + 1 : nullptr, 1);
     NB_LAUNCH_CHECK();
@@ -1339,7 +1430,7 @@ static int gemm_fp16x3(const GemmArgs &g) {
     { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
     // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
     const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
-    const int64_t rows_layout = (g.sA ? chunk : 1) * g.M, cols_layout = (g.sB ? chunk : 1) * g.N;
+    const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);   // 16-byte aligned sub-arrays
     const int64_t na32 = round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)), nb32 = round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N));
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
@@ -1351,7 +1442,7 @@ static int gemm_fp16x3(const GemmArgs &g) {
         __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
         unsigned int *row_max = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);
         unsigned int *col_max = row_max + rows_layout;
-        float *a_lo32 = reinterpret_cast<float *>(col_max + cols_layout + ((4 - ((rows_layout + cols_layout) & 3)) & 3));   // keep 16-byte alignment
+        float *a_lo32 = reinterpret_cast<float *>(col_max + cols_layout);
         float *b_lo32 = a_lo32 + na32;
         const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
         const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once
@@ -1363,12 +1454,16 @@ static int gemm_fp16x3(const GemmArgs &g) {
         }
         if (do_b) {
             NB_CUDA(cudaMemsetAsync(col_max, 0, (size_t)(bb * g.N) * 4, ctx().stream));
-            const int64_t bx = (g.N + 255) / 256;                // row segments: enough blocks to fill the machine
-            int64_t by = (4 * ctx().num_sms + bx * bb - 1) / (bx * bb);
+            const bool vec4 = (g.N % 4 == 0);                     // (ldb % 4 == 0 and 16-byte bases: tensor_path_ok)
+            const int64_t bx = vec4 ? (g.N / 4 + 255) / 256 : (g.N + 255) / 256;
+            int64_t by = (8 * ctx().num_sms + bx * bb - 1) / (bx * bb);   // row segments: ~8 blocks per SM in total
             if (by < 1) by = 1;
-            if (by > g.K) by = g.K;
+            if (by > (g.K + 3) / 4) by = (g.K + 3) / 4;
             if (by > 65535) by = 65535;
-            absmax_cols_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
+            if (vec4)
+                absmax_cols4_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
+            else
+                absmax_cols_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
             NB_LAUNCH_CHECK();
         }
         SplitSpanF16 sa, sb;
@@ -1376,7 +1471,13 @@ static int gemm_fp16x3(const GemmArgs &g) {
         sa.max_bits = row_max; sa.by_col = 0;
         sb.s = make_span(b_src, b_hi, b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
         sb.max_bits = col_max; sb.by_col = 1;
-        if (sa.s.groups + sb.s.groups > 0) {
+        if ((sa.s.flat || sa.s.groups == 0) && (sb.s.flat || sb.s.groups == 0) && sa.s.groups + sb.s.groups > 0) {
+            const int64_t g0 = sa.s.groups >> 1, g1 = sb.s.groups >> 1;   // 8-element groups
+            int64_t blocks = (g0 + g1 + 255) / 256;
+            if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+            split_f16_flat_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, g0, g1, nonfinite_flag(), ctx().nonfinite_gen);
+            NB_LAUNCH_CHECK();
+        } else if (sa.s.groups + sb.s.groups > 0) {
             int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
             if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
             split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
@@ -1540,12 +1641,14 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
     return gemm_impl(g, precision);
 }
 
+extern "C" int nb200_gemm_resolve_precision(int precision, int64_t K) { return gemm_resolve_precision(precision, K); }
+
 extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes) {
     if (!bytes) return set_error(NB200_EINVAL, "null argument");
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
     precision = gemm_resolve_precision(precision, K);
     int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024
-                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * (M + N) + 1024
+                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * (round4(M) + round4(N)) + 4 * (round4(M * K) + round4(K * N)) + 1024
                                                  : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = gemm_ws_budget();
