@@ -98,10 +98,13 @@ enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
  *   2^-16 + 2*2^-17, zero-mean - measured max rel. error 1.2-2.5e-6 vs fp64 on random data from
  *   K = 77 to 8192, but coherent inputs (constant matrices) can reach ~3e-5.  Opt-in per call, or
  *   NB200_GEMM_AUTO_MODE=bf16x3 lets AUTO choose it for K >= 128.  Accepts any alignment / ld.
- * FP16X3 (experimental, opt-in): the BF16X3 pipeline with IEEE-half parts (11-bit significands:
- *   TF32X3-class split error, no coherent-input problem) of A scaled per row and B scaled per
- *   column by powers of two; the epilogue undoes the scaling exactly.  Norm-wise guarantee:
- *   |E_ij| <= 3*2^-22 (|A||B|)_ij + 2^-38 K max|A_i,:| max|B_:,j|.
+ * FP16X3 (experimental, opt-in; also NB200_GEMM_AUTO_MODE=fp16x3): the same pipeline with IEEE-half
+ *   parts of A scaled per row and B scaled per column by powers of two (lo parts stored x2^11; the
+ *   epilogue undoes all scaling exactly).  Every non-zero element within 2^-28 of its row / column
+ *   maximum keeps a 2^-22 relative split error: TF32X3-class guaranteed bound, no coherent-input
+ *   problem.  The split pre-pass checks that window ON THE DEVICE; if an element falls outside, the
+ *   gated TF32X3 fallback enqueued with the call produces the result instead (bit-identical to a
+ *   TF32X3 call).  Needs operands the TF32 path can read (16-byte aligned, ld % 4 == 0).
  * AUTO: see above. */
 enum nb200_gemm_precision { NB200_GEMM_TF32X3 = 0, NB200_GEMM_TF32X1 = 1, NB200_GEMM_BF16X3 = 2, NB200_GEMM_AUTO = 3,
                             NB200_GEMM_FP16X3 = 4 };

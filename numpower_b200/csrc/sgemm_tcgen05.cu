@@ -572,9 +572,22 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const int64_t col = col0 + c * 32;
                 if (row < p.M) {
                     if constexpr (Cfg::SCALED) {
+                        if (vec_ok && col + 32 <= p.N && (p.N & 3) == 0) {   // column maxima and C rows 16-byte aligned
+                            const uint4 *mb = reinterpret_cast<const uint4 *>(cmax + col);
+                            float4 *dst = reinterpret_cast<float4 *>(crow + col);
 #pragma unroll
-                        for (int q = 0; q < 32; q++)
-                            if (col + q < p.N) crow[col + q] = scale_pow2(__uint_as_float(v[q]), -(e_row + scale_exp(cmax[col + q])));
+                            for (int q = 0; q < 8; q++) {
+                                const uint4 m4 = __ldg(mb + q);
+                                dst[q] = make_float4(scale_pow2(__uint_as_float(v[4 * q]), -(e_row + scale_exp(m4.x))),
+                                                     scale_pow2(__uint_as_float(v[4 * q + 1]), -(e_row + scale_exp(m4.y))),
+                                                     scale_pow2(__uint_as_float(v[4 * q + 2]), -(e_row + scale_exp(m4.z))),
+                                                     scale_pow2(__uint_as_float(v[4 * q + 3]), -(e_row + scale_exp(m4.w))));
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; q++)
+                                if (col + q < p.N) crow[col + q] = scale_pow2(__uint_as_float(v[q]), -(e_row + scale_exp(cmax[col + q])));
+                        }
                     } else if (vec_ok && col + 32 <= p.N) {
                         float4 *dst = reinterpret_cast<float4 *>(crow + col);
 #pragma unroll
