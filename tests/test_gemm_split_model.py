@@ -198,3 +198,42 @@ def test_fp16x3_eligibility_window_and_gather():
     assert (np.abs(got - a[:, perm].astype(np.float64)) / a[:, perm]).max() <= 2.0 ** -21
     a[3, 4] = a[3].max() * np.float32(2.0 ** -40)
     assert fp16x3_model(a, pm) is None
+
+
+def fp16x3_model_with_fixup(a, b):
+    """Round-2 plan for out-of-window elements: keep the call on the FP16 path and repair the
+    few elements the half parts cannot represent with a sparse rank-1 update.  For such an element of A the split leaves a
+    residual d = a_ik - (hi + lo * 2^-11) / 2^e_i, and C[i, :] += d * B[k, :] (fp32 axpy) restores its full contribution;
+    symmetrically C[:, j] += A[:, k] * d for an element of B.  Returns (C, number of repaired elements)."""
+    d64 = np.float64
+    ea = scale_exp(np.abs(a).max(axis=1))[:, None]
+    eb = scale_exp(np.abs(b).max(axis=0))[None, :]
+    ah, al, _ = split_f16_scaled(a, ea)
+    bh, bl, _ = split_f16_scaled(b, eb)
+    c = np.ldexp(ah @ bh + ah @ bl + al @ bh, -(ea + eb))
+    ra = a.astype(d64) - np.ldexp(ah + al, -ea)                  # what the half parts missed
+    rb = b.astype(d64) - np.ldexp(bh + bl, -eb)
+    xa, xb = np.ldexp(a.astype(d64), ea), np.ldexp(b.astype(d64), eb)
+    out_a = (xa != 0) & (np.abs(xa) < 2.0 ** -14)                # the window test of split_f16()
+    out_b = (xb != 0) & (np.abs(xb) < 2.0 ** -14)
+    for i, k in zip(*np.nonzero(out_a)):
+        c[i, :] += ra[i, k] * b[k, :].astype(d64)
+    for k, j in zip(*np.nonzero(out_b)):
+        c[:, j] += a[:, k].astype(d64) * rb[k, j]
+    return c, int(out_a.sum() + out_b.sum())
+
+
+def test_fp16x3_sparse_fixup_model_restores_out_of_window_elements():
+    r = np.random.default_rng(11)
+    a = (r.random((48, 96), dtype=np.float32) + 0.5).astype(np.float32)
+    b = (r.random((96, 40), dtype=np.float32) + 0.5).astype(np.float32)
+    # out-of-window elements whose products dominate an output: the partner column is zero everywhere else
+    a[5, 7] = np.float32(2.0 ** -40)
+    b[:, 3] = 0.0
+    b[7, 3] = 1.0                                                # C[5, 3] == a[5, 7] exactly
+    b[20, 9] = np.float32(3.0 * 2.0 ** -45)                      # an out-of-window element of B
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    assert fp16x3_model(a, b) is None                            # today: the gated TF32x3 fallback
+    c, repaired = fp16x3_model_with_fixup(a, b)
+    assert repaired == 2
+    assert (np.abs(c - exact) / np.abs(exact)).max() <= 2.0 ** -20
