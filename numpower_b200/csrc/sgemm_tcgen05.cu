@@ -1003,7 +1003,17 @@ __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restri
 // 2^-28 of its row / column maximum) the remainder a' - hi - lo * 2^-11 is <= 2^-22 |a'|: the same class as TF32x3.  A
 // non-zero element below that (or a subnormal fp32) marks the call INELIGIBLE: nonfinite[1] = gen, and the gated TF32x3
 // fallback produces the result instead (see gemm_fp16x3).
-__device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, unsigned short &l, int *nonfinite, int gen) {
+// Out-of-window elements (see above) do not abandon the call as long as there are few of them: the split records
+// (row, column, d) with d = a - (hi + lo * 2^-11) * 2^-e, the part of the element the half pair cannot hold, and
+// fp16_fixup_kernel adds d times the partner row / column to C after the GEMM (a sparse rank-1 repair).  Only when a
+// record list overflows is the call marked ineligible (nonfinite[1] = gen) and left to the gated TF32x3 fallback.
+constexpr int FIX_CAP = 4096;              // records per operand and chunk
+struct FixList {
+    unsigned int *count;                   // device counter (reset by the host before the operand is split)
+    int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
+};
+__device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, unsigned short &l, int *nonfinite, int gen,
+                                          const FixList &fix, int64_t row, int64_t col) {
     const unsigned int ab = __float_as_uint(a) & 0x7FFFFFFFu;
     if (ab >= 0x7F800000u) {                       // +-inf (flag: see the MMA issuer) or NaN: hi carries it, lo = 0
         if (ab == 0x7F800000u) *nonfinite = gen;
@@ -1012,15 +1022,22 @@ __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, uns
         return;
     }
     const float x = scale_pow2(a, e);
-    if (ab != 0u && fabsf(x) < 6.103515625e-05f) nonfinite[1] = gen;   // below 2^-14: hi would be a subnormal half
     const __half hh = __float2half_rn(x);
+    const __half ll = __float2half_rn((x - __half2float(hh)) * 2048.0f);
     h = __half_as_ushort(hh);
-    l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.0f));
+    l = __half_as_ushort(ll);
+    if (ab != 0u && fabsf(x) < 6.103515625e-05f) {  // below 2^-14: hi is a subnormal half -> repair record
+        const float held = scale_pow2(__half2float(hh) + __half2float(ll) * (1.0f / 2048.0f), -e);
+        const unsigned int idx = atomicAdd(fix.count, 1u);
+        if (idx < (unsigned int)FIX_CAP && row < 0x7FFFFFFF) fix.recs[idx] = make_int4((int)row, (int)col, __float_as_int(a - held), 0);
+        else nonfinite[1] = gen;
+    }
 }
 struct SplitSpanF16 {
     SplitSpan s;
     const unsigned int *max_bits;   // per row (by_col == 0: index = output row) or per column (index = batch * cols + column)
     int by_col;
+    FixList fix;
 };
 __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int *__restrict__ nonfinite, int gen) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.s.groups + s1.s.groups; i += (int64_t)gridDim.x * 256) {
@@ -1043,7 +1060,7 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, c
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int ex = sp.by_col ? (c + e < s.cols ? scale_exp(sp.max_bits[b * s.cols + c + e]) : 0) : e_row;
-            split_f16(v[e], ex, h[e], l[e], nonfinite, gen);
+            split_f16(v[e], ex, h[e], l[e], nonfinite, gen, sp.fix, r, c + e);
         }
         const int64_t o = r * s.ld_out + c;
         uint2 hv, lv;
@@ -1092,20 +1109,49 @@ __global__ void __launch_bounds__(256) split_f16_flat_kernel(const SplitSpanF16 
             hp[q] = *reinterpret_cast<const uint32_t *>(&h2);
             lp[q] = *reinterpret_cast<const uint32_t *>(&l2);
         }
-        if (special) {                                   // careful per-element path (flags +-inf, keeps NaN)
+        if (special || small) {                          // careful per-element path (flags +-inf, keeps NaN, records out-of-window elements)
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 unsigned short h0, l0, h1, l1;
-                split_f16(v[2 * q], ex[2 * q], h0, l0, nonfinite, gen);
-                split_f16(v[2 * q + 1], ex[2 * q + 1], h1, l1, nonfinite, gen);
+                split_f16(v[2 * q], ex[2 * q], h0, l0, nonfinite, gen, sp.fix, r, c + 2 * q);
+                split_f16(v[2 * q + 1], ex[2 * q + 1], h1, l1, nonfinite, gen, sp.fix, r, c + 2 * q + 1);
                 hp[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
                 lp[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
-        } else if (small) {
-            nonfinite[1] = gen;                          // a non-zero element below the FP16x3 window: the fallback will run
         }
         reinterpret_cast<uint4 *>(sp.s.hi)[j] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         reinterpret_cast<uint4 *>(sp.s.lo)[j] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+}
+
+// Sparse repair after the FP16x3 GEMM (see split_f16): one block per record.  A-record (i, k, d): C[i, :] += d * B[k, :];
+// B-record (k, j, d): C[:, j] += A[:, k] * d.  A record of an operand that is shared by the whole batch applies to every
+// matrix of the batch.  atomicAdd: several records may touch the same element.  Skipped when the call went to the fallback.
+__global__ void __launch_bounds__(256) fp16_fixup_kernel(float *__restrict__ C, const float *__restrict__ A, const float *__restrict__ B,
+                                                         int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                                         int64_t ldc, int64_t sA, int64_t sB, int64_t sC, FixList fa, FixList fb,
+                                                         const int *gate, int gen) {
+    if (*reinterpret_cast<const volatile int *>(gate) == gen) return;
+    const unsigned int na = min(*fa.count, (unsigned int)FIX_CAP), nb = min(*fb.count, (unsigned int)FIX_CAP);
+    for (unsigned int rec = blockIdx.x; rec < na + nb; rec += gridDim.x) {
+        const bool from_a = rec < na;
+        const int4 q = from_a ? fa.recs[rec] : fb.recs[rec - na];
+        const float d = __int_as_float(q.z);
+        if (from_a) {
+            const int64_t bi = sA ? q.x / M : 0, i = sA ? q.x - bi * M : q.x, k = q.y;
+            for (int64_t bb = sA ? bi : 0; bb < (sA ? bi + 1 : batch); bb++) {
+                const float *brow = B + (sB ? bb * sB : 0) + k * ldb;
+                float *crow = C + bb * sC + i * ldc;
+                for (int64_t j = threadIdx.x; j < N; j += 256) atomicAdd(crow + j, d * brow[j]);
+            }
+        } else {
+            const int64_t bk = sB ? q.x / K : 0, k = sB ? q.x - bk * K : q.x, j = q.y;
+            for (int64_t bb = sB ? bk : 0; bb < (sB ? bk + 1 : batch); bb++) {
+                const float *acol = A + (sA ? bb * sA : 0) + k;
+                float *ccol = C + bb * sC + j;
+                for (int64_t i = threadIdx.x; i < M; i += 256) atomicAdd(ccol + i * ldc, acol[i * lda] * d);
+            }
+        }
     }
 }
 
@@ -1449,7 +1495,8 @@ static int gemm_fp16x3(const GemmArgs &g) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;   // matrices of each operand in this chunk
         const int64_t n_rows = ba * g.M;
-        int rc = ensure_gemm_ws((na + nbb) * 4 + (rows_layout + cols_layout) * 4 + (na32 + nb32) * 4 + 1024);
+        const int64_t fix_bytes = 16 + 2 * (int64_t)FIX_CAP * (int64_t)sizeof(int4);
+        int rc = ensure_gemm_ws((na + nbb) * 4 + (rows_layout + cols_layout) * 4 + (na32 + nb32) * 4 + fix_bytes + 1024);
         if (rc != NB200_OK) return rc;
         __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);   // (16-bit storage; the contents are IEEE half)
         __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
@@ -1457,8 +1504,12 @@ static int gemm_fp16x3(const GemmArgs &g) {
         unsigned int *col_max = row_max + rows_layout;
         float *a_lo32 = reinterpret_cast<float *>(col_max + cols_layout);
         float *b_lo32 = a_lo32 + na32;
+        unsigned int *fix_cnt = reinterpret_cast<unsigned int *>(b_lo32 + nb32);   // [0] A records, [1] B records (16-byte slot)
+        FixList fix_a{fix_cnt, reinterpret_cast<int4 *>(fix_cnt + 4)}, fix_b{fix_cnt + 1, reinterpret_cast<int4 *>(fix_cnt + 4) + FIX_CAP};
         const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
-        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once
+        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once (its records persist)
+        if (do_a) NB_CUDA(cudaMemsetAsync(fix_cnt, 0, 4, ctx().stream));
+        if (do_b) NB_CUDA(cudaMemsetAsync(fix_cnt + 1, 0, 4, ctx().stream));
         if (do_a) {
             int64_t blocks = (n_rows + 7) / 8;
             if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
@@ -1481,9 +1532,9 @@ static int gemm_fp16x3(const GemmArgs &g) {
         }
         SplitSpanF16 sa, sb;
         sa.s = make_span(a_src, a_hi, a_lo, do_a ? ba : 0, g.M, g.K, g.lda, g.sA);
-        sa.max_bits = row_max; sa.by_col = 0;
+        sa.max_bits = row_max; sa.by_col = 0; sa.fix = fix_a;
         sb.s = make_span(b_src, b_hi, b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
-        sb.max_bits = col_max; sb.by_col = 1;
+        sb.max_bits = col_max; sb.by_col = 1; sb.fix = fix_b;
         if ((sa.s.flat || sa.s.groups == 0) && (sb.s.flat || sb.s.groups == 0) && sa.s.groups + sb.s.groups > 0) {
             const int64_t g0 = sa.s.groups >> 1, g1 = sb.s.groups >> 1;   // 8-element groups
             int64_t blocks = (g0 + g1 + 255) / 256;
@@ -1510,6 +1561,10 @@ static int gemm_fp16x3(const GemmArgs &g) {
         c.gate_want = 0;
         rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
         if (rc != NB200_OK) return rc;
+        // (1b) sparse repair of the recorded out-of-window elements (normally none: the kernel returns at once)
+        fp16_fixup_kernel<<<256, 256, 0, ctx().stream>>>(g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB,
+                                                         g.sC, fix_a, fix_b, nonfinite_flag() + 1, ctx().nonfinite_gen);
+        NB_LAUNCH_CHECK();
         // (2) TF32x3 fallback on the raw operands, runs only if it did
         const int64_t s_a = span(ba, g.sA, g.M, g.lda, g.K), s_b = span(bb, g.sB, g.K, g.ldb, g.N);
         if ((rc = launch_split(a_src, a_lo32, do_a ? s_a : 0, b_src, b_lo32, do_b ? s_b : 0, true)) != NB200_OK) return rc;
@@ -1661,7 +1716,7 @@ extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, 
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
     precision = gemm_resolve_precision(precision, K);
     int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024
-                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * (round4(M) + round4(N)) + 4 * (round4(M * K) + round4(K * N)) + 1024
+                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * (round4(M) + round4(N)) + 4 * (round4(M * K) + round4(K * N)) + 16 + 2 * (int64_t)FIX_CAP * 16 + 1024
                                                  : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = gemm_ws_budget();

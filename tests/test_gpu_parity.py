@@ -400,9 +400,10 @@ def test_matmul_fp16x3_coherent_inputs_dynamic_range_and_specials(nb):
         lib.nb200_free(p)
 
 
-def test_matmul_fp16x3_device_side_fallback_and_gather(nb):
-    """FP16x3 needs every non-zero element within 2^-28 of its row (A) / column (B) maximum; the split pre-pass decides on
-    the device and the gated TF32x3 fallback produces the result otherwise — bit-identical to a plain TF32X3 call."""
+def test_matmul_fp16x3_device_side_fallback_repair_and_gather(nb):
+    """FP16x3 keeps 22 bits of every element within 2^-28 of its row (A) / column (B) maximum.  A few elements outside that
+    window are repaired by a sparse rank-1 update after the GEMM; if there are too many (or a subnormal storm) the split
+    pre-pass marks the call on the device and the gated TF32x3 fallback produces the result — bit-identical to TF32X3."""
     r = _rng(55)
     a = r.random((384, 256), dtype=np.float32) + 0.25
     b = r.random((256, 320), dtype=np.float32) + 0.25
@@ -411,17 +412,43 @@ def test_matmul_fp16x3_device_side_fallback_and_gather(nb):
     fast = nb.nd.matmul(A, B, nb.FP16X3).toArray()
     assert rel_err(fast, ORACLE.matmul(a, b)).max() <= RTOL
     assert not np.array_equal(fast, strict)                  # eligible data really took the FP16 path
+    # (1) repair: one element of A 2^-40 below its row maximum, made observable by a column of B that selects only it;
+    #     one element of B 2^-40 below its column maximum, observable because the large element's partner column of A is 0
+    a1, b1 = a.copy(), b.copy()
+    a1[17, 5] = a1[17].max() * np.float32(2.0 ** -40)
+    b1[:, 11] = 0.0
+    b1[5, 11] = 1.5                                           # C[17, 11] = a1[17, 5] * 1.5
+    a1[:, 9] = 0.0
+    b1[:, 21] = 0.0
+    b1[9, 21] = 1.0                                           # multiplies the zero column of A: contributes nothing
+    b1[30, 21] = np.float32(2.0 ** -40)                      # C[:, 21] = a1[:, 30] * 2^-40
+    exp1 = ORACLE.matmul(a1, b1)
+    got1 = nb.nd.matmul(nb.NDArray.array(a1).gpu(), nb.NDArray.array(b1).gpu(), nb.FP16X3).toArray()
+    assert rel_err(got1[17, 11], exp1[17, 11]) <= RTOL and rel_err(got1[:, 21], exp1[:, 21]).max() <= RTOL
+    ok = np.abs(exp1) > 0
+    assert rel_err(got1[ok], exp1[ok]).max() <= RTOL
+    assert not np.array_equal(got1, nb.nd.matmul(nb.NDArray.array(a1).gpu(), nb.NDArray.array(b1).gpu(), nb.TF32X3).toArray())
+    # (2) too many out-of-window elements: the fallback takes over, bit for bit the TF32X3 result
     a_bad = a.copy()
-    a_bad[17, 5] = a_bad[17].max() * np.float32(2.0 ** -40)  # one element far below its row's maximum
+    a_bad[:40, :128] *= np.float32(2.0 ** -40)               # 5120 elements far below their rows' maxima
     Ab = nb.NDArray.array(a_bad).gpu()
     np.testing.assert_array_equal(nb.nd.matmul(Ab, B, nb.FP16X3).toArray(), nb.nd.matmul(Ab, B, nb.TF32X3).toArray())
-    b_bad = b.copy()
-    b_bad[100, 7] = np.float32(1e-42)                        # subnormal fp32 in B
-    Bb = nb.NDArray.array(b_bad).gpu()
-    np.testing.assert_array_equal(nb.nd.matmul(A, Bb, nb.FP16X3).toArray(), nb.nd.matmul(A, Bb, nb.TF32X3).toArray())
     # the next (eligible) call is not affected by the previous call's flag
     np.testing.assert_array_equal(nb.nd.matmul(A, B, nb.FP16X3).toArray(), fast)
-    # gather through a permutation matrix: every output IS one input element, also the ones 2^-20 below their row maximum
+    # (3) batch with a shared B that carries a repaired element: the record applies to every matrix of the batch
+    lib = nb.lib()
+    batch = 3
+    a3 = r.random((batch, 256, 256), dtype=np.float32) + 0.25
+    a3[:, :, 9] = 0.0
+    da, db, dc = _dev(nb, a3), _dev(nb, b1), _dev(nb, np.zeros((batch, 256, 320), np.float32))
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, 256, 320, 256, 256 * 256, 0, 256 * 320, 4) == 0, lib.nb200_last_error()
+    got3 = _fetch(nb, dc, (batch, 256, 320))
+    for i in range(batch):
+        e3 = ORACLE.matmul(a3[i], b1)
+        assert rel_err(got3[i][:, 21], e3[:, 21]).max() <= RTOL
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+    # (4) gather through a permutation matrix: every output IS one input element, also the ones 2^-20 below their row maximum
     g = (r.random((256, 256), dtype=np.float32) + 0.5) * np.exp2(r.integers(-20, 1, size=(256, 256))).astype(np.float32)
     perm = r.permutation(256)
     pm = np.zeros((256, 256), np.float32)
