@@ -1004,8 +1004,8 @@ __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restri
 // non-zero element below that (or a subnormal fp32) marks the call INELIGIBLE: nonfinite[1] = gen, and the gated TF32x3
 // fallback produces the result instead (see gemm_fp16x3).
 // Out-of-window elements (see above) do not abandon the call as long as there are few of them: the split records
-// (row, column, d) with d = a - (hi + lo * 2^-11) * 2^-e, the part of the element the half pair cannot hold, and
-// fp16_fixup_kernel adds d times the partner row / column to C after the GEMM (a sparse rank-1 repair).  Only when a
+// (row, column, a), zeroes the element's half parts, and fp16_fixup_kernel adds a times the partner row / column of the
+// other (raw fp32) operand to C after the GEMM (a sparse rank-1 repair in full fp32 precision).  Only when a
 // record list overflows is the call marked ineligible (nonfinite[1] = gen) and left to the gated TF32x3 fallback.
 constexpr int FIX_CAP = 4096;              // records per operand and chunk
 struct FixList {
@@ -1026,10 +1026,13 @@ __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, uns
     const __half ll = __float2half_rn((x - __half2float(hh)) * 2048.0f);
     h = __half_as_ushort(hh);
     l = __half_as_ushort(ll);
-    if (ab != 0u && fabsf(x) < 6.103515625e-05f) {  // below 2^-14: hi is a subnormal half -> repair record
-        const float held = scale_pow2(__half2float(hh) + __half2float(ll) * (1.0f / 2048.0f), -e);
+    if (ab != 0u && fabsf(x) < 6.103515625e-05f) {  // below 2^-14: hi would be a subnormal half -> repair record
+        // The element leaves the GEMM entirely (hi = lo = 0) and is carried by the record in full fp32: a lo-only
+        // representation would multiply it with the partner's hi part alone, i.e. with 11 bits (measured 4.7e-4).
+        h = 0;
+        l = 0;
         const unsigned int idx = atomicAdd(fix.count, 1u);
-        if (idx < (unsigned int)FIX_CAP && row < 0x7FFFFFFF) fix.recs[idx] = make_int4((int)row, (int)col, __float_as_int(a - held), 0);
+        if (idx < (unsigned int)FIX_CAP && row < 0x7FFFFFFF) fix.recs[idx] = make_int4((int)row, (int)col, __float_as_int(a), 0);
         else nonfinite[1] = gen;
     }
 }

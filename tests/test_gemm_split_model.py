@@ -204,18 +204,19 @@ def fp16x3_model_with_fixup(a, b):
     """Round-2 plan for out-of-window elements: keep the call on the FP16 path and repair the
     few elements the half parts cannot represent with a sparse rank-1 update.  For such an element of A the split leaves a
     residual d = a_ik - (hi + lo * 2^-11) / 2^e_i, and C[i, :] += d * B[k, :] (fp32 axpy) restores its full contribution;
-    symmetrically C[:, j] += A[:, k] * d for an element of B.  Returns (C, number of repaired elements)."""
+    symmetrically C[:, j] += A[:, k] * d for an element of B.  (The kernel takes the element out of the GEMM entirely,
+    hi = lo = 0 and d = a: a lo-only remnant would meet only the partner's 11-bit hi part.)  Returns (C, repaired)."""
     d64 = np.float64
     ea = scale_exp(np.abs(a).max(axis=1))[:, None]
     eb = scale_exp(np.abs(b).max(axis=0))[None, :]
-    ah, al, _ = split_f16_scaled(a, ea)
-    bh, bl, _ = split_f16_scaled(b, eb)
-    c = np.ldexp(ah @ bh + ah @ bl + al @ bh, -(ea + eb))
-    ra = a.astype(d64) - np.ldexp(ah + al, -ea)                  # what the half parts missed
-    rb = b.astype(d64) - np.ldexp(bh + bl, -eb)
     xa, xb = np.ldexp(a.astype(d64), ea), np.ldexp(b.astype(d64), eb)
     out_a = (xa != 0) & (np.abs(xa) < 2.0 ** -14)                # the window test of split_f16()
     out_b = (xb != 0) & (np.abs(xb) < 2.0 ** -14)
+    ah, al, _ = split_f16_scaled(np.where(out_a, np.float32(0), a), ea)
+    bh, bl, _ = split_f16_scaled(np.where(out_b, np.float32(0), b), eb)
+    c = np.ldexp(ah @ bh + ah @ bl + al @ bh, -(ea + eb))
+    ra = np.where(out_a, a.astype(d64), 0.0)                     # the records carry the whole element
+    rb = np.where(out_b, b.astype(d64), 0.0)
     for i, k in zip(*np.nonzero(out_a)):
         c[i, :] += ra[i, k] * b[k, :].astype(d64)
     for k, j in zip(*np.nonzero(out_b)):
