@@ -102,7 +102,8 @@ enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
  *   parts of A scaled per row and B scaled per column by powers of two (lo parts stored x2^11; the
  *   epilogue undoes all scaling exactly).  Every non-zero element within 2^-28 of its row / column
  *   maximum keeps a 2^-22 relative split error: TF32X3-class guaranteed bound, no coherent-input
- *   problem.  The split pre-pass checks that window ON THE DEVICE; if an element falls outside, the
+ *   problem.  The split pre-pass checks that window ON THE DEVICE: a few elements outside it are
+ *   taken out of the GEMM and added back by a sparse fp32 repair kernel; if there are too many, the
  *   gated TF32X3 fallback enqueued with the call produces the result instead (bit-identical to a
  *   TF32X3 call).  Needs operands the TF32 path can read (16-byte aligned, ld % 4 == 0).
  * AUTO: see above. */
