@@ -201,8 +201,8 @@ def test_fp16x3_eligibility_window_and_gather():
 
 
 def fp16x3_model_with_fixup(a, b):
-    """Round-2 plan for out-of-window elements: keep the call on the FP16 path and repair the
-    few elements the half parts cannot represent with a sparse rank-1 update.  For such an element of A the split leaves a
+    """Out-of-window elements (fp16_fixup_kernel in sgemm_tcgen05.cu): the call stays on the FP16 path
+    and the few elements the half parts cannot represent are repaired with a sparse rank-1 update.  For such an element of A the split leaves a
     residual d = a_ik - (hi + lo * 2^-11) / 2^e_i, and C[i, :] += d * B[k, :] (fp32 axpy) restores its full contribution;
     symmetrically C[:, j] += A[:, k] * d for an element of B.  (The kernel takes the element out of the GEMM entirely,
     hi = lo = 0 and d = a: a lo-only remnant would meet only the partner's 11-bit hi part.)  Returns (C, repaired)."""
@@ -234,7 +234,7 @@ def test_fp16x3_sparse_fixup_model_restores_out_of_window_elements():
     b[7, 3] = 1.0                                                # C[5, 3] == a[5, 7] exactly
     b[20, 9] = np.float32(3.0 * 2.0 ** -45)                      # an out-of-window element of B
     exact = a.astype(np.float64) @ b.astype(np.float64)
-    assert fp16x3_model(a, b) is None                            # today: the gated TF32x3 fallback
+    assert fp16x3_model(a, b) is None                            # without the repair: ineligible (the gated TF32x3 fallback)
     c, repaired = fp16x3_model_with_fixup(a, b)
     assert repaired == 2
     assert (np.abs(c - exact) / np.abs(exact)).max() <= 2.0 ** -20
