@@ -16,7 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libnb200.so")
-SOURCES = ["abi.cu", "ew.cu", "reduce.cu", "sgemm_tcgen05.cu", "sgemm_debug.cu", "misc.cu", "host_pipeline.cu", "legacy.cu", "host/ndarray_host.cpp"]
+SOURCES = ["abi.cu", "ew.cu", "reduce.cu", "sgemm_tcgen05.cu", "misc.cu", "host_pipeline.cu", "legacy.cu", "host/ndarray_host.cpp"]
+# bring-up probes (scripts/tcgen05_probe.py): a separate library on top of libnb200.so, never loaded by the product
+DEBUG_LIB = os.path.join(HERE, "libnb200_debug.so")
+DEBUG_SOURCES = ["sgemm_debug.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
@@ -51,6 +54,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-lrt", "-lpthread", "-ldl"])
+    dobjs = []
+    for src in DEBUG_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        dobjs.append(o)
+        if force or _stale(o, [s] + headers):
+            run([NVCC, *FLAGS, "-c", s, "-o", o])
+    if force or _stale(DEBUG_LIB, dobjs + [LIB]):
+        run([NVCC, "-shared", "-o", DEBUG_LIB, *dobjs, "-cudart", "static", "-L", HERE, "-lnb200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     return LIB
 
 

@@ -43,10 +43,14 @@ struct GemmCfg {
     // A scaled per row and B scaled per column by powers of two (so that every row / column uses the top of fp16's
     // exponent range); the epilogue undoes the scaling with one exact scalbnf per output element.
     static constexpr bool SCALED = SCALED_;
-    static_assert(!SCALED_ || (BF16_ && !MERGED_), "scaled mode: 16-bit operands, separate cross-term accumulator");
-    // SCALED stores the lo parts times 2^11 (so that they use the same fp16 binades as the hi parts); the cross-term
-    // accumulator is therefore 2^11 too large and is scaled back (exactly) when it is folded into the total.
-    static constexpr float CROSS_SCALE = SCALED_ ? 1.0f / 2048.0f : 1.0f;
+    static_assert(!SCALED_ || BF16_, "scaled mode: 16-bit operands");
+    // SCALED stores the lo parts as IEEE half times 2^11 (so that they use the same fp16 binades as the hi parts): the two
+    // cross products come out 2^11 too large.
+    //  * separate cross-term accumulator (256x128 tiles): scaled back (exactly) when it is folded into the total;
+    //  * SCALED + MERGED (256x256 tiles, ONE accumulator per chunk): a chunk is a single k-block (K = 64); its cross
+    //    products are issued first and the first a_hi.b_hi MMA of the chunk carries tcgen05.mma's scale-input-d = 11
+    //    (D = A.B + D * 2^-11, exact), so the chunk accumulator ends up holding hh + 2^-11 (lh + hl).
+    static constexpr float CROSS_SCALE = (SCALED_ && !MERGED_) ? 1.0f / 2048.0f : 1.0f;
     // MERGED (BF16x3, BN = 256): all three products of a chunk accumulate into ONE 256-column TMEM accumulator (2-deep
     // ring = all 512 columns) and the running total lives in the registers of eight epilogue warps.  Twice the flops
     // per staged byte and no cross-accumulator hand-off between tiles; costs 48 instead of 32 truncating accumulation
@@ -85,13 +89,22 @@ struct GemmCfg {
     // (tcgen05.ld / FADD / tcgen05.st), and (b) keeps the 2^-11-smaller cross terms in their own
     // accumulator.  TMEM columns: [0,BN) [BN,2BN) main ring | [2BN,3BN) cross terms | [3BN,4BN) running total.
     static constexpr bool CHUNKED = PASSES == 3;
-    static constexpr int KC = (BF16_ && !MERGED_) ? 512 : 256;   // K elements per accumulation chunk (32 MMA k-steps; MERGED: 16 x 3 products)
+    // K elements per accumulation chunk (32 MMA k-steps; MERGED: 16 x 3 products; SCALED + MERGED: one k-block, see above)
+    static constexpr int KC = (SCALED_ && MERGED_) ? BK : (BF16_ && !MERGED_) ? 512 : 256;
     static constexpr int KB_PER_CHUNK = KC / BK;
     static constexpr int TMEM_COLS = (CHUNKED && !MERGED_) ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
     static_assert(!CHUNKED || MERGED_ || BN == 128, "chunked x3 uses 128-column tiles (4 x 128 TMEM columns)");
     static_assert(!MERGED_ || (BF16_ && BN == 256 && PASSES_ == 3), "merged accumulation exists for BF16x3 with 256-column tiles");
     static constexpr int EPI_WARPS = MERGED_ ? 8 : 4;
-    static constexpr int THREADS = (INK_ || MERGED_) ? 320 : 192;     // + 4 converter warps / + 4 more epilogue warps
+    // MERGED epilogue: accumulator columns per tcgen05.ld (each load is followed by a wait of a few hundred cycles).  One k-block
+    // per chunk (SCALED) drains a 256-column accumulator every 12 MMAs: 64 columns per load, two waits per chunk.
+    static constexpr int EPI_LD = (SCALED_ && MERGED_) ? 64 : 16;
+    // MERGED: 12 warps = 3 warpgroups.  Warpgroup 0 = TMA producer, MMA issuer and two idle warps (TMEM allocation); warpgroups
+    // 1-2 = eight epilogue warps that keep 128 running totals + the TMEM load in flight in registers: setmaxnreg moves registers
+    // from warpgroup 0 (72 per thread) to the epilogue warpgroups (216 per thread; 128 * 72 + 256 * 216 <= 64 Ki).  A 10-warp CTA
+    // would be allocated as 12 warps anyway (168 registers per thread, spills in the epilogue).
+    static constexpr int THREADS = MERGED_ ? 384 : (INK_ ? 320 : 192);     // INK: + 4 converter warps
+    static constexpr int EPI_WARP0 = MERGED_ ? 4 : 2;                     // first epilogue warp
     static constexpr int TMA_BYTES = INK_ ? (A_BYTES + B_BYTES) : STAGE_BYTES;   // bytes the TMA lands per stage per CTA
     static_assert(!INK_ || (PASSES_ == 3 && !BF16_), "in-kernel split only exists for TF32x3");
     static_assert(!BF16_ || PASSES_ == 3, "bf16 operands are only used by the x3 error-compensated mode");
@@ -237,6 +250,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
             ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
+// kind::f16 with scale-input-d: D = A.B + D * 2^-11 (SCALED + MERGED: folds the 2^11-scaled cross products of a chunk)
+template <int CG>
+__device__ __forceinline__ void umma_f16_scale_d11(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 11;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u) : "memory");
+    }
+}
 // all previously issued MMAs complete -> one arrival on `bar` (in both CTAs of a pair when CG == 2)
 template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -265,6 +293,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -298,8 +333,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 // B MN-major (bit 16 =1), N>>3 at bits 17-22, M>>4 at bits 24-28.
 // kind::f16 uses the same fields with A=B=bf16 (format code 1).
 // fmt: 0 = f16, 1 = bf16 (both kind::f16), 2 = tf32.
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, uint32_t fmt = 2u) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t fmt_a, uint32_t fmt_b) {
+    return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 
@@ -384,169 +419,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
     const int64_t tiles_per_mat = (int64_t)p.tiles_m * p.tiles_n;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
-                // work item -> tile (+ which half of it when the last wave is split, see launch_gemm)
-                const bool half_tile = Cfg::MERGED && t >= p.full_items;
-                const int64_t tt = half_tile ? p.full_items + ((t - p.full_items) >> 1) : t;
-                const int ncols_cta = half_tile ? Cfg::BN_CTA / 2 : Cfg::BN_CTA;   // B columns this CTA stages
-                const int64_t b = tt / tiles_per_mat, r = tt % tiles_per_mat;
-                int m_tile, n_tile;
-                tile_coords(r, p, m_tile, n_tile);
-                const int row0 = m_tile * BM * CG + (int)rank * BM;
-                const int col0 = n_tile * BN + (half_tile ? (int)((t - p.full_items) & 1) * (BN / 2) : 0) + (int)rank * ncols_cta;
-                const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
-                for (int kb = 0; kb < num_kb; kb++) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u, p.debug, 0x100u + stage);
-                    const int k0 = kb * BK;
-                    if constexpr (Cfg::INK) {
-                        // raw operands only, signalled on THIS CTA's full barrier (its converter warps wait on it)
-                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::TMA_BYTES);
-                        tma_load_3d<1>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
-#pragma unroll
-                        for (int j = 0; j < Cfg::BN_CTA / 32; j++)
-                            tma_load_3d<1>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
-                    } else {
-                        if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(NPART * (Cfg::A_BYTES + ncols_cta * BK * Cfg::ESZ)) * CG);
-                        tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
-                        if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
-#pragma unroll
-                        for (int j = 0; j < Cfg::BN_CTA / Cfg::B_CHUNK_N; j++) {
-                            if (j * Cfg::B_CHUNK_N >= ncols_cta) break;
-                            tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
-                            if (PASSES == 3)
-                                tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
-                        }
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA only) =====================
-        if (leader) {
-            constexpr uint32_t FMT = Cfg::SCALED ? 0u : (Cfg::BF16 ? 1u : 2u);
-            constexpr uint32_t idesc_full = make_idesc_tf32(BM * CG, BN, FMT);
-            constexpr uint32_t idesc_half = make_idesc_tf32(BM * CG, BN / 2, FMT);
-            constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
-            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
-                const uint32_t idesc = (Cfg::MERGED && t >= p.full_items) ? idesc_half : idesc_full;
-                if constexpr (!Cfg::CHUNKED) {
-                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    for (int kb = 0; kb < num_kb; kb++) {
-                        mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
-                        tc_fence_after();
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
-                                const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                umma_tf32<CG, Cfg::BF16>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                            }
-                            umma_commit<CG>(empty_bar(stage));
-                            if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
-                        }
-                        __syncwarp();
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                    }
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                } else {
-                    // cross-term accumulator of the previous tile must have been read out
-                    if constexpr (!Cfg::MERGED) mbar_wait(cross_empty_bar, tile_phase ^ 1u, p.debug, 0x500u);
-                    // An operand with +-inf: a_hi = inf times b_lo = 0 would turn cblas_sgemm's inf into NaN.  The pre-pass
-                    // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
-                    // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
-                    const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite) == p.nonfinite_gen) ? 1 : 0;
-                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
-                    for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
-                        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
-                        tc_fence_after();
-                        const uint32_t d_main = tmem_base + (uint32_t)(acc * BN);
-                        const uint32_t d_x = Cfg::MERGED ? d_main : d_cross;   // where the cross products go
-                        const int kb1 = kb0 + Cfg::KB_PER_CHUNK < num_kb ? kb0 + Cfg::KB_PER_CHUNK : num_kb;
-                        for (int kb = kb0; kb < kb1; kb++) {
-                            if (Cfg::INK) mbar_wait(conv_bar(stage), phase, p.debug, 0x600u + stage);
-                            else mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                // a_lo.b_hi and a_hi.b_lo -> cross accumulator (whole K); a_hi.b_hi -> this chunk's accumulator
-#pragma unroll
-                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                    const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
-                                }
-#pragma unroll
-                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                    const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, 1u);
-                                }
-#pragma unroll
-                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
-                                    const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
-                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_main, da, db, idesc, (Cfg::MERGED || kb != kb0 || k != 0) ? 1u : 0u);
-                                }
-                                umma_commit<CG>(empty_bar(stage));
-                                if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(acc));
-                            }
-                            __syncwarp();
-                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                        }
-                        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-                    }
-                    tile_phase ^= 1u;
-                }
-            }
-        }
-    } else if (Cfg::INK && warp >= 6) {
-        // ===================== lo-part converters (warps 6..9, TF32x3 in-kernel split) =====================
-        // a_lo = rna_tf32(a - trunc_tf32(a)) element for element: the swizzled layout of the raw tile carries over
-        // unchanged because the lo tile sits at the same offset modulo 1024 B.
-        const int ct = threadIdx.x - 192;   // 0..127
-        int stage = 0;
-        uint32_t phase = 0;
-        auto lo_of = [](float a) {
-            const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-            uint32_t r;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a - hi));
-            return __uint_as_float(r);
-        };
-        auto convert = [&](uint32_t src, uint32_t dst, int bytes) {
-#pragma unroll 4
-            for (int off = ct * 16; off < bytes; off += 128 * 16) {
-                float4 v;
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + off));
-                v.x = lo_of(v.x); v.y = lo_of(v.y); v.z = lo_of(v.z); v.w = lo_of(v.w);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-            }
-        };
-        for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                mbar_wait(full_bar(stage), phase, p.debug, 0x700u + stage);
-                convert(a_smem(stage, 0), a_smem(stage, 1), Cfg::A_BYTES);
-                convert(b_smem(stage, 0), b_smem(stage, 1), Cfg::B_BYTES);
-                fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_leader(conv_bar(stage));
-                    else mbar_arrive_local(conv_bar(stage));
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-        }
-    } else if (warp >= 2 && warp < 2 + Cfg::EPI_WARPS) {
-        // ===================== epilogue (warps 2..5; MERGED: 2..9, warps 6..9 take the upper 128 columns) =====================
+    auto run_epilogue = [&]() {
+        // ===================== epilogue (warps 2..5; MERGED: 4..11, warps 8..11 take the upper 128 columns) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -603,7 +477,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             };
             if constexpr (Cfg::MERGED) {
                 // running total of this thread's row (128 of the tile's 256 columns) in registers, chunks added round-to-nearest
-                const int half = (warp - 2) >> 2;
+                const int half = (warp - Cfg::EPI_WARP0) >> 2;
                 const bool idle = half_tile && half == 1;   // half tiles only have the lower 128 accumulator columns
                 float tot[128];
                 for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
@@ -613,13 +487,14 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     const uint32_t t_main = tmem_base + lane_sel + (uint32_t)(acc * BN + half * 128);
                     if (!idle) {
 #pragma unroll
-                        for (int c = 0; c < 8; c++) {   // 16 columns at a time: 128 totals + 16 in flight fit the 168-register budget
-                            uint32_t v[16];
-                            tmem_ld_32x16(t_main + (uint32_t)(c * 16), v);
+                        for (int c = 0; c < 128 / Cfg::EPI_LD; c++) {   // EPI_LD columns per TMEM load (one wait each): 128 totals + EPI_LD in flight
+                            uint32_t v[Cfg::EPI_LD];
+                            if constexpr (Cfg::EPI_LD == 64) tmem_ld_32x64(t_main + (uint32_t)(c * 64), v);
+                            else tmem_ld_32x16(t_main + (uint32_t)(c * 16), v);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int q = 0; q < 16; q++)
-                                tot[c * 16 + q] = first ? __uint_as_float(v[q]) : __fadd_rn(tot[c * 16 + q], __uint_as_float(v[q]));
+                            for (int q = 0; q < Cfg::EPI_LD; q++)
+                                tot[c * Cfg::EPI_LD + q] = first ? __uint_as_float(v[q]) : __fadd_rn(tot[c * Cfg::EPI_LD + q], __uint_as_float(v[q]));
                         }
                     }
                     tc_fence_before();
@@ -631,9 +506,21 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     if (last && row < p.M && !idle) {
                         const int64_t colh = col0 + half * 128;
                         if constexpr (Cfg::SCALED) {
+                            if (colh + 128 <= p.N && (p.N & 3) == 0) {   // column maxima 16-byte aligned (col_max sub-arrays are)
+                                const uint4 *mb = reinterpret_cast<const uint4 *>(cmax + colh);
 #pragma unroll
-                            for (int q = 0; q < 128; q++)
-                                if (colh + q < p.N) tot[q] = scale_pow2(tot[q], -(e_row + scale_exp(cmax[colh + q])));
+                                for (int q = 0; q < 32; q++) {
+                                    const uint4 m4 = __ldg(mb + q);
+                                    tot[4 * q] = scale_pow2(tot[4 * q], -(e_row + scale_exp(m4.x)));
+                                    tot[4 * q + 1] = scale_pow2(tot[4 * q + 1], -(e_row + scale_exp(m4.y)));
+                                    tot[4 * q + 2] = scale_pow2(tot[4 * q + 2], -(e_row + scale_exp(m4.z)));
+                                    tot[4 * q + 3] = scale_pow2(tot[4 * q + 3], -(e_row + scale_exp(m4.w)));
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 128; q++)
+                                    if (colh + q < p.N) tot[q] = scale_pow2(tot[q], -(e_row + scale_exp(cmax[colh + q])));
+                            }
                         }
                         if (vec_ok && colh + 128 <= p.N) {
                             float4 *dst = reinterpret_cast<float4 *>(crow + colh);
@@ -766,6 +653,183 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 }
             }
         }
+    };
+
+    // MERGED: warpgroup-uniform branch so that each side is dominated by its setmaxnreg (register re-balancing, see GemmCfg::THREADS)
+    if (Cfg::MERGED && warp >= 4) {
+        if constexpr (Cfg::MERGED) {
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+            run_epilogue();
+        }
+    } else {
+    if constexpr (Cfg::MERGED) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                // work item -> tile (+ which half of it when the last wave is split, see launch_gemm)
+                const bool half_tile = Cfg::MERGED && t >= p.full_items;
+                const int64_t tt = half_tile ? p.full_items + ((t - p.full_items) >> 1) : t;
+                const int ncols_cta = half_tile ? Cfg::BN_CTA / 2 : Cfg::BN_CTA;   // B columns this CTA stages
+                const int64_t b = tt / tiles_per_mat, r = tt % tiles_per_mat;
+                int m_tile, n_tile;
+                tile_coords(r, p, m_tile, n_tile);
+                const int row0 = m_tile * BM * CG + (int)rank * BM;
+                const int col0 = n_tile * BN + (half_tile ? (int)((t - p.full_items) & 1) * (BN / 2) : 0) + (int)rank * ncols_cta;
+                const int ba = p.a_batched ? (int)b : 0, bb = p.b_batched ? (int)b : 0;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u, p.debug, 0x100u + stage);
+                    const int k0 = kb * BK;
+                    if constexpr (Cfg::INK) {
+                        // raw operands only, signalled on THIS CTA's full barrier (its converter warps wait on it)
+                        mbar_expect_tx(full_bar(stage), (uint32_t)Cfg::TMA_BYTES);
+                        tma_load_3d<1>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
+#pragma unroll
+                        for (int j = 0; j < Cfg::BN_CTA / 32; j++)
+                            tma_load_3d<1>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * 4096, col0 + j * 32, k0, bb);
+                    } else {
+                        if (leader) mbar_expect_tx(full_bar(stage), (uint32_t)(NPART * (Cfg::A_BYTES + ncols_cta * BK * Cfg::ESZ)) * CG);
+                        tma_load_3d<CG>(&tmA_hi, full_bar(stage), a_smem(stage, 0), k0, row0, ba);
+                        if (PASSES == 3) tma_load_3d<CG>(&tmA_lo, full_bar(stage), a_smem(stage, 1), k0, row0, ba);
+#pragma unroll
+                        for (int j = 0; j < Cfg::BN_CTA / Cfg::B_CHUNK_N; j++) {
+                            if (j * Cfg::B_CHUNK_N >= ncols_cta) break;
+                            tma_load_3d<CG>(&tmB_hi, full_bar(stage), b_smem(stage, 0) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
+                            if (PASSES == 3)
+                                tma_load_3d<CG>(&tmB_lo, full_bar(stage), b_smem(stage, 1) + j * Cfg::B_CHUNK_BYTES, col0 + j * Cfg::B_CHUNK_N, k0, bb);
+                        }
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            constexpr uint32_t FMT = Cfg::SCALED ? 0u : (Cfg::BF16 ? 1u : 2u);   // operand format: f16 / bf16 (kind::f16), tf32
+            constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
+            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+                const int nn = (Cfg::MERGED && t >= p.full_items) ? BN / 2 : BN;
+                const uint32_t idesc = make_idesc(BM * CG, nn, FMT, FMT);
+                if constexpr (!Cfg::CHUNKED) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    for (int kb = 0; kb < num_kb; kb++) {
+                        mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                        tc_fence_after();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
+                                const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                umma_tf32<CG, Cfg::BF16>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit<CG>(empty_bar(stage));
+                            if (kb == num_kb - 1) umma_commit<CG>(tfull_bar(acc));
+                        }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                } else {
+                    // cross-term accumulator of the previous tile must have been read out
+                    if constexpr (!Cfg::MERGED) mbar_wait(cross_empty_bar, tile_phase ^ 1u, p.debug, 0x500u);
+                    // An operand with +-inf: a_hi = inf times b_lo = 0 would turn cblas_sgemm's inf into NaN.  The pre-pass
+                    // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
+                    // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
+                    const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite) == p.nonfinite_gen) ? 1 : 0;
+                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+                    for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
+                        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
+                        tc_fence_after();
+                        const uint32_t d_main = tmem_base + (uint32_t)(acc * BN);
+                        const uint32_t d_x = Cfg::MERGED ? d_main : d_cross;   // where the cross products go
+                        const int kb1 = kb0 + Cfg::KB_PER_CHUNK < num_kb ? kb0 + Cfg::KB_PER_CHUNK : num_kb;
+                        for (int kb = kb0; kb < kb1; kb++) {
+                            if (Cfg::INK) mbar_wait(conv_bar(stage), phase, p.debug, 0x600u + stage);
+                            else mbar_wait(full_bar(stage), phase, p.debug, 0x200u + stage);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                // a_lo.b_hi and a_hi.b_lo -> cross accumulator (whole K); a_hi.b_hi -> this chunk's accumulator
+#pragma unroll
+                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                    const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
+                                }
+#pragma unroll
+                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                    const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, 1u);
+                                }
+#pragma unroll
+                                for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
+                                    const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
+                                    const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
+                                    if constexpr (Cfg::SCALED && Cfg::MERGED) {   // chunk == this k-block: fold its cross products (x 2^11) first
+                                        if (k == 0) umma_f16_scale_d11<CG>(d_main, da, db, idesc);
+                                        else umma_tf32<CG, true>(d_main, da, db, idesc, 1u);
+                                    } else {
+                                        umma_tf32<CG, Cfg::BF16>(d_main, da, db, idesc, (Cfg::MERGED || kb != kb0 || k != 0) ? 1u : 0u);
+                                    }
+                                }
+                                umma_commit<CG>(empty_bar(stage));
+                                if (kb == kb1 - 1) umma_commit<CG>(tfull_bar(acc));
+                            }
+                            __syncwarp();
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                    }
+                    tile_phase ^= 1u;
+                }
+            }
+        }
+    } else if (Cfg::INK && warp >= 6) {
+        // ===================== lo-part converters (warps 6..9, TF32x3 in-kernel split) =====================
+        // a_lo = rna_tf32(a - trunc_tf32(a)) element for element: the swizzled layout of the raw tile carries over
+        // unchanged because the lo tile sits at the same offset modulo 1024 B.
+        const int ct = threadIdx.x - 192;   // 0..127
+        int stage = 0;
+        uint32_t phase = 0;
+        auto lo_of = [](float a) {
+            const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a - hi));
+            return __uint_as_float(r);
+        };
+        auto convert = [&](uint32_t src, uint32_t dst, int bytes) {
+#pragma unroll 4
+            for (int off = ct * 16; off < bytes; off += 128 * 16) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + off));
+                v.x = lo_of(v.x); v.y = lo_of(v.y); v.z = lo_of(v.z); v.w = lo_of(v.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            }
+        };
+        for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                mbar_wait(full_bar(stage), phase, p.debug, 0x700u + stage);
+                convert(a_smem(stage, 0), a_smem(stage, 1), Cfg::A_BYTES);
+                convert(b_smem(stage, 0), b_smem(stage, 1), Cfg::B_BYTES);
+                fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_leader(conv_bar(stage));
+                    else mbar_arrive_local(conv_bar(stage));
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (!Cfg::MERGED && warp >= Cfg::EPI_WARP0 && warp < Cfg::EPI_WARP0 + Cfg::EPI_WARPS) {
+        if constexpr (!Cfg::MERGED) run_epilogue();
+    }
     }
 
     // ---- teardown: everyone done with TMEM before it is released
@@ -803,10 +867,9 @@ __device__ __forceinline__ float lo_part(float a, int *nonfinite, int gen) {
     const float hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
     return to_tf32(a - hi);
 }
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
-                                                         const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
-                                                         int *__restrict__ nonfinite, int gen, const int *gate, int gate_want) {
-    if (gate != nullptr && ((*reinterpret_cast<const volatile int *>(gate) == gen) != (gate_want != 0))) return;   // see GemmParams::gate
+__device__ __forceinline__ void split_tf32_body(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
+                                                const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
+                                                int *__restrict__ nonfinite, int gen) {
     const int64_t g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;   // 4-element groups (spans are padded to a multiple of 4)
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= g0;
@@ -822,6 +885,11 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
             for (int64_t e = j << 2; e < n; e++) lo[e] = lo_part(in[e], nonfinite, gen);
         }
     }
+}
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
+                                                         const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
+                                                         int *__restrict__ nonfinite, int gen) {
+    split_tf32_body(in0, lo0, n0, in1, lo1, n1, nonfinite, gen);
 }
 
 // ------------------------------------------------------------------ BF16 split pre-pass (BF16x3)
@@ -969,7 +1037,10 @@ __global__ void __launch_bounds__(256) absmax_cols_kernel(const float *__restric
     for (int64_t r = r0; r < r1; r++) m = max(m, finite_abs_bits(ldg_stream(src + r * ld_in)));
     if (m) atomicMax(out + (int64_t)blockIdx.z * cols + c, m);
 }
-// same, four adjacent columns per thread with 16-byte loads (needs 16-byte aligned rows: ld % 4 == 0, cols % 4 == 0)
+// same, four adjacent columns per thread with 16-byte loads (needs 16-byte aligned rows: ld % 4 == 0, cols % 4 == 0).
+// Default-policy loads on purpose: the split that follows re-reads B, and whatever of it is still in L2 is not fetched
+// from HBM again.  Eight loads in flight per thread; the host sizes the row segments so that ~2 blocks per SM run
+// (few, long segments: the final atomicMax traffic is 4 per thread).
 __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
                                                            int64_t stride_in, unsigned int *__restrict__ out) {
     const int64_t c4 = (int64_t)blockIdx.x * 256 + threadIdx.x;   // column group
@@ -980,16 +1051,18 @@ __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restri
     const int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
     unsigned int mx = 0, my = 0, mz = 0, mw = 0;
     int64_t r = r0;
-    for (; r + 3 < r1; r += 4) {   // four independent 16-byte loads in flight per thread
-        const float4 v0 = ldg_stream(src + r * ld4), v1 = ldg_stream(src + (r + 1) * ld4), v2 = ldg_stream(src + (r + 2) * ld4),
-                     v3 = ldg_stream(src + (r + 3) * ld4);
-        mx = max(mx, max(max(finite_abs_bits(v0.x), finite_abs_bits(v1.x)), max(finite_abs_bits(v2.x), finite_abs_bits(v3.x))));
-        my = max(my, max(max(finite_abs_bits(v0.y), finite_abs_bits(v1.y)), max(finite_abs_bits(v2.y), finite_abs_bits(v3.y))));
-        mz = max(mz, max(max(finite_abs_bits(v0.z), finite_abs_bits(v1.z)), max(finite_abs_bits(v2.z), finite_abs_bits(v3.z))));
-        mw = max(mw, max(max(finite_abs_bits(v0.w), finite_abs_bits(v1.w)), max(finite_abs_bits(v2.w), finite_abs_bits(v3.w))));
+    for (; r + 7 < r1; r += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = ld_ew(src + (r + u) * ld4);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            mx = max(mx, finite_abs_bits(v[u].x)); my = max(my, finite_abs_bits(v[u].y));
+            mz = max(mz, finite_abs_bits(v[u].z)); mw = max(mw, finite_abs_bits(v[u].w));
+        }
     }
     for (; r < r1; r++) {
-        const float4 v = ldg_stream(src + r * ld4);
+        const float4 v = ld_ew(src + r * ld4);
         mx = max(mx, finite_abs_bits(v.x)); my = max(my, finite_abs_bits(v.y)); mz = max(mz, finite_abs_bits(v.z)); mw = max(mw, finite_abs_bits(v.w));
     }
     unsigned int *o = out + (int64_t)blockIdx.z * cols + c4 * 4;
@@ -998,15 +1071,13 @@ __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restri
     if (mz) atomicMax(o + 2, mz);
     if (mw) atomicMax(o + 3, mw);
 }
-// a' = a * 2^e (e from the row or column |max|), hi = rn_f16(a'), lo = rn_f16((a' - hi) * 2^11); |a'| < 2^15 and
-// |a' - hi| * 2^11 <= 2^15, so nothing overflows.  As long as hi is a NORMAL half (|a'| >= 2^-14, i.e. the element lies within
-// 2^-28 of its row / column maximum) the remainder a' - hi - lo * 2^-11 is <= 2^-22 |a'|: the same class as TF32x3.  A
-// non-zero element below that (or a subnormal fp32) marks the call INELIGIBLE: nonfinite[1] = gen, and the gated TF32x3
-// fallback produces the result instead (see gemm_fp16x3).
-// Out-of-window elements (see above) do not abandon the call as long as there are few of them: the split records
-// (row, column, a), zeroes the element's half parts, and fp16_fixup_kernel adds a times the partner row / column of the
-// other (raw fp32) operand to C after the GEMM (a sparse rank-1 repair in full fp32 precision).  Only when a
-// record list overflows is the call marked ineligible (nonfinite[1] = gen) and left to the gated TF32x3 fallback.
+// a' = a * 2^e (e from the row or column |max|), hi = rn_f16(a'), |a'| < 2^15; lo = rn_f16((a' - hi) * 2^11): a' - hi is exact
+// in fp32, |.| * 2^11 <= 2^15 so nothing overflows, and the remainder a' - hi - lo * 2^-11 is <= 2^-22 |a'|: the same class as
+// TF32x3.  The bound needs hi to be a NORMAL half (|a'| >= 2^-14, i.e. the element lies within 2^-28 of its row / column maximum).
+// Out-of-window elements do not abandon the call as long as there are few of them: the split records (row, column, a),
+// zeroes the element's half parts, and the post kernel adds a times the partner row / column of the other (raw fp32)
+// operand to C after the GEMM (a sparse rank-1 repair in full fp32 precision).  Only when a record list overflows is
+// the call marked ineligible (nonfinite[1] = gen) and left to the gated fallback (see gemm_fp16x3).
 constexpr int FIX_CAP = 4096;              // records per operand and chunk
 struct FixList {
     unsigned int *count;                   // device counter (reset by the host before the operand is split)
@@ -1023,9 +1094,8 @@ __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, uns
     }
     const float x = scale_pow2(a, e);
     const __half hh = __float2half_rn(x);
-    const __half ll = __float2half_rn((x - __half2float(hh)) * 2048.0f);
     h = __half_as_ushort(hh);
-    l = __half_as_ushort(ll);
+    l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.0f));
     if (ab != 0u && fabsf(x) < 6.103515625e-05f) {  // below 2^-14: hi would be a subnormal half -> repair record
         // The element leaves the GEMM entirely (hi = lo = 0) and is carried by the record in full fp32: a lo-only
         // representation would multiply it with the partner's hi part alone, i.e. with 11 bits (measured 4.7e-4).
@@ -1042,6 +1112,7 @@ struct SplitSpanF16 {
     int by_col;
     FixList fix;
 };
+// General operands (any alignment / leading dimension; rows are repacked to ld_out = cols rounded up to 8): four elements per thread.
 __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int *__restrict__ nonfinite, int gen) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.s.groups + s1.s.groups; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= s0.s.groups;
@@ -1074,14 +1145,56 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, c
     }
 }
 
-// Contiguous operands with cols % 8 == 0: eight elements per thread, 2 x 16-byte loads, 2 x 16-byte stores, packed conversions;
-// any +-inf / NaN in the group sends it through the careful per-element path.
-__global__ void __launch_bounds__(256) split_f16_flat_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int64_t g0, int64_t g1,
-                                                             int *__restrict__ nonfinite, int gen) {
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
-        const bool second = i >= g0;
-        const SplitSpanF16 &sp = second ? s1 : s0;
-        const int64_t j = second ? i - g0 : i;
+// Eight adjacent elements (row r, columns c .. c+7) with their scaling exponents -> packed hi / lo words.  Packed
+// conversions on the fast path; any +-inf / NaN / out-of-window element sends the group through the careful per-element path.
+__device__ __forceinline__ void split8_f16(const float (&v)[8], const int (&ex)[8], uint32_t (&hp)[4], uint32_t (&lp)[4],
+                                           int *nonfinite, int gen, const FixList &fix, int64_t r, int64_t c) {
+    uint32_t special = 0;
+    bool small = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float x0 = scale_pow2(v[2 * q], ex[2 * q]), x1 = scale_pow2(v[2 * q + 1], ex[2 * q + 1]);
+        special |= (uint32_t)((__float_as_uint(v[2 * q]) & 0x7F800000u) == 0x7F800000u) |
+                   (uint32_t)((__float_as_uint(v[2 * q + 1]) & 0x7F800000u) == 0x7F800000u);   // inf / NaN in the group?
+        small |= (x0 != 0.f && fabsf(x0) < 6.103515625e-05f) | (x1 != 0.f && fabsf(x1) < 6.103515625e-05f);
+        const __half2 h2 = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h2);
+        hp[q] = *reinterpret_cast<const uint32_t *>(&h2);
+        const __half2 l2 = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+        lp[q] = *reinterpret_cast<const uint32_t *>(&l2);
+    }
+    if (special || small) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            unsigned short h0, l0, h1, l1;
+            split_f16(v[2 * q], ex[2 * q], h0, l0, nonfinite, gen, fix, r, c + 2 * q);
+            split_f16(v[2 * q + 1], ex[2 * q + 1], h1, l1, nonfinite, gen, fix, r, c + 2 * q + 1);
+            hp[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            lp[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+    }
+}
+
+// The flat pre-pass (contiguous operands, cols % 8 == 0, 16-byte aligned: output index == input index), ONE launch:
+//   blocks [0, group_blocks): one 8-element group per thread — B with its per-column exponents (col_max from
+//       absmax_cols4_kernel; B goes first: much of it is still in L2 from that pass), then, when A's row maxima were
+//       computed by a separate launch (few long rows), A with its per-row exponents;
+//   remaining blocks: A one WARP PER ROW, fused: pass 1 reads the row and reduces its |max| (written to row_max for
+//       the GEMM epilogue), pass 2 re-reads it (L1 / L2) and splits.  A is read from HBM once instead of twice.
+struct Prep16 {
+    SplitSpanF16 a, b;
+    int64_t gb, ga;            // 8-element groups handled by the group blocks: B first, then A (ga == 0 when A is fused)
+    int64_t group_blocks;
+    int64_t a_rows;            // rows of A handled warp-per-row (0: none)
+    unsigned int *row_max_out;
+};
+__global__ void __launch_bounds__(256) prep16_kernel(const Prep16 q, int *__restrict__ nonfinite, int gen) {
+    if ((int64_t)blockIdx.x < q.group_blocks) {
+        const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        if (i >= q.gb + q.ga) return;
+        const bool second = i >= q.gb;
+        const SplitSpanF16 &sp = second ? q.a : q.b;
+        const int64_t j = second ? i - q.gb : i;
         const int64_t gpr8 = sp.s.cols >> 3;                    // 8-element groups per row
         const int64_t r = j / gpr8, c = (j - r * gpr8) << 3;   // global row (over the batch), first column
         const float4 *src = reinterpret_cast<const float4 *>(sp.s.in) + 2 * j;
@@ -1096,45 +1209,72 @@ __global__ void __launch_bounds__(256) split_f16_flat_kernel(const SplitSpanF16 
         } else {
             const int e = scale_exp(sp.max_bits[r]);
 #pragma unroll
-            for (int q = 0; q < 8; q++) ex[q] = e;
+            for (int u = 0; u < 8; u++) ex[u] = e;
         }
-        uint32_t hp[4], lp[4], special = 0;
-        bool small = false;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float x0 = scale_pow2(v[2 * q], ex[2 * q]), x1 = scale_pow2(v[2 * q + 1], ex[2 * q + 1]);
-            special |= (uint32_t)((__float_as_uint(v[2 * q]) & 0x7F800000u) == 0x7F800000u) |
-                       (uint32_t)((__float_as_uint(v[2 * q + 1]) & 0x7F800000u) == 0x7F800000u);   // inf / NaN in the group?
-            small |= (x0 != 0.f && fabsf(x0) < 6.103515625e-05f) | (x1 != 0.f && fabsf(x1) < 6.103515625e-05f);
-            const __half2 h2 = __floats2half2_rn(x0, x1);
-            const float2 hf = __half22float2(h2);
-            const __half2 l2 = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
-            hp[q] = *reinterpret_cast<const uint32_t *>(&h2);
-            lp[q] = *reinterpret_cast<const uint32_t *>(&l2);
-        }
-        if (special || small) {                          // careful per-element path (flags +-inf, keeps NaN, records out-of-window elements)
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                unsigned short h0, l0, h1, l1;
-                split_f16(v[2 * q], ex[2 * q], h0, l0, nonfinite, gen, sp.fix, r, c + 2 * q);
-                split_f16(v[2 * q + 1], ex[2 * q + 1], h1, l1, nonfinite, gen, sp.fix, r, c + 2 * q + 1);
-                hp[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                lp[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
-        }
+        uint32_t hp[4], lp[4];
+        split8_f16(v, ex, hp, lp, nonfinite, gen, sp.fix, r, c);
         reinterpret_cast<uint4 *>(sp.s.hi)[j] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         reinterpret_cast<uint4 *>(sp.s.lo)[j] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x - q.group_blocks) * 8 + (threadIdx.x >> 5);
+    if (r >= q.a_rows) return;
+    const int64_t n4 = q.a.s.cols >> 2, n8 = q.a.s.cols >> 3;
+    const float4 *s4 = reinterpret_cast<const float4 *>(q.a.s.in) + r * n4;
+    unsigned int m = 0;
+    int64_t c = lane;
+    for (; c + 96 < n4; c += 128) {   // four independent 16-byte loads in flight per lane
+        const float4 v0 = ld_ew(s4 + c), v1 = ld_ew(s4 + c + 32), v2 = ld_ew(s4 + c + 64), v3 = ld_ew(s4 + c + 96);
+        m = max(m, max(max(abs4_bits(v0), abs4_bits(v1)), max(abs4_bits(v2), abs4_bits(v3))));
+    }
+    for (; c < n4; c += 32) m = max(m, abs4_bits(ld_ew(s4 + c)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (lane == 0) q.row_max_out[r] = m;
+    const int e = scale_exp(m);
+    int ex[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) ex[u] = e;
+    uint4 *hi = reinterpret_cast<uint4 *>(q.a.s.hi) + r * n8, *lo = reinterpret_cast<uint4 *>(q.a.s.lo) + r * n8;
+    int64_t g = lane;
+    for (; g + 32 < n8; g += 64) {    // two groups (4 x 16-byte loads) in flight per lane
+        const float4 a0 = ld_ew(s4 + 2 * g), b0 = ld_ew(s4 + 2 * g + 1), a1 = ld_ew(s4 + 2 * (g + 32)), b1 = ld_ew(s4 + 2 * (g + 32) + 1);
+        const float v0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w}, v1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t hp[4], lp[4];
+        split8_f16(v0, ex, hp, lp, nonfinite, gen, q.a.fix, r, g << 3);
+        hi[g] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        lo[g] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        split8_f16(v1, ex, hp, lp, nonfinite, gen, q.a.fix, r, (g + 32) << 3);
+        hi[g + 32] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        lo[g + 32] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+    for (; g < n8; g += 32) {
+        const float4 a0 = ld_ew(s4 + 2 * g), b0 = ld_ew(s4 + 2 * g + 1);
+        const float v0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
+        uint32_t hp[4], lp[4];
+        split8_f16(v0, ex, hp, lp, nonfinite, gen, q.a.fix, r, g << 3);
+        hi[g] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        lo[g] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
     }
 }
 
-// Sparse repair after the FP16x3 GEMM (see split_f16): one block per record.  A-record (i, k, d): C[i, :] += d * B[k, :];
-// B-record (k, j, d): C[:, j] += A[:, k] * d.  A record of an operand that is shared by the whole batch applies to every
-// matrix of the batch.  atomicAdd: several records may touch the same element.  Skipped when the call went to the fallback.
-__global__ void __launch_bounds__(256) fp16_fixup_kernel(float *__restrict__ C, const float *__restrict__ A, const float *__restrict__ B,
-                                                         int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
-                                                         int64_t ldc, int64_t sA, int64_t sB, int64_t sC, FixList fa, FixList fb,
-                                                         const int *gate, int gen) {
-    if (*reinterpret_cast<const volatile int *>(gate) == gen) return;
+// After the FP16x3 GEMM, one launch, exactly one of two jobs:
+//  * the call stayed eligible: sparse repair of the recorded out-of-window elements (see split_f16), one block per
+//    record.  A-record (i, k, d): C[i, :] += d * B[k, :]; B-record (k, j, d): C[:, j] += A[:, k] * d.  A record of an operand
+//    that is shared by the whole batch applies to every matrix of the batch.  atomicAdd: several records may touch the
+//    same element.  Normally there are no records and the kernel returns at once.
+//  * the split marked the call ineligible (*gate == gen): write the TF32 lo parts of the raw operands for the gated
+//    TF32x3 fallback GEMM that follows (lo0 == nullptr: the fallback is the SIMT kernel, nothing to prepare).
+__global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, const float *__restrict__ A, const float *__restrict__ B,
+                                                        int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                                        int64_t ldc, int64_t sA, int64_t sB, int64_t sC, FixList fa, FixList fb,
+                                                        float *lo0, int64_t n0, float *lo1, int64_t n1,
+                                                        int *nonfinite, int gen) {
+    if (*reinterpret_cast<const volatile int *>(nonfinite + 1) == gen) {
+        if (lo0 != nullptr) split_tf32_body(A, lo0, n0, B, lo1, n1, nonfinite, gen);
+        return;
+    }
     const unsigned int na = min(*fa.count, (unsigned int)FIX_CAP), nb = min(*fb.count, (unsigned int)FIX_CAP);
     for (unsigned int rec = blockIdx.x; rec < na + nb; rec += gridDim.x) {
         const bool from_a = rec < na;
@@ -1163,7 +1303,8 @@ __global__ void __launch_bounds__(256) fp16_fixup_kernel(float *__restrict__ C, 
 __global__ void __launch_bounds__(256) sgemm_simt_kernel(float *__restrict__ C, const float *__restrict__ A,
                                                          const float *__restrict__ B, int64_t M, int64_t N, int64_t K,
                                                          int64_t lda, int64_t ldb, int64_t ldc, int64_t sA, int64_t sB,
-                                                         int64_t sC) {
+                                                         int64_t sC, const int *gate = nullptr, int gate_gen = 0) {
+    if (gate != nullptr && *reinterpret_cast<const volatile int *>(gate) != gate_gen) return;   // FP16x3 fallback for operands the TF32 path cannot read
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
     const int64_t b = blockIdx.z;
@@ -1292,10 +1433,12 @@ static int launch_gemm(const GemmArgs &g) {
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
     p.debug = reinterpret_cast<unsigned int *>(ctx().host_result) + 4;
     auto kern = sgemm_tf32_kernel<Cfg>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in shared-memory size is a per-device function attribute (nb200_set_device may move the context)
+    static bool attr_set[64] = {};
+    const int dev = ctx().device;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     int64_t clusters = ctx().num_sms / Cfg::CG;
     if (clusters > p.total_tiles) clusters = p.total_tiles;
@@ -1316,15 +1459,12 @@ static int launch_gemm(const GemmArgs &g) {
     return NB200_OK;
 }
 
-// gate: run only if the FP16x3 split of the same call marked it ineligible (nonfinite_flag()[1] == gen)
-static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1, bool gate = false) {
+static int launch_split(const float *in0, float *lo0, int64_t n0, const float *in1, float *lo1, int64_t n1) {
     int64_t groups = ((n0 + 3) >> 2) + ((n1 + 3) >> 2);
     if (groups == 0) return NB200_OK;
     int64_t blocks = (groups + 255) / 256;   // one 4-element group per thread, non-persistent (see common.cuh)
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-    if (gate && blocks > (int64_t)ctx().num_sms * 16) blocks = (int64_t)ctx().num_sms * 16;   // normally exits at once: keep the launch small (grid-stride loop)
-    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag(), ctx().nonfinite_gen,
-                                                                  gate ? nonfinite_flag() + 1 : nullptr, 1);
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(in0, lo0, n0, in1, lo1, n1, nonfinite_flag(), ctx().nonfinite_gen);
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }
@@ -1472,86 +1612,122 @@ static int gemm_bf16x3(const GemmArgs &g) {
     return NB200_OK;
 }
 
-// FP16x3: the BF16x3 pipeline (256x128 pair tiles: separate cross-term accumulator) with IEEE-half parts of row-scaled A /
-// column-scaled B (GemmCfg::SCALED).  11-bit parts give the TF32x3 error class at the kind::f16 rate — provided every
-// non-zero element lies within 2^-28 of its row / column maximum (split_f16).  That is decided ON THE DEVICE by the split
-// pre-pass; the host enqueues both the gated FP16x3 GEMM and the gated TF32x3 fallback (lo-split + GEMM on the raw operands),
-// exactly one of which does the work.  Requires operands the TF32 path can read (tensor_path_ok).
-// Workspace: [a_hi | a_lo | b_hi | b_lo (half) | row_max | col_max (u32) | a_lo32 | b_lo32 (fp32 lo parts of the fallback)].
+// FP16x3: the BF16x3 pipeline with IEEE-half hi parts of row-scaled A / column-scaled B (GemmCfg::SCALED): 11-bit parts give
+// the TF32x3 error class at the kind::f16 rate - provided every non-zero element lies within 2^-28 of its row / column
+// maximum (split_f16).  That is decided ON THE DEVICE by the split pre-pass; the host enqueues both the gated FP16x3 GEMM
+// (+ the sparse repair of the few elements outside the window) and the gated fallback, exactly one of which does the work.
+// Tiles per CTA pair: 256x128 with the separate cross-term accumulator (default), or 256x256 with one merged accumulator per
+// k-block whose cross products are folded with scale-input-d (GemmCfg; slower, see fp16_pair_bn).
+// The pre-pass repacks the operands, so there is no alignment / leading-dimension requirement; the fallback is TF32x3 on the
+// raw operands when the TF32 path can read them (tensor_path_ok) and the fp32 SIMT kernel otherwise.
+// Workspace: [a_hi | a_lo | b_hi | b_lo (16-bit)] [fix counters (16 B) | col_max] [row_max] [a_lo32 | b_lo32 (fp32 lo parts
+// of the TF32x3 fallback)] [fix records].
+// Measured on B200 (profiles/r2_summary.md): the merged SCALED tile is correct (max rel. error 7e-7, the K = 64 chunks shorten
+// the truncating accumulation) but SLOWER: draining a 256-column accumulator after every k-block reads 128 KB of TMEM per CTA
+// per 12 MMAs, and tcgen05.ld moves 64 B/clk per SM (2048 clk against 1536 clk of MMA time): 4096^3 GEMM 398 us vs 265 us with the
+// 256x128 tile.  Chunks of two k-blocks would need four 64 KB stages resident.  The 256x128 tile is therefore the default;
+// NB200_FP16_TILE=256 selects the merged one (tests, experiments).
+static int fp16_pair_bn(int64_t batch, int64_t M, int64_t N) {
+    (void)batch; (void)M;
+    const char *e = getenv("NB200_FP16_TILE");   // read per call
+    return (e && atoi(e) == 256 && N > 128) ? 256 : 128;
+}
+static int launch_fp16_prepass(const float *a_src, const float *b_src, const GemmArgs &g, int64_t ba, int64_t bb, bool do_a, bool do_b,
+                               SplitSpanF16 &sa, SplitSpanF16 &sb, unsigned int *row_max, unsigned int *col_max) {
+    const int64_t n_rows = ba * g.M;
+    const bool flat = (sa.s.flat || sa.s.groups == 0) && (sb.s.flat || sb.s.groups == 0);
+    const char *pe = getenv("NB200_FP16_PREPASS");
+    const bool old_prepass = pe && atoi(pe) == 0;   // A/B switch (read per call): separate |max| launches, many short column segments
+    // fused row maxima need enough rows to fill the machine with one warp per row
+    const bool fuse_a = flat && do_a && !old_prepass && n_rows >= (int64_t)ctx().num_sms * 8;
+    if (do_a && !fuse_a) {
+        int64_t blocks = (n_rows + 7) / 8;
+        if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+        absmax_rows_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(a_src, g.M, n_rows, g.K, g.lda, g.sA, row_max);
+        NB_LAUNCH_CHECK();
+    }
+    if (do_b) {
+        const bool vec4 = (g.N % 4 == 0) && sb.s.vec;
+        const int64_t bx = vec4 ? (g.N / 4 + 255) / 256 : (g.N + 255) / 256;
+        int64_t by = ((old_prepass ? 8 : 2) * ctx().num_sms + bx * bb - 1) / (bx * bb);   // row segments: ~2 blocks per SM in total
+        if (by < 1) by = 1;
+        if (by > (g.K + 7) / 8) by = (g.K + 7) / 8;
+        if (by > 65535) by = 65535;
+        if (vec4)
+            absmax_cols4_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
+        else
+            absmax_cols_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
+        NB_LAUNCH_CHECK();
+    }
+    if (sa.s.groups + sb.s.groups == 0) return NB200_OK;
+    if (flat) {
+        Prep16 q;
+        q.a = sa; q.b = sb;
+        q.gb = sb.s.groups >> 1;
+        q.ga = fuse_a ? 0 : sa.s.groups >> 1;
+        q.group_blocks = (q.gb + q.ga + 255) / 256;
+        q.a_rows = fuse_a ? n_rows : 0;
+        q.row_max_out = row_max;
+        const int64_t blocks = q.group_blocks + (q.a_rows + 7) / 8;
+        if (blocks > 0x7FFFFFFF) return set_error(NB200_EINVAL, "sgemm: operand too large for the FP16x3 pre-pass");
+        prep16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(q, nonfinite_flag(), ctx().nonfinite_gen);
+        NB_LAUNCH_CHECK();
+    } else {
+        int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
+        if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+        split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
+        NB_LAUNCH_CHECK();
+    }
+    return NB200_OK;
+}
+
 static int gemm_fp16x3(const GemmArgs &g) {
+    const bool raw_ok = tensor_path_ok(g);                       // the TF32x3 fallback can read the raw operands
     const int64_t lda = round8(g.K), ldb = round8(g.N);
     const int64_t per_a = g.M * lda, per_b = g.K * ldb;          // 16-bit elements per matrix
     int64_t chunk = g.batch;
     const int64_t budget = gemm_ws_budget();
     if (g.batch > 1) {
-        const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0)) + 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0));
+        const int64_t per = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0)) + (raw_ok ? 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0)) : 0);
         if (per > 0 && per * chunk > budget) chunk = budget / per;
         if (chunk < 1) chunk = 1;
-        if (chunk > 65535) chunk = 65535;                        // absmax_cols_kernel puts the batch on gridDim.z
+        if (chunk > 65535) chunk = 65535;                        // absmax_cols_kernel / the SIMT fallback put the batch on gridDim.z
     }
     { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
+    const int v = gemm_variant();
+    const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
+    const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? fp16_pair_bn(chunk, g.M, g.N) : 128);
+    const bool merged = cg == 2 && bn == 256;
     // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
     const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
     const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);   // 16-byte aligned sub-arrays
-    const int64_t na32 = round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)), nb32 = round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N));
+    const int64_t na32 = raw_ok ? round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)) : 0, nb32 = raw_ok ? round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N)) : 0;
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;   // matrices of each operand in this chunk
-        const int64_t n_rows = ba * g.M;
-        const int64_t fix_bytes = 16 + 2 * (int64_t)FIX_CAP * (int64_t)sizeof(int4);
-        int rc = ensure_gemm_ws((na + nbb) * 4 + (rows_layout + cols_layout) * 4 + (na32 + nb32) * 4 + fix_bytes + 1024);
+        const int64_t fix_bytes = 2 * (int64_t)FIX_CAP * (int64_t)sizeof(int4);
+        int rc = ensure_gemm_ws((na + nbb) * 4 + 16 + (rows_layout + cols_layout) * 4 + (na32 + nb32) * 4 + fix_bytes + 1024);
         if (rc != NB200_OK) return rc;
         __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);   // (16-bit storage; the contents are IEEE half)
         __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
-        unsigned int *row_max = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);
-        unsigned int *col_max = row_max + rows_layout;
-        float *a_lo32 = reinterpret_cast<float *>(col_max + cols_layout);
+        unsigned int *fix_cnt = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);   // [0] A records, [1] B records (16-byte slot)
+        unsigned int *col_max = fix_cnt + 4;                                               // zeroed together with the counters
+        unsigned int *row_max = col_max + cols_layout;
+        float *a_lo32 = reinterpret_cast<float *>(row_max + rows_layout);
         float *b_lo32 = a_lo32 + na32;
-        unsigned int *fix_cnt = reinterpret_cast<unsigned int *>(b_lo32 + nb32);   // [0] A records, [1] B records (16-byte slot)
-        FixList fix_a{fix_cnt, reinterpret_cast<int4 *>(fix_cnt + 4)}, fix_b{fix_cnt + 1, reinterpret_cast<int4 *>(fix_cnt + 4) + FIX_CAP};
+        int4 *recs = reinterpret_cast<int4 *>(b_lo32 + nb32);
+        FixList fix_a{fix_cnt, recs}, fix_b{fix_cnt + 1, recs + FIX_CAP};
         const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
         const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once (its records persist)
-        if (do_a) NB_CUDA(cudaMemsetAsync(fix_cnt, 0, 4, ctx().stream));
-        if (do_b) NB_CUDA(cudaMemsetAsync(fix_cnt + 1, 0, 4, ctx().stream));
-        if (do_a) {
-            int64_t blocks = (n_rows + 7) / 8;
-            if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-            absmax_rows_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(a_src, g.M, n_rows, g.K, g.lda, g.sA, row_max);
-            NB_LAUNCH_CHECK();
-        }
-        if (do_b) {
-            NB_CUDA(cudaMemsetAsync(col_max, 0, (size_t)(bb * g.N) * 4, ctx().stream));
-            const bool vec4 = (g.N % 4 == 0);                     // (ldb % 4 == 0 and 16-byte bases: tensor_path_ok)
-            const int64_t bx = vec4 ? (g.N / 4 + 255) / 256 : (g.N + 255) / 256;
-            int64_t by = (8 * ctx().num_sms + bx * bb - 1) / (bx * bb);   // row segments: ~8 blocks per SM in total
-            if (by < 1) by = 1;
-            if (by > (g.K + 3) / 4) by = (g.K + 3) / 4;
-            if (by > 65535) by = 65535;
-            if (vec4)
-                absmax_cols4_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
-            else
-                absmax_cols_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
-            NB_LAUNCH_CHECK();
-        }
+        // one memset: both record counters and the column maxima (atomicMax targets) when B is prepared, else A's counter only
+        if (do_b) NB_CUDA(cudaMemsetAsync(do_a ? fix_cnt : fix_cnt + 1, 0, (size_t)(do_a ? 16 : 12) + (size_t)(bb * g.N) * 4, ctx().stream));
+        else if (do_a) NB_CUDA(cudaMemsetAsync(fix_cnt, 0, 4, ctx().stream));
         SplitSpanF16 sa, sb;
         sa.s = make_span(a_src, a_hi, a_lo, do_a ? ba : 0, g.M, g.K, g.lda, g.sA);
         sa.max_bits = row_max; sa.by_col = 0; sa.fix = fix_a;
         sb.s = make_span(b_src, b_hi, b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
         sb.max_bits = col_max; sb.by_col = 1; sb.fix = fix_b;
-        if ((sa.s.flat || sa.s.groups == 0) && (sb.s.flat || sb.s.groups == 0) && sa.s.groups + sb.s.groups > 0) {
-            const int64_t g0 = sa.s.groups >> 1, g1 = sb.s.groups >> 1;   // 8-element groups
-            int64_t blocks = (g0 + g1 + 255) / 256;
-            if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-            split_f16_flat_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, g0, g1, nonfinite_flag(), ctx().nonfinite_gen);
-            NB_LAUNCH_CHECK();
-        } else if (sa.s.groups + sb.s.groups > 0) {
-            int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
-            if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-            split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
-            NB_LAUNCH_CHECK();
-        }
-        const int v = gemm_variant();
-        const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
+        if ((rc = launch_fp16_prepass(a_src, b_src, g, ba, bb, do_a, do_b, sa, sb, row_max, col_max)) != NB200_OK) return rc;
         // (1) FP16x3 product, runs unless the split marked the call ineligible
         GemmArgs c = g;
         c.batch = nb;
@@ -1562,36 +1738,49 @@ static int gemm_fp16x3(const GemmArgs &g) {
         c.C = g.C + b0 * g.sC;
         c.row_max = row_max; c.col_max = col_max;
         c.gate_want = 0;
-        rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
+        if (merged) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
+        else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
         if (rc != NB200_OK) return rc;
-        // (1b) sparse repair of the recorded out-of-window elements (normally none: the kernel returns at once)
-        fp16_fixup_kernel<<<256, 256, 0, ctx().stream>>>(g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB,
-                                                         g.sC, fix_a, fix_b, nonfinite_flag() + 1, ctx().nonfinite_gen);
-        NB_LAUNCH_CHECK();
-        // (2) TF32x3 fallback on the raw operands, runs only if it did
+        // (2) eligible: sparse repair of the recorded out-of-window elements (normally none: returns at once);
+        //     ineligible: TF32 lo parts of BOTH raw operands of this chunk (a shared operand is split again with every chunk:
+        //     an earlier chunk's fallback split may never have run)
         const int64_t s_a = span(ba, g.sA, g.M, g.lda, g.K), s_b = span(bb, g.sB, g.K, g.ldb, g.N);
-        if ((rc = launch_split(a_src, a_lo32, do_a ? s_a : 0, b_src, b_lo32, do_b ? s_b : 0, true)) != NB200_OK) return rc;
-        GemmArgs f = g;
-        f.batch = nb;
-        f.A = a_src; f.A_lo = a_lo32; f.B = b_src; f.B_lo = b_lo32;
-        f.C = g.C + b0 * g.sC;
-        f.gate_want = 1;
-        if ((rc = dispatch_cfg<3>(f)) != NB200_OK) return rc;
+        fp16_post_kernel<<<(unsigned)(ctx().num_sms * 4), 256, 0, ctx().stream>>>(g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb,
+                                                                                  g.ldc, g.sA, g.sB, g.sC, fix_a, fix_b, raw_ok ? a_lo32 : nullptr, s_a,
+                                                                                  raw_ok ? b_lo32 : nullptr, s_b, nonfinite_flag(), ctx().nonfinite_gen);
+        NB_LAUNCH_CHECK();
+        // (3) the gated fallback, runs only if the call was marked: TF32x3 on the raw operands, bit-identical to a TF32X3 call
+        if (raw_ok) {
+            GemmArgs f = g;
+            f.batch = nb;
+            f.A = a_src; f.A_lo = a_lo32; f.B = b_src; f.B_lo = b_lo32;
+            f.C = g.C + b0 * g.sC;
+            f.gate_want = 1;
+            if ((rc = dispatch_cfg<3>(f)) != NB200_OK) return rc;
+        } else {
+            dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)nb);
+            sgemm_simt_kernel<<<grid, 256, 0, ctx().stream>>>(g.C + b0 * g.sC, a_src, b_src, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
+                                                              nonfinite_flag() + 1, ctx().nonfinite_gen);
+            NB_LAUNCH_CHECK();
+        }
     }
     return NB200_OK;
 }
 
-// AUTO = the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every input: TF32x3 (<= 3 * 2^-22 per
-// product plus the chunked accumulation, measured 1.8e-6).  BF16x3 is twice as fast on the tensor pipe but its bound is
-// only statistical: each product may be off by up to 2^-16 + 2 * 2^-17 (dropped a2.b2 and the split remainders) — zero-mean,
-// so it averages out over K for ordinary data (measured 1.2-2.5e-6) but adds up coherently for e.g. constant matrices
-// (tests/test_gemm_split_model.py: 4.7 % of random constant pairs exceed 1e-5).  It therefore has to be asked for:
-// precision = NB200_GEMM_BF16X3 per call, or NB200_GEMM_AUTO_MODE=bf16x3 in the environment to let AUTO use it for K >= 128.
+// AUTO = the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every input: FP16x3 (per product
+// <= 3 * 2^-22 plus the chunked accumulation; measured ~3e-6),
+// whose out-of-window handling (sparse repair / gated TF32x3 fallback) is decided on the device.  TF32x3 has the same
+// class of bound at half the tensor rate and is what AUTO uses for K < 128 (pre-pass not worth it) and what the FP16x3
+// fallback runs.  BF16x3 is as fast as FP16x3 but its bound is only statistical: each product may be off by up to
+// 2^-16 + 2 * 2^-17 (dropped a2.b2 and the split remainders) - zero-mean, so it averages out over K for ordinary data
+// (measured 1.2-2.5e-6) but adds up coherently for e.g. constant matrices (tests/test_gemm_split_model.py: 4.7 % of random
+// constant pairs exceed 1e-5).  It has to be asked for: precision = NB200_GEMM_BF16X3 per call.
+// NB200_GEMM_AUTO_MODE = tf32x3 | bf16x3 | fp16x3 overrides what AUTO stands for at K >= 128.
 int gemm_resolve_precision(int precision, int64_t K) {
     if (precision != NB200_GEMM_AUTO) return precision;
     static const char *mode = getenv("NB200_GEMM_AUTO_MODE");
-    static const int fast = !mode ? NB200_GEMM_TF32X3 : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
-                                  : strcmp(mode, "fp16x3") == 0 ? NB200_GEMM_FP16X3 : NB200_GEMM_TF32X3;
+    static const int fast = !mode ? NB200_GEMM_FP16X3 : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
+                                  : strcmp(mode, "tf32x3") == 0 ? NB200_GEMM_TF32X3 : NB200_GEMM_FP16X3;
     return K >= 128 ? fast : NB200_GEMM_TF32X3;
 }
 
@@ -1608,7 +1797,10 @@ static int gemm_impl(GemmArgs g, int precision) {
     const bool bf16_ok = g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
     static const bool force_simt = getenv("NB200_GEMM_FORCE_SIMT") != nullptr;   // debugging switch, read once
     if (precision == NB200_GEMM_BF16X3 && bf16_ok && !force_simt) return gemm_bf16x3(g);
-    if (precision == NB200_GEMM_FP16X3 && bf16_ok && tensor_path_ok(g) && !force_simt) return gemm_fp16x3(g);
+    if (precision == NB200_GEMM_FP16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g);
+    // TF32X3 asked for on operands the TF32 path cannot read (4-byte aligned views, ld % 4 != 0): the FP16x3 pre-pass
+    // repacks them, same class of guaranteed bound, so they stay on the tensor pipe instead of the fp32 SIMT kernel
+    if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g);
     if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);

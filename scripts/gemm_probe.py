@@ -14,13 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 PNAME = {0: "x3", 1: "x1", 2: "bf16x3", 4: "fp16x3"}
-VARIANTS = {"cg1_bn256": 384, "cg1_bn128": 320, "cg2_bn256": 640, "cg2_bn128": 576}
+VARIANTS = {"auto": 0, "cg1_bn256": 384, "cg1_bn128": 320, "cg2_bn256": 640, "cg2_bn128": 576}
 
 
 def child(variant: str, precision: int, sizes):
     import ctypes as C
     import torch
-    os.environ["NB200_GEMM_VARIANT"] = str(VARIANTS[variant])
+    if VARIANTS[variant]:
+        os.environ["NB200_GEMM_VARIANT"] = str(VARIANTS[variant])
     import numpower_b200 as nb
     lib = nb.lib()
     nb._lib.check(lib.nb200_init(0))

@@ -12,9 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpower_b200 as nb
 
-lib = nb.lib()
-lib.nb200_debug_tcgen05_probe.restype = C.c_int
-lib.nb200_debug_tcgen05_probe.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p] * 4
+lib = nb.lib()   # libnb200.so first: the probe library links against it
+dbg = C.CDLL(os.path.join(ROOT, "numpower_b200", "libnb200_debug.so"))   # bring-up probes live outside the product library
+dbg.nb200_debug_tcgen05_probe.restype = C.c_int
+dbg.nb200_debug_tcgen05_probe.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p] * 4
 assert lib.nb200_init(0) == 0
 
 
@@ -45,7 +46,7 @@ for flags, b_layout, lbo, sbo, kstep in CASES:
     stld = torch.full((128 * 32,), -7.0, device="cuda")
     acc = torch.full((128 * 128,), -7.0, device="cuda")
     info = torch.zeros(16, dtype=torch.int32, device="cuda")
-    rc = lib.nb200_debug_tcgen05_probe(A.data_ptr(), B.data_ptr(), Bt.data_ptr(), K, 128, K, flags, b_layout, lbo, sbo, kstep, smem.data_ptr(), stld.data_ptr(),
+    rc = dbg.nb200_debug_tcgen05_probe(A.data_ptr(), B.data_ptr(), Bt.data_ptr(), K, 128, K, flags, b_layout, lbo, sbo, kstep, smem.data_ptr(), stld.data_ptr(),
                                        acc.data_ptr(), info.data_ptr())
     rec = {"flags": flags, "b_layout": b_layout, "lbo": lbo, "sbo": sbo, "kstep": kstep, "rc": rc, "err": lib.nb200_last_error().decode() if rc else ""}
     if rc == 0:

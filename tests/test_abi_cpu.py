@@ -66,12 +66,13 @@ def test_product_never_imports_oracle():
 
 
 def test_gemm_auto_resolves_to_the_guaranteed_mode_by_default(monkeypatch):
-    """NB200_GEMM_AUTO (what nd::matmul passes) = TF32X3 unless the deployment opts into a faster mode; explicit modes are
-    returned unchanged.  Pure host logic: callable without a GPU."""
+    """NB200_GEMM_AUTO (what nd::matmul passes) = FP16X3 for K >= 128 (guaranteed bound at the kind::f16 rate, device-side
+    repair / TF32X3 fallback) and TF32X3 below; explicit modes are returned unchanged.  Pure host logic: callable without a GPU."""
     monkeypatch.delenv("NB200_GEMM_AUTO_MODE", raising=False)
     import numpower_b200 as nb
     lib = nb.lib()
-    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 4096) == nb.TF32X3
+    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 4096) == nb.FP16X3
+    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 128) == nb.FP16X3
     assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 16) == nb.TF32X3
     for mode in (nb.TF32X3, nb.TF32X1, nb.BF16X3, nb.FP16X3):
         assert lib.nb200_gemm_resolve_precision(mode, 4096) == mode

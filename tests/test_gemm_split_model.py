@@ -238,3 +238,42 @@ def test_fp16x3_sparse_fixup_model_restores_out_of_window_elements():
     c, repaired = fp16x3_model_with_fixup(a, b)
     assert repaired == 2
     assert (np.abs(c - exact) / np.abs(exact)).max() <= 2.0 ** -20
+
+
+# ------------------------------------------------------------------ FP16x3, merged 256x256 tile: scale-input-d accumulation
+def fp16x3_merged_model(a, b, kc=64):
+    """GemmCfg<SCALED, MERGED> (sgemm_tcgen05.cu): the lo parts are stored times 2^11, so the two cross products of a k-block
+    come out 2^11 too large; they are accumulated FIRST (fp32, in TMEM) and the first a_hi.b_hi MMA of the block carries
+    tcgen05.mma's scale-input-d = 11 (D = A.B + D * 2^-11, exact power of two).  Blocks of kc = 64 along K are then added
+    round-to-nearest in fp32 registers.  Returns None when an element is outside the window (repair / fallback path)."""
+    ea = scale_exp(np.abs(a).max(axis=1))[:, None]
+    eb = scale_exp(np.abs(b).max(axis=0))[None, :]
+    ah, al, ok_a = split_f16_scaled(a, ea)       # al, bl returned with the 2^-11 already applied
+    bh, bl, ok_b = split_f16_scaled(b, eb)
+    if not (ok_a and ok_b):
+        return None
+    tot = np.zeros((a.shape[0], b.shape[1]), np.float32)
+    for k0 in range(0, a.shape[1], kc):
+        sl = slice(k0, k0 + kc)
+        cross = ((al[:, sl] * 2048.0) @ bh[sl] + ah[:, sl] @ (bl[sl] * 2048.0)).astype(np.float32)    # what TMEM holds, x 2^11
+        d = (cross.astype(np.float64) / 2048.0).astype(np.float32)                                    # scale-input-d: exact
+        d = (d.astype(np.float64) + ah[:, sl] @ bh[sl]).astype(np.float32)
+        tot = (tot + d).astype(np.float32)                                                            # FADD.RN in the epilogue warps
+    return np.ldexp(tot.astype(np.float64), -(ea + eb))
+
+
+@pytest.mark.parametrize("k", [8, 64, 200, 1024])
+def test_fp16x3_merged_scale_input_d_matches_the_split_model(k):
+    """The merged tile computes the same three products as the 256x128 tile (fp16x3_model), only the accumulation order differs:
+    both stay within the 3 * 2^-22 split bound plus fp32 accumulation rounding."""
+    r = np.random.default_rng(300 + k)
+    a, b = r.random((48, k), dtype=np.float32), r.random((k, 40), dtype=np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    got = fp16x3_merged_model(a, b)
+    assert (np.abs(got - exact) / exact).max() <= 3 * 2.0 ** -22 + (k / 64 + 2) * 2.0 ** -24
+    assert (np.abs(got - fp16x3_model(a, b)) / exact).max() <= (k / 64 + 2) * 2.0 ** -24
+    # coherent inputs: the bound is per product, so constants do not accumulate an error beyond it
+    a[:] = 1.0004883
+    b[:] = 0.7501221
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    assert (np.abs(fp16x3_merged_model(a, b) - exact) / exact).max() <= 3 * 2.0 ** -22 + (k / 64 + 2) * 2.0 ** -24

@@ -333,13 +333,14 @@ def test_matmul_bf16x3_vs_cblas_sgemm(nb, mkn):
 
 
 def test_matmul_auto_is_the_guaranteed_mode(nb):
-    """AUTO (nd::matmul's default) == TF32X3 bit for bit: the mode whose error bound holds for every input.  BF16X3 is
-    opt-in (include/nb200.h); on a constant matrix pair its coherent split error shows, TF32X3's does not."""
+    """AUTO (nd::matmul's default) == FP16X3 bit for bit for K >= 128 and == TF32X3 below: the modes whose error bound holds
+    for every input.  BF16X3 is opt-in (include/nb200.h); on a constant matrix pair its coherent split error shows, AUTO's
+    does not."""
     r = _rng(77)
-    for (m, k, n) in ((256, 512, 256), (256, 96, 256)):
+    for (m, k, n), mode in (((256, 512, 256), nb.FP16X3), ((256, 96, 256), nb.TF32X3)):
         a, b = r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32)
         A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
-        np.testing.assert_array_equal(nb.nd.matmul(A, B).toArray(), nb.nd.matmul(A, B, nb.TF32X3).toArray())
+        np.testing.assert_array_equal(nb.nd.matmul(A, B).toArray(), nb.nd.matmul(A, B, mode).toArray())
     # coherent inputs: every product carries the same split error (values chosen next to a bf16 rounding boundary)
     a = np.full((256, 512), 1.00390613, np.float32)
     b = np.full((512, 256), 1.00390613, np.float32)
@@ -347,6 +348,125 @@ def test_matmul_auto_is_the_guaranteed_mode(nb):
     exp = ORACLE.matmul(a, b)
     assert rel_err(nb.nd.matmul(A, B).toArray(), exp).max() <= RTOL
     assert rel_err(nb.nd.matmul(A, B, nb.BF16X3).toArray(), exp).max() <= 5e-5    # documented statistical mode
+
+
+@pytest.mark.parametrize("tile", ["128", "256"])
+def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
+    """The two FP16x3 tile shapes (256x128 with the separate cross accumulator; merged 256x256 whose per-k-block accumulator
+    folds the 2^11-scaled cross products with tcgen05.mma's scale-input-d) through AUTO: random, coherent, row/column dynamic range, signed (norm-wise),
+    inf/NaN propagation, ragged shapes, batch with a shared operand.  NB200_FP16_TILE is read per call."""
+    monkeypatch.setenv("NB200_FP16_TILE", tile)
+    r = _rng(1000 + int(tile))
+    for (m, k, n) in ((256, 512, 256), (512, 1024, 768), (1000, 520, 776), (300, 136, 264), (257, 1001, 267)):
+        _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.GEMM_AUTO, RTOL)
+    # coherent: one product repeated K times, values next to rounding boundaries of the 11-bit / 8-bit parts
+    for val in (1.00390613, 1.0004883, 0.33333334, 1.9990234):
+        a = np.full((256, 640), val, np.float32)
+        b = np.full((640, 512), val * 0.7501221, np.float32)
+        got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+        assert rel_err(got, ORACLE.matmul(a, b)).max() <= RTOL
+    # rows / columns scaled by 2^-60 .. 2^60
+    a2 = (r.random((512, 160), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(512, 1))).astype(np.float32)).astype(np.float32)
+    b2 = (r.random((160, 512), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(1, 512))).astype(np.float32)).astype(np.float32)
+    exp2 = ORACLE.matmul(a2, b2)
+    ok = np.isfinite(exp2) & (np.abs(exp2) > 1e-30)
+    got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu()).toArray()
+    assert rel_err(got2[ok], exp2[ok]).max() <= RTOL
+    # elements spread over 2^-20 .. 1 inside every row / column, gathered one by one through a permutation matrix
+    g = ((r.random((256, 512), dtype=np.float32) + 0.5) * np.exp2(r.integers(-20, 1, size=(256, 512))).astype(np.float32)).astype(np.float32)
+    perm = r.permutation(512)
+    pm = np.zeros((512, 512), np.float32)
+    pm[perm, np.arange(512)] = 1.0
+    got = nb.nd.matmul(nb.NDArray.array(g).gpu(), nb.NDArray.array(pm).gpu()).toArray()
+    assert rel_err(got, g[:, perm]).max() <= 2.0 ** -19
+    # inf / NaN propagate like cblas_sgemm
+    a3 = r.random((256, 256), dtype=np.float32)
+    b3 = r.random((256, 512), dtype=np.float32)
+    a3[3, 7] = np.inf; a3[100, 5] = -np.inf; b3[9, 200] = np.nan; b3[7, 50] = 0.0
+    exp3 = ORACLE.matmul(a3, b3)
+    got3 = nb.nd.matmul(nb.NDArray.array(a3).gpu(), nb.NDArray.array(b3).gpu()).toArray()
+    np.testing.assert_array_equal(np.isnan(got3), np.isnan(exp3))
+    np.testing.assert_array_equal(np.isposinf(got3), np.isposinf(exp3))
+    np.testing.assert_array_equal(np.isneginf(got3), np.isneginf(exp3))
+    fin = np.isfinite(exp3)
+    assert rel_err(got3[fin], exp3[fin]).max() <= 2e-3
+    # signed inputs, norm-wise
+    a4 = (r.random((640, 1024), dtype=np.float32) * 2 - 1).astype(np.float32)
+    b4 = (r.random((1024, 512), dtype=np.float32) * 2 - 1).astype(np.float32)
+    got4 = nb.nd.matmul(nb.NDArray.array(a4).gpu(), nb.NDArray.array(b4).gpu()).toArray()
+    scale = (np.abs(a4).astype(np.float64) @ np.abs(b4).astype(np.float64)).max()
+    assert np.abs(got4.astype(np.float64) - ORACLE.matmul(a4, b4)).max() / scale <= RTOL
+    # out-of-window elements: repaired (few) / fallback (many) - the fallback is bit for bit the TF32X3 result
+    a5 = r.random((384, 256), dtype=np.float32) + 0.25
+    b5 = r.random((256, 512), dtype=np.float32) + 0.25
+    a5[17, 5] = a5[17].max() * np.float32(2.0 ** -40)
+    b5[:, 11] = 0.0
+    b5[5, 11] = 1.5
+    exp5 = ORACLE.matmul(a5, b5)
+    got5 = nb.nd.matmul(nb.NDArray.array(a5).gpu(), nb.NDArray.array(b5).gpu()).toArray()
+    assert rel_err(got5[17, 11], exp5[17, 11]) <= RTOL and rel_err(got5, exp5).max() <= RTOL
+    a6 = a5.copy()
+    a6[:40, :128] *= np.float32(2.0 ** -40)
+    A6, B5 = nb.NDArray.array(a6).gpu(), nb.NDArray.array(b5).gpu()
+    np.testing.assert_array_equal(nb.nd.matmul(A6, B5).toArray(), nb.nd.matmul(A6, B5, nb.TF32X3).toArray())
+    # batch with a shared B through the C-ABI
+    lib = nb.lib()
+    batch, M, N, K = 3, 256, 264, 200
+    a7, b7 = r.random((batch, M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
+    da, db, dc = _dev(nb, a7), _dev(nb, b7), _dev(nb, np.zeros((batch, M, N), np.float32))
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, nb.GEMM_AUTO) == 0, lib.nb200_last_error()
+    got7 = _fetch(nb, dc, (batch, M, N))
+    for i in range(batch):
+        assert rel_err(got7[i], ORACLE.matmul(a7[i], b7)).max() <= RTOL
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
+def test_matmul_unaligned_operands_stay_on_the_tensor_path(nb):
+    """Leading dimensions that are not multiples of 4 and 4-byte aligned bases (row views): the FP16x3 pre-pass repacks the
+    operands, so AUTO and TF32X3 calls neither fail nor drop to the fp32 SIMT kernel (one tcgen05 GEMM launch is counted by
+    its runtime: a 1030^3 SIMT product takes > 1 ms, the tensor path a few tens of microseconds); results within 1e-5."""
+    import time
+    lib = nb.lib()
+    r = _rng(4097)
+    M = N = K = 1030                      # 1030 % 4 == 2
+    a, b = r.random((M + 1, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
+    da, db, dc = _dev(nb, a), _dev(nb, b), _dev(nb, np.zeros((M, N), np.float32))
+    a_view = da.value + 4 * K             # row 1 of A: 8-byte aligned base, ld % 4 == 2
+    exp = ORACLE.matmul(np.ascontiguousarray(a[1:]), b)
+    for prec in (nb.GEMM_AUTO, nb.TF32X3):
+        assert lib.nb200_sgemm(dc, a_view, db, M, N, K, K, N, N, prec) == 0, lib.nb200_last_error()
+        assert rel_err(_fetch(nb, dc, (M, N)), exp).max() <= RTOL
+    lib.nb200_synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        assert lib.nb200_sgemm(dc, a_view, db, M, N, K, K, N, N, nb.GEMM_AUTO) == 0
+    lib.nb200_synchronize()
+    per_call = (time.perf_counter() - t0) / 10
+    assert per_call < 1e-3, f"{per_call * 1e3:.2f} ms per 1030^3 call: not on the tensor path"
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
+def test_fp16x3_shared_operand_fallback_in_a_late_chunk(nb, monkeypatch):
+    """batch processed in several workspace chunks, B shared (stride 0), and only a LATE chunk of A holds too many
+    out-of-window elements.  The fallback of that chunk needs the TF32 lo parts of the shared B although chunk 0 (eligible)
+    never wrote them: the post kernel splits both operands of every chunk that falls back."""
+    lib = nb.lib()
+    r = _rng(34)
+    batch, M, N, K = 5, 256, 128, 512
+    a = r.random((batch, M, K), dtype=np.float32) + 0.25
+    b = r.random((K, N), dtype=np.float32) + 0.25
+    a[3, :40, :128] *= np.float32(2.0 ** -40)          # 5120 out-of-window elements in batch 3 only (> the 4096-record cap)
+    da, db = _dev(nb, a), _dev(nb, b)
+    dc = _dev(nb, np.zeros((batch, M, N), np.float32))
+    monkeypatch.setenv("NB200_GEMM_WS_BUDGET_MB", "1")
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, nb.FP16X3) == 0, lib.nb200_last_error()
+    got = _fetch(nb, dc, (batch, M, N))
+    for i in range(batch):
+        assert rel_err(got[i], ORACLE.matmul(a[i], b)).max() <= RTOL, i
+    for p in (da, db, dc):
+        lib.nb200_free(p)
 
 
 @pytest.mark.parametrize("mkn", [(128, 128, 256), (384, 1024, 640), (1000, 520, 776), (333, 77, 129), (257, 1001, 67), (2048, 2048, 512)])
