@@ -125,6 +125,10 @@ void *nb200_stream(void);
 int nb200_set_stream(void *cuda_stream);
 /* Number of kernels this library has launched since init (bench.py "gpu_launches"). */
 int64_t nb200_launch_count(void);
+/* Diagnostics: when `dev_slots` (>= 16 device uint64 words; "first" slots preset to ~0, "last" slots to 0) is set, the kernels
+ * of the matmul pipeline stamp %globaltimer nanoseconds into it (slot map: csrc/common.cuh); NULL switches it off.
+ * scripts/gemm_timeline.py turns the stamps into profiles/r2_gemm_timeline.json. */
+int nb200_trace_enable(unsigned long long *dev_slots);
 /* Returns and clears the sticky math-domain flag set by arccos/arccosh/arctanh
  * (synchronises). 0 = none. */
 int nb200_poll_domain_error(int *flag);

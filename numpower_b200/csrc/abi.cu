@@ -104,6 +104,7 @@ int ensure_scratch(int64_t bytes) {
 
 int ensure_gemm_ws(int64_t bytes) {
     Ctx &c = g_ctx;
+    c.ctl_stride = -1;   // whoever asks for the workspace may overwrite the FP16x3 control blocks; gemm_fp16x3 re-validates its own layout
     if (bytes <= c.gemm_ws_bytes) return NB200_OK;
     if (c.gemm_ws) {
         NB_CUDA(cudaStreamSynchronize(c.stream));
@@ -192,6 +193,12 @@ extern "C" int nb200_set_stream(void *cuda_stream) {
 }
 
 extern "C" int64_t nb200_launch_count(void) { return ctx().launches; }
+
+extern "C" int nb200_trace_enable(unsigned long long *dev_slots) {
+    NB_READY();
+    ctx().trace = dev_slots;
+    return NB200_OK;
+}
 
 extern "C" int nb200_poll_domain_error(int *flag) {
     NB_READY();

@@ -25,6 +25,11 @@ struct Ctx {
     // GEMM workspace (3xTF32 lo parts)
     void *gemm_ws = nullptr;
     int64_t gemm_ws_bytes = 0;
+    // FP16x3 control blocks at the start of gemm_ws (record counters, pre-pass barrier, column maxima), double-buffered by call
+    // parity: the pre-pass of call n zeroes the block call n+1 will use, so steady-state calls need no memset (sgemm_tcgen05.cu)
+    int64_t ctl_stride = -1;              // bytes per block in the current layout; -1: layout unknown (workspace used by another mode / reallocated)
+    int64_t ctl_ready[2] = {0, 0};        // leading bytes of each block known to be zero
+    int ctl_parity = 0;
     unsigned int *ticket = nullptr;       // last-block-done counters
     int *domain_flag = nullptr;           // sticky math-domain flag (device)
     float *host_result = nullptr;         // pinned 64-byte result slot
@@ -33,6 +38,7 @@ struct Ctx {
     int64_t live_allocs = 0;
     int64_t live_bytes = 0;
     int64_t launches = 0;
+    unsigned long long *trace = nullptr;  // optional device buffer for %globaltimer stamps of the GEMM pipeline (nb200_trace_enable)
 };
 
 Ctx &ctx();
@@ -93,6 +99,38 @@ __device__ __forceinline__ float ldg_stream(const float *p) {
     float v;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
+}
+
+// ---- optional timeline of the matmul pipeline: kernels stamp %globaltimer (ns) into Ctx::trace when it is set.
+// Slots: 0 pre-pass first CTA starts | 1 its phase A done | 2 its phase B1 done | 3 grid barrier passed | 4 last pre-pass CTA done |
+//        5 GEMM first CTA enters | 6 it passed griddepcontrol.wait | 7 last GEMM CTA done | 8 post kernel enters | 9 post kernel done |
+//        10 gated fallback enters | 11 gated fallback done.  "first" = atomicMin over the CTAs, "last" = atomicMax.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_min(unsigned long long *trace, int slot) { if (trace) atomicMin(trace + slot, global_ns()); }
+__device__ __forceinline__ void trace_max(unsigned long long *trace, int slot) { if (trace) atomicMax(trace + slot, global_ns()); }
+
+// L2 eviction priority for 128-bit accesses goes through a cache-policy operand (the plain .L2::evict_* qualifiers exist only for
+// 256-bit accesses on sm_100).  evict_first: stream-once data that must not push a working set out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ldg_stream_l2(const float4 *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_l2(uint4 *p, const uint4 &v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_l2(uint2 *p, const uint2 &v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.b32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -131,6 +131,7 @@ struct GemmParams {
     const int *nonfinite;      // x3 modes: the split pre-pass stores nonfinite_gen here when an operand holds +-inf (see lo_part)
     int nonfinite_gen;         // this call's tag (a fresh value per call instead of a memset per call)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
+    unsigned long long *trace; // optional timeline stamps (common.cuh), nullptr normally
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -191,6 +192,13 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still running (once every CTA of the predecessor has called launch_dependents or exited);
+// griddepcontrol.wait blocks until the predecessor has completed and its writes are visible.  Every kernel of a chain executes
+// the wait before it exits, so completion stays ordered along the stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <int CG>
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -375,7 +383,16 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   const GemmParams p) {
     constexpr int CG = Cfg::CG, BN = Cfg::BN, BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
     constexpr int PASSES = Cfg::PASSES, NPART = Cfg::NPART;
-    if (p.gate != nullptr && ((*reinterpret_cast<const volatile int *>(p.gate) == p.gate_gen) != (p.gate_want != 0))) return;   // uniform over the grid
+    // Gated fallback (gate_want = 1: run only if the pre-pass marked the call): normally not needed, leave before any set-up.
+    const int tslot = (p.gate != nullptr && p.gate_want != 0) ? 10 : 5;
+    if (threadIdx.x == 0) trace_min(p.trace, tslot);
+    if (p.gate != nullptr && p.gate_want != 0) {
+        pdl_wait();
+        if (*reinterpret_cast<const volatile int *>(p.gate) != p.gate_gen) {   // uniform over the grid
+            if (threadIdx.x == 0) trace_max(p.trace, 11);
+            return;
+        }
+    }
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -418,6 +435,14 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+    // Everything above touched only this CTA's shared / tensor memory and overlapped the tail of the previous kernel in the stream
+    // (the split pre-pass); the operands, the gate and the non-finite flag are read below.
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x == 0 && tslot == 5) trace_min(p.trace, 6);
+    // gate_want = 0 (FP16x3 product): skip the work if the pre-pass marked the call ineligible (the gated fallback runs instead)
+    const bool skip = p.gate != nullptr && p.gate_want == 0 && *reinterpret_cast<const volatile int *>(p.gate) == p.gate_gen;   // uniform over the grid
+    const int64_t total_tiles = skip ? 0 : p.total_tiles;
     const int64_t tiles_per_mat = (int64_t)p.tiles_m * p.tiles_n;
     auto run_epilogue = [&]() {
         // ===================== epilogue (warps 2..5; MERGED: 4..11, warps 8..11 take the upper 128 columns) =====================
@@ -426,7 +451,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         uint32_t acc_phase = 0;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
-        for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+        for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
             const bool half_tile = Cfg::MERGED && t >= p.full_items;
             const int64_t tt = half_tile ? p.full_items + ((t - p.full_items) >> 1) : t;
             const int64_t b = tt / tiles_per_mat, r = tt % tiles_per_mat;
@@ -668,7 +693,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
                 // work item -> tile (+ which half of it when the last wave is split, see launch_gemm)
                 const bool half_tile = Cfg::MERGED && t >= p.full_items;
                 const int64_t tt = half_tile ? p.full_items + ((t - p.full_items) >> 1) : t;
@@ -712,7 +737,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
-            for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+            for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
                 const int nn = (Cfg::MERGED && t >= p.full_items) ? BN / 2 : BN;
                 const uint32_t idesc = make_idesc(BM * CG, nn, FMT, FMT);
                 if constexpr (!Cfg::CHUNKED) {
@@ -813,7 +838,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
             }
         };
-        for (int64_t t = cluster_id; t < p.total_tiles; t += num_clusters) {
+        for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
             for (int kb = 0; kb < num_kb; kb++) {
                 mbar_wait(full_bar(stage), phase, p.debug, 0x700u + stage);
                 convert(a_smem(stage, 0), a_smem(stage, 1), Cfg::A_BYTES);
@@ -840,6 +865,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         tc_fence_after();
         tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
     }
+    if (threadIdx.x == 0) trace_max(p.trace, tslot == 5 ? 7 : 11);
 }
 
 // ------------------------------------------------------------------ TF32 split pre-pass (x3)
@@ -889,6 +915,7 @@ __device__ __forceinline__ void split_tf32_body(const float *__restrict__ in0, f
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ in0, float *__restrict__ lo0, int64_t n0,
                                                          const float *__restrict__ in1, float *__restrict__ lo1, int64_t n1,
                                                          int *__restrict__ nonfinite, int gen) {
+    pdl_launch_dependents();   // the GEMM that follows may set itself up while the split is still running (it waits before reading)
     split_tf32_body(in0, lo0, n0, in1, lo1, n1, nonfinite, gen);
 }
 
@@ -929,6 +956,7 @@ __global__ void __launch_bounds__(256) split_bf16_flat_kernel(const float *__res
                                                               const float *__restrict__ in1, __nv_bfloat16 *__restrict__ hi1,
                                                               __nv_bfloat16 *__restrict__ lo1, int64_t g1,
                                                               int *__restrict__ nonfinite, int gen) {
+    pdl_launch_dependents();   // see split_tf32_kernel
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < g0 + g1; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= g0;
         const int64_t j = second ? i - g0 : i;
@@ -963,6 +991,7 @@ __global__ void __launch_bounds__(256) split_bf16_flat_kernel(const float *__res
     }
 }
 __global__ void __launch_bounds__(256) split_bf16_kernel(const SplitSpan s0, const SplitSpan s1, int *__restrict__ nonfinite, int gen) {
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.groups + s1.groups; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= s0.groups;
         const SplitSpan &s = second ? s1 : s0;
@@ -1114,6 +1143,7 @@ struct SplitSpanF16 {
 };
 // General operands (any alignment / leading dimension; rows are repacked to ld_out = cols rounded up to 8): four elements per thread.
 __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int *__restrict__ nonfinite, int gen) {
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.s.groups + s1.s.groups; i += (int64_t)gridDim.x * 256) {
         const bool second = i >= s0.s.groups;
         const SplitSpanF16 &sp = second ? s1 : s0;
@@ -1145,118 +1175,301 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, c
     }
 }
 
-// Eight adjacent elements (row r, columns c .. c+7) with their scaling exponents -> packed hi / lo words.  Packed
-// conversions on the fast path; any +-inf / NaN / out-of-window element sends the group through the careful per-element path.
-__device__ __forceinline__ void split8_f16(const float (&v)[8], const int (&ex)[8], uint32_t (&hp)[4], uint32_t (&lp)[4],
-                                           int *nonfinite, int gen, const FixList &fix, int64_t r, int64_t c) {
-    uint32_t special = 0;
-    bool small = false;
+// Four adjacent elements (row r, columns c .. c+3), each with the two exact power-of-two factors of its scaling (scale_factors),
+// -> packed hi / lo half words.  Fast path: packed conversions; an element that is +-inf / NaN or (non-zero and) below 2^-14 after
+// scaling sends the quad through the careful per-element path (flags, repair records), which is kept out of line.
+struct Pow2Pair { float f1, f2; };   // 2^e as f1 * f2 (2^e itself may not be representable)
+__device__ __forceinline__ Pow2Pair scale_factors(int e) {
+    const int e1 = e / 2, e2 = e - e1;
+    return {__int_as_float((e1 + 127) << 23), __int_as_float((e2 + 127) << 23)};
+}
+// returns {hi.x, hi.y, lo.x, lo.y} by value (pointer outputs would pin the caller's fast-path results to local memory)
+__device__ __noinline__ uint4 split4_careful(float4 v, int e0, int e1, int e2, int e3, int *nonfinite, int gen,
+                                             unsigned int *fix_count, int4 *fix_recs, int64_t r, int64_t c) {
+    const FixList fix{fix_count, fix_recs};
+    unsigned short h[4], l[4];
+    split_f16(v.x, e0, h[0], l[0], nonfinite, gen, fix, r, c);
+    split_f16(v.y, e1, h[1], l[1], nonfinite, gen, fix, r, c + 1);
+    split_f16(v.z, e2, h[2], l[2], nonfinite, gen, fix, r, c + 2);
+    split_f16(v.w, e3, h[3], l[3], nonfinite, gen, fix, r, c + 3);
+    return make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                      (uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+// not in [2^-14, inf) and not zero: the element needs the careful path
+__device__ __forceinline__ bool outside_window(float x) {
+    const unsigned int b = __float_as_uint(x) & 0x7FFFFFFFu;
+    return (b - 0x38800000u) >= 0x47000000u && b != 0u;
+}
+__device__ __forceinline__ bool split4_fast(const float4 &v, const Pow2Pair &s0, const Pow2Pair &s1, const Pow2Pair &s2, const Pow2Pair &s3,
+                                            uint2 &hi, uint2 &lo) {
+    const float x0 = v.x * s0.f1 * s0.f2, x1 = v.y * s1.f1 * s1.f2, x2 = v.z * s2.f1 * s2.f2, x3 = v.w * s3.f1 * s3.f2;
+    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((x0 - f01.x) * 2048.0f, (x1 - f01.y) * 2048.0f);
+    const __half2 l23 = __floats2half2_rn((x2 - f23.x) * 2048.0f, (x3 - f23.y) * 2048.0f);
+    hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+    return outside_window(x0) | outside_window(x1) | outside_window(x2) | outside_window(x3);
+}
+
+// ---- The flat FP16x3 pre-pass (contiguous operands, cols % 8 == 0, 16-byte aligned: output index == input index): ONE persistent
+// launch whose CTAs are all co-resident (grid sized by the occupancy API); the CTAs are divided between the two operands in
+// proportion to their sizes (interleaved, so every SM hosts both kinds) and both parts stream concurrently:
+//   A-CTAs    rows of A, each held in REGISTERS between its |max| reduction and its split (32 / 64 / 128 / 256 threads per row,
+//             two 8-element groups per thread; rows longer than 4096 are re-read from L1 / L2 by the CTA that just read them).
+//             A is read from HBM once; row_max is written for the GEMM epilogue.
+//   B-CTAs    phase 1: column maxima over (matrix, 1024-column block, row segment) tiles, eight 16-byte loads in flight per
+//             thread, atomicMax into the zeroed col_max; barrier among the B-CTAs (arrival counter zeroed by the same memset as
+//             col_max; bounded spin); phase 2: the SAME CTA splits the SAME tile with the same thread-to-column mapping, rows in
+//             reverse order: the four scale factors of a thread's columns are computed once, and the tile comes back from the
+//             SM's own L1 / the near L2 partition that phase 1 pulled it into instead of from HBM.
+// Every CTA calls griddepcontrol.launch_dependents as soon as it no longer needs the rest of the grid (A-CTAs at once, B-CTAs
+// after the barrier): the GEMM's prologue (barriers, TMEM allocation, tensor-map prefetch) overlaps the tail.
+struct PrepCoop {
+    SplitSpanF16 a, b;
+    int64_t a_rows;            // rows of A over the batch (0: A is not prepared by this launch)
+    int64_t b_mats;            // matrices of B (0: B is not prepared by this launch)
+    int n_b;                   // CTAs working on B (0 <= n_b <= gridDim.x), evenly interleaved with the A-CTAs
+    unsigned int *row_max_out;
+    unsigned int *barrier;     // zero on entry
+    unsigned int *zero_ptr;    // control block of the NEXT call (other parity): zero_words words are cleared here, so that call
+    int64_t zero_words;        //   needs no memset.  Its last users (the previous call's kernels) are complete: stream order.
+    unsigned int *debug;       // pinned host words: [0] = timeout flag, [1] = tag
+    unsigned long long *trace; // optional timeline stamps (common.cuh)
+};
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int abs8_bits(const float4 &a, const float4 &b) { return max(abs4_bits(a), abs4_bits(b)); }
+// one 8-element group of a row of A (both quads share the row's factors) -> 16-byte stores
+__device__ __forceinline__ void store_group_a(const float4 &a, const float4 &b, int e, const Pow2Pair &sc, uint4 *hi, uint4 *lo, int *nonfinite,
+                                              int gen, const FixList &fix, int64_t r, int64_t c, uint64_t pol) {
+    uint2 h0, l0, h1, l1;
+    const bool bad0 = split4_fast(a, sc, sc, sc, sc, h0, l0), bad1 = split4_fast(b, sc, sc, sc, sc, h1, l1);
+    if (bad0) { const uint4 w = split4_careful(a, e, e, e, e, nonfinite, gen, fix.count, fix.recs, r, c); h0 = make_uint2(w.x, w.y); l0 = make_uint2(w.z, w.w); }
+    if (bad1) { const uint4 w = split4_careful(b, e, e, e, e, nonfinite, gen, fix.count, fix.recs, r, c + 4); h1 = make_uint2(w.x, w.y); l1 = make_uint2(w.z, w.w); }
+    st_l2(hi, make_uint4(h0.x, h0.y, h1.x, h1.y), pol);
+    st_l2(lo, make_uint4(l0.x, l0.y, l1.x, l1.y), pol);
+}
+// Rows of A held in registers: TPR threads per row, 256 / TPR rows per CTA pass, up to two groups per thread (row length <= 16 * TPR).
+template <int TPR>
+__device__ __forceinline__ void prep_a_rows(const PrepCoop &q, int rank, int n_ctas, int *nonfinite, int gen, unsigned int (*red)[8], uint64_t pol) {
+    constexpr int RPC = 256 / TPR;                         // rows per CTA pass
+    const int t = threadIdx.x % TPR, rg = threadIdx.x / TPR, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n8 = q.a.s.cols >> 3;
+    int it = 0;
+    for (int64_t base = (int64_t)rank * RPC; base < q.a_rows; base += (int64_t)n_ctas * RPC, it++) {   // uniform trip count over the CTA
+        const int64_t r = base + rg;
+        const bool live = r < q.a_rows;
+        const float4 *s4 = reinterpret_cast<const float4 *>(q.a.s.in) + r * (2 * n8);
+        float4 v[2][2];
+        unsigned int m = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const float x0 = scale_pow2(v[2 * q], ex[2 * q]), x1 = scale_pow2(v[2 * q + 1], ex[2 * q + 1]);
-        special |= (uint32_t)((__float_as_uint(v[2 * q]) & 0x7F800000u) == 0x7F800000u) |
-                   (uint32_t)((__float_as_uint(v[2 * q + 1]) & 0x7F800000u) == 0x7F800000u);   // inf / NaN in the group?
-        small |= (x0 != 0.f && fabsf(x0) < 6.103515625e-05f) | (x1 != 0.f && fabsf(x1) < 6.103515625e-05f);
-        const __half2 h2 = __floats2half2_rn(x0, x1);
-        const float2 hf = __half22float2(h2);
-        hp[q] = *reinterpret_cast<const uint32_t *>(&h2);
-        const __half2 l2 = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
-        lp[q] = *reinterpret_cast<const uint32_t *>(&l2);
-    }
-    if (special || small) {
+        for (int u = 0; u < 2; u++) {
+            const int64_t g = t + u * TPR;
+            if (live && g < n8) { v[u][0] = ldg_stream_l2(s4 + 2 * g, pol); v[u][1] = ldg_stream_l2(s4 + 2 * g + 1, pol); }
+        }
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            unsigned short h0, l0, h1, l1;
-            split_f16(v[2 * q], ex[2 * q], h0, l0, nonfinite, gen, fix, r, c + 2 * q);
-            split_f16(v[2 * q + 1], ex[2 * q + 1], h1, l1, nonfinite, gen, fix, r, c + 2 * q + 1);
-            hp[q] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            lp[q] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        for (int u = 0; u < 2; u++)
+            if (live && t + u * TPR < n8) m = max(m, abs8_bits(v[u][0], v[u][1]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if constexpr (TPR > 32) {
+            if (lane == 0) red[it & 1][warp] = m;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < TPR / 32; w++) m = max(m, red[it & 1][rg * (TPR / 32) + w]);
+        }
+        if (!live) continue;
+        if (t == 0) q.row_max_out[r] = m;
+        const int e = scale_exp(m);
+        const Pow2Pair sc = scale_factors(e);
+        uint4 *hi = reinterpret_cast<uint4 *>(q.a.s.hi) + r * n8, *lo = reinterpret_cast<uint4 *>(q.a.s.lo) + r * n8;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int64_t g = t + u * TPR;
+            if (g < n8) store_group_a(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
         }
     }
 }
-
-// The flat pre-pass (contiguous operands, cols % 8 == 0, 16-byte aligned: output index == input index), ONE launch:
-//   blocks [0, group_blocks): one 8-element group per thread — B with its per-column exponents (col_max from
-//       absmax_cols4_kernel; B goes first: much of it is still in L2 from that pass), then, when A's row maxima were
-//       computed by a separate launch (few long rows), A with its per-row exponents;
-//   remaining blocks: A one WARP PER ROW, fused: pass 1 reads the row and reduces its |max| (written to row_max for
-//       the GEMM epilogue), pass 2 re-reads it (L1 / L2) and splits.  A is read from HBM once instead of twice.
-struct Prep16 {
-    SplitSpanF16 a, b;
-    int64_t gb, ga;            // 8-element groups handled by the group blocks: B first, then A (ga == 0 when A is fused)
-    int64_t group_blocks;
-    int64_t a_rows;            // rows of A handled warp-per-row (0: none)
-    unsigned int *row_max_out;
-};
-__global__ void __launch_bounds__(256) prep16_kernel(const Prep16 q, int *__restrict__ nonfinite, int gen) {
-    if ((int64_t)blockIdx.x < q.group_blocks) {
-        const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-        if (i >= q.gb + q.ga) return;
-        const bool second = i >= q.gb;
-        const SplitSpanF16 &sp = second ? q.a : q.b;
-        const int64_t j = second ? i - q.gb : i;
-        const int64_t gpr8 = sp.s.cols >> 3;                    // 8-element groups per row
-        const int64_t r = j / gpr8, c = (j - r * gpr8) << 3;   // global row (over the batch), first column
-        const float4 *src = reinterpret_cast<const float4 *>(sp.s.in) + 2 * j;
-        const float4 a = ld_ew(src), b = ld_ew(src + 1);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        int ex[8];
-        if (sp.by_col) {
-            const uint4 *mb = reinterpret_cast<const uint4 *>(sp.max_bits + (r / sp.s.rows_per) * sp.s.cols + c);
-            const uint4 m0 = mb[0], m1 = mb[1];
-            ex[0] = scale_exp(m0.x); ex[1] = scale_exp(m0.y); ex[2] = scale_exp(m0.z); ex[3] = scale_exp(m0.w);
-            ex[4] = scale_exp(m1.x); ex[5] = scale_exp(m1.y); ex[6] = scale_exp(m1.z); ex[7] = scale_exp(m1.w);
-        } else {
-            const int e = scale_exp(sp.max_bits[r]);
+// rows longer than 4096: one CTA per row, pass 1 reduces the |max|, pass 2 re-reads the row (L1 / L2: this CTA just read it) and splits
+__device__ __forceinline__ void prep_a_rows_long(const PrepCoop &q, int rank, int n_ctas, int *nonfinite, int gen, unsigned int (*red)[8], uint64_t pol) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t n8 = q.a.s.cols >> 3;
+    int it = 0;
+    for (int64_t r = rank; r < q.a_rows; r += n_ctas, it++) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(q.a.s.in) + r * (2 * n8);
+        unsigned int m = 0;
+        for (int64_t g0 = 0; g0 < n8; g0 += 512) {
+            float4 v[2][2];
 #pragma unroll
-            for (int u = 0; u < 8; u++) ex[u] = e;
+            for (int u = 0; u < 2; u++) {
+                const int64_t g = g0 + t + u * 256;
+                if (g < n8) { v[u][0] = ld_ew(s4 + 2 * g); v[u][1] = ld_ew(s4 + 2 * g + 1); }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (g0 + t + u * 256 < n8) m = max(m, abs8_bits(v[u][0], v[u][1]));
         }
-        uint32_t hp[4], lp[4];
-        split8_f16(v, ex, hp, lp, nonfinite, gen, sp.fix, r, c);
-        reinterpret_cast<uint4 *>(sp.s.hi)[j] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        reinterpret_cast<uint4 *>(sp.s.lo)[j] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if (lane == 0) red[it & 1][warp] = m;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; w++) m = max(m, red[it & 1][w]);
+        if (t == 0) q.row_max_out[r] = m;
+        const int e = scale_exp(m);
+        const Pow2Pair sc = scale_factors(e);
+        uint4 *hi = reinterpret_cast<uint4 *>(q.a.s.hi) + r * n8, *lo = reinterpret_cast<uint4 *>(q.a.s.lo) + r * n8;
+        for (int64_t g0 = 0; g0 < n8; g0 += 512) {
+            float4 v[2][2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int64_t g = g0 + t + u * 256;
+                if (g < n8) { v[u][0] = ld_ew(s4 + 2 * g); v[u][1] = ld_ew(s4 + 2 * g + 1); }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int64_t g = g0 + t + u * 256;
+                if (g < n8) store_group_a(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, int *__restrict__ nonfinite, int gen) {
+    __shared__ unsigned int red[2][8];
+    const int t = threadIdx.x;
+    pdl_wait();   // launched with programmatic stream serialization: the operands / control blocks belong to earlier work until here
+    if (t == 0) trace_min(q.trace, 0);
+    if (blockIdx.x == gridDim.x - 1)
+        for (int64_t w = t; w < q.zero_words; w += 256) q.zero_ptr[w] = 0u;
+    // Everything except B's first read is stream-once traffic: marked evict_first so that B (read again in phase 2) stays in L2.
+    const uint64_t pol = l2_policy_evict_first();
+    // role: n_b of the gridDim.x CTAs work on B, spread evenly over the block indices
+    const int G = (int)gridDim.x, i = (int)blockIdx.x;
+    const int b_before = (int)(((int64_t)i * q.n_b) / G);
+    const bool is_b = (int)(((int64_t)(i + 1) * q.n_b) / G) > b_before;
+    if (!is_b) {
+        pdl_launch_dependents();   // nothing here needs the rest of the grid
+        const int rank = i - b_before, n_a = G - q.n_b;
+        const int64_t n8 = q.a.s.cols >> 3;
+        if (q.a_rows > 0) {
+            if (n8 <= 64) prep_a_rows<32>(q, rank, n_a, nonfinite, gen, red, pol);
+            else if (n8 <= 128) prep_a_rows<64>(q, rank, n_a, nonfinite, gen, red, pol);
+            else if (n8 <= 256) prep_a_rows<128>(q, rank, n_a, nonfinite, gen, red, pol);
+            else if (n8 <= 512) prep_a_rows<256>(q, rank, n_a, nonfinite, gen, red, pol);
+            else prep_a_rows_long(q, rank, n_a, nonfinite, gen, red, pol);
+        }
+        if (t == 0) { trace_max(q.trace, 1); trace_max(q.trace, 4); }
         return;
     }
-    const int lane = threadIdx.x & 31;
-    const int64_t r = ((int64_t)blockIdx.x - q.group_blocks) * 8 + (threadIdx.x >> 5);
-    if (r >= q.a_rows) return;
-    const int64_t n4 = q.a.s.cols >> 2, n8 = q.a.s.cols >> 3;
-    const float4 *s4 = reinterpret_cast<const float4 *>(q.a.s.in) + r * n4;
-    unsigned int m = 0;
-    int64_t c = lane;
-    for (; c + 96 < n4; c += 128) {   // four independent 16-byte loads in flight per lane
-        const float4 v0 = ld_ew(s4 + c), v1 = ld_ew(s4 + c + 32), v2 = ld_ew(s4 + c + 64), v3 = ld_ew(s4 + c + 96);
-        m = max(m, max(max(abs4_bits(v0), abs4_bits(v1)), max(abs4_bits(v2), abs4_bits(v3))));
-    }
-    for (; c < n4; c += 32) m = max(m, abs4_bits(ld_ew(s4 + c)));
+    // ---------------- B-CTAs.  Tile decomposition shared by both phases.
+    const int rank = b_before, n_b = q.n_b;
+    const int64_t K = q.b.s.rows_per, N = q.b.s.cols, n4 = N >> 2;
+    unsigned int *col_max = const_cast<unsigned int *>(q.b.max_bits);
+    int cw = 256;                                 // threads across the columns (16 bytes each); the rest stack up along the rows
+    while (cw > 32 && (cw >> 1) >= n4) cw >>= 1;
+    const int ty = t / cw, tx = t - ty * cw, TY = 256 / cw;
+    const int64_t ncb = (n4 + cw - 1) / cw;
+    int64_t nseg = ((int64_t)n_b + q.b_mats * ncb - 1) / (q.b_mats * ncb);
+    const int64_t max_seg = (K + 8 * TY - 1) / (8 * TY);
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    const int64_t per = (K + nseg - 1) / nseg;
+    const int64_t tasks = q.b_mats * nseg * ncb;
+    // phase 1: column maxima
+    for (int64_t task = rank; task < tasks; task += n_b) {
+        const int64_t cb = task % ncb, rest = task / ncb, seg = rest % nseg, mat = rest / nseg;
+        const int64_t c4 = cb * cw + tx;
+        if (c4 >= n4) continue;
+        const float4 *src = reinterpret_cast<const float4 *>(q.b.s.in) + mat * K * n4 + c4;
+        const int64_t r0 = seg * per, r1 = r0 + per < K ? r0 + per : K;
+        unsigned int mx = 0, my = 0, mz = 0, mw = 0;
+        int64_t r = r0 + ty;
+        for (; r + 7 * TY < r1; r += 8 * TY) {
+            float4 v[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if (lane == 0) q.row_max_out[r] = m;
-    const int e = scale_exp(m);
-    int ex[8];
+            for (int u = 0; u < 8; u++) v[u] = ld_ew(src + (r + u * TY) * n4);
 #pragma unroll
-    for (int u = 0; u < 8; u++) ex[u] = e;
-    uint4 *hi = reinterpret_cast<uint4 *>(q.a.s.hi) + r * n8, *lo = reinterpret_cast<uint4 *>(q.a.s.lo) + r * n8;
-    int64_t g = lane;
-    for (; g + 32 < n8; g += 64) {    // two groups (4 x 16-byte loads) in flight per lane
-        const float4 a0 = ld_ew(s4 + 2 * g), b0 = ld_ew(s4 + 2 * g + 1), a1 = ld_ew(s4 + 2 * (g + 32)), b1 = ld_ew(s4 + 2 * (g + 32) + 1);
-        const float v0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w}, v1[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
-        uint32_t hp[4], lp[4];
-        split8_f16(v0, ex, hp, lp, nonfinite, gen, q.a.fix, r, g << 3);
-        hi[g] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        lo[g] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        split8_f16(v1, ex, hp, lp, nonfinite, gen, q.a.fix, r, (g + 32) << 3);
-        hi[g + 32] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        lo[g + 32] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            for (int u = 0; u < 8; u++) {
+                mx = max(mx, finite_abs_bits(v[u].x)); my = max(my, finite_abs_bits(v[u].y));
+                mz = max(mz, finite_abs_bits(v[u].z)); mw = max(mw, finite_abs_bits(v[u].w));
+            }
+        }
+        for (; r < r1; r += TY) {
+            const float4 v = ld_ew(src + r * n4);
+            mx = max(mx, finite_abs_bits(v.x)); my = max(my, finite_abs_bits(v.y)); mz = max(mz, finite_abs_bits(v.z)); mw = max(mw, finite_abs_bits(v.w));
+        }
+        unsigned int *o = col_max + mat * N + c4 * 4;
+        if (mx) atomicMax(o, mx);
+        if (my) atomicMax(o + 1, my);
+        if (mz) atomicMax(o + 2, mz);
+        if (mw) atomicMax(o + 3, mw);
     }
-    for (; g < n8; g += 32) {
-        const float4 a0 = ld_ew(s4 + 2 * g), b0 = ld_ew(s4 + 2 * g + 1);
-        const float v0[8] = {a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, b0.w};
-        uint32_t hp[4], lp[4];
-        split8_f16(v0, ex, hp, lp, nonfinite, gen, q.a.fix, r, g << 3);
-        hi[g] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        lo[g] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    // barrier among the B-CTAs (all CTAs of the grid are resident: the host sizes it with the occupancy API)
+    __syncthreads();
+    if (t == 0) {
+        trace_max(q.trace, 2);
+        __threadfence();
+        atomicAdd(q.barrier, 1u);
+        unsigned int spins = 0;
+        while (ld_acquire_u32(q.barrier) < (unsigned int)n_b) {
+            __nanosleep(32);
+            if (++spins > (1u << 24)) {   // a protocol bug must surface as an error, never as a hung GPU
+                if (q.debug) { q.debug[0] = 1u; q.debug[1] = 0x900u; q.debug[2] = blockIdx.x; }
+                __threadfence_system();
+                asm volatile("trap;");
+            }
+        }
     }
+    __syncthreads();
+    pdl_launch_dependents();
+    if (t == 0) trace_max(q.trace, 3);
+    // phase 2: split the same tiles, last task / last rows first (most recently read = most likely still in L1 / L2)
+    const int64_t my_tasks = rank < tasks ? (tasks - 1 - rank) / n_b + 1 : 0;
+    for (int64_t k = my_tasks - 1; k >= 0; k--) {
+        const int64_t task = rank + k * n_b;
+        const int64_t cb = task % ncb, rest = task / ncb, seg = rest % nseg, mat = rest / nseg;
+        const int64_t c4 = cb * cw + tx;
+        if (c4 >= n4) continue;
+        const uint4 mb = __ldcg(reinterpret_cast<const uint4 *>(col_max + mat * N) + c4);
+        const int e0 = scale_exp(mb.x), e1 = scale_exp(mb.y), e2 = scale_exp(mb.z), e3 = scale_exp(mb.w);
+        const Pow2Pair s0 = scale_factors(e0), s1 = scale_factors(e1), s2 = scale_factors(e2), s3 = scale_factors(e3);
+        const float4 *src = reinterpret_cast<const float4 *>(q.b.s.in) + mat * K * n4 + c4;
+        uint2 *hi = reinterpret_cast<uint2 *>(q.b.s.hi) + mat * K * n4 + c4, *lo = reinterpret_cast<uint2 *>(q.b.s.lo) + mat * K * n4 + c4;
+        const int64_t r0 = seg * per, r1 = r0 + per < K ? r0 + per : K;
+        // rows r1-1-ty, r1-1-ty-TY, ... >= r0, four in flight
+        int64_t r = r1 - 1 - ty;
+        for (; r - 3 * TY >= r0; r -= 4 * TY) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = ldg_stream_l2(src + (r - u * TY) * n4, pol);   // last use of the raw tile
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t rr = r - u * TY;
+                uint2 h, l;
+                if (split4_fast(v[u], s0, s1, s2, s3, h, l)) {
+                    const uint4 w = split4_careful(v[u], e0, e1, e2, e3, nonfinite, gen, q.b.fix.count, q.b.fix.recs, mat * K + rr, c4 * 4);
+                    h = make_uint2(w.x, w.y); l = make_uint2(w.z, w.w);
+                }
+                st_l2(hi + rr * n4, h, pol);
+                st_l2(lo + rr * n4, l, pol);
+            }
+        }
+        for (; r >= r0; r -= TY) {
+            const float4 v = ldg_stream_l2(src + r * n4, pol);
+            uint2 h, l;
+            if (split4_fast(v, s0, s1, s2, s3, h, l)) {
+                const uint4 w = split4_careful(v, e0, e1, e2, e3, nonfinite, gen, q.b.fix.count, q.b.fix.recs, mat * K + r, c4 * 4);
+                h = make_uint2(w.x, w.y); l = make_uint2(w.z, w.w);
+            }
+            st_l2(hi + r * n4, h, pol);
+            st_l2(lo + r * n4, l, pol);
+        }
+    }
+    if (t == 0) trace_max(q.trace, 4);
 }
 
 // After the FP16x3 GEMM, one launch, exactly one of two jobs:
@@ -1270,12 +1483,23 @@ __global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, c
                                                         int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                                         int64_t ldc, int64_t sA, int64_t sB, int64_t sC, FixList fa, FixList fb,
                                                         float *lo0, int64_t n0, float *lo1, int64_t n1,
-                                                        int *nonfinite, int gen) {
-    if (*reinterpret_cast<const volatile int *>(nonfinite + 1) == gen) {
+                                                        int *nonfinite, int gen, unsigned long long *trace) {
+    if (threadIdx.x == 0) trace_min(trace, 8);
+    // Launched with programmatic stream serialization: these reads only touch what the PRE-PASS wrote (complete before any CTA of
+    // the GEMM passed its own griddepcontrol.wait, which precedes its launch_dependents).  In the normal case - eligible, no
+    // records - the grid leaves at once, while the GEMM is still running; one thread stays to keep completion ordered.
+    const bool fallback = *reinterpret_cast<const volatile int *>(nonfinite + 1) == gen;
+    const unsigned int na = min(*reinterpret_cast<volatile unsigned int *>(fa.count), (unsigned int)FIX_CAP),
+                       nb = min(*reinterpret_cast<volatile unsigned int *>(fb.count), (unsigned int)FIX_CAP);
+    if (!fallback && na + nb == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); trace_max(trace, 9); }
+        return;
+    }
+    pdl_wait();   // the GEMM (or, for an ineligible call, its immediate exit) is complete
+    if (fallback) {
         if (lo0 != nullptr) split_tf32_body(A, lo0, n0, B, lo1, n1, nonfinite, gen);
         return;
     }
-    const unsigned int na = min(*fa.count, (unsigned int)FIX_CAP), nb = min(*fb.count, (unsigned int)FIX_CAP);
     for (unsigned int rec = blockIdx.x; rec < na + nb; rec += gridDim.x) {
         const bool from_a = rec < na;
         const int4 q = from_a ? fa.recs[rec] : fb.recs[rec - na];
@@ -1384,6 +1608,11 @@ struct GemmArgs {
     int gate_want = -1;   // -1: ungated; 0: run unless the call was marked ineligible for FP16x3; 1: run only if it was
 };
 
+static bool pdl_enabled() {
+    static const bool on = !(getenv("NB200_PDL") && atoi(getenv("NB200_PDL")) == 0);   // A/B switch, read once
+    return on;
+}
+
 template <class Cfg>
 static int launch_gemm(const GemmArgs &g) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
@@ -1432,6 +1661,7 @@ static int launch_gemm(const GemmArgs &g) {
     p.b_batched = g.sB != 0;
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
     p.debug = reinterpret_cast<unsigned int *>(ctx().host_result) + 4;
+    p.trace = ctx().trace;
     auto kern = sgemm_tf32_kernel<Cfg>;
     // the opt-in shared-memory size is a per-device function attribute (nb200_set_device may move the context)
     static bool attr_set[64] = {};
@@ -1447,13 +1677,15 @@ static int launch_gemm(const GemmArgs &g) {
     cfg.blockDim = dim3(Cfg::THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = ctx().stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = Cfg::CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the prologue overlaps the tail of the pre-pass (pdl_wait in the kernel)
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     NB_CUDA(cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, p));
     ctx().launches++;
     return NB200_OK;
@@ -1633,14 +1865,62 @@ static int fp16_pair_bn(int64_t batch, int64_t M, int64_t N) {
     return (e && atoi(e) == 256 && N > 128) ? 256 : 128;
 }
 static int launch_fp16_prepass(const float *a_src, const float *b_src, const GemmArgs &g, int64_t ba, int64_t bb, bool do_a, bool do_b,
-                               SplitSpanF16 &sa, SplitSpanF16 &sb, unsigned int *row_max, unsigned int *col_max) {
+                               SplitSpanF16 &sa, SplitSpanF16 &sb, unsigned int *row_max, unsigned int *col_max, unsigned int *barrier,
+                               unsigned int *zero_ptr, int64_t zero_words, bool *zeroed_other) {
+    *zeroed_other = false;
     const int64_t n_rows = ba * g.M;
+    if (sa.s.groups + sb.s.groups == 0) return NB200_OK;
     const bool flat = (sa.s.flat || sa.s.groups == 0) && (sb.s.flat || sb.s.groups == 0);
-    const char *pe = getenv("NB200_FP16_PREPASS");
-    const bool old_prepass = pe && atoi(pe) == 0;   // A/B switch (read per call): separate |max| launches, many short column segments
-    // fused row maxima need enough rows to fill the machine with one warp per row
-    const bool fuse_a = flat && do_a && !old_prepass && n_rows >= (int64_t)ctx().num_sms * 8;
-    if (do_a && !fuse_a) {
+    if (flat) {
+        // one persistent launch, all CTAs co-resident (prep16_coop_kernel has a grid barrier between B's two phases)
+        static int per_sm[64] = {};
+        const int dev = ctx().device;
+        int occ = (dev >= 0 && dev < 64) ? per_sm[dev] : 0;
+        if (occ == 0) {
+            NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep16_coop_kernel, 256, 0));
+            if (occ < 1) return set_error(NB200_ECUDA, "sgemm: the FP16x3 pre-pass kernel does not fit on an SM");
+            if (dev >= 0 && dev < 64) per_sm[dev] = occ;
+        }
+        PrepCoop q;
+        q.a = sa; q.b = sb;
+        q.a_rows = do_a ? n_rows : 0;
+        q.b_mats = do_b ? bb : 0;
+        q.row_max_out = row_max;
+        q.barrier = barrier;
+        q.zero_ptr = zero_ptr; q.zero_words = zero_words;
+        q.debug = reinterpret_cast<unsigned int *>(ctx().host_result) + 4;
+        q.trace = ctx().trace;
+        // grid: every CTA resident; small problems get fewer CTAs (a CTA pass covers 256 / TPR rows of A or ~32 K elements of B)
+        const int64_t n8 = g.K >> 3;
+        const int64_t rpc = n8 <= 64 ? 8 : n8 <= 128 ? 4 : n8 <= 256 ? 2 : 1;
+        const int64_t a_elems = q.a_rows * g.K, b_elems = q.b_mats * g.K * g.N;
+        const int64_t a_ctas = (q.a_rows + rpc - 1) / rpc, b_ctas = (b_elems + 32767) / 32768;
+        int64_t grid = (int64_t)ctx().num_sms * occ;
+        if (grid > a_ctas + b_ctas) grid = a_ctas + b_ctas;
+        if (grid < 2) grid = 2;
+        // CTAs per operand in proportion to the bytes each side moves through L2: A is read once and written once (8 B per element),
+        // B is read twice and written once (12 B per element; NB200_PREP_BW overrides the B weight in percent of A's, default 150)
+        static const int64_t bw = getenv("NB200_PREP_BW") ? atoll(getenv("NB200_PREP_BW")) : 150;
+        const int64_t wa = a_elems * 100, wb = b_elems * bw;
+        int64_t n_b = a_elems == 0 ? grid : b_elems == 0 ? 0 : (int64_t)(((double)grid * (double)wb) / ((double)wa + (double)wb) + 0.5);
+        if (a_elems > 0 && b_elems > 0) { if (n_b < 1) n_b = 1; if (n_b > grid - 1) n_b = grid - 1; }
+        q.n_b = (int)n_b;
+        cudaLaunchConfig_t pc = {};
+        pc.gridDim = dim3((unsigned)grid);
+        pc.blockDim = dim3(256);
+        pc.stream = ctx().stream;
+        cudaLaunchAttribute pa[1];
+        pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // back-to-back calls: the launch latency hides behind the previous call's tail
+        pa[0].val.programmaticStreamSerializationAllowed = 1;
+        pc.attrs = pa;
+        pc.numAttrs = pdl_enabled() ? 1 : 0;
+        NB_CUDA(cudaLaunchKernelEx(&pc, prep16_coop_kernel, q, nonfinite_flag(), ctx().nonfinite_gen));
+        ctx().launches++;
+        *zeroed_other = zero_words > 0;
+        return NB200_OK;
+    }
+    // general operands (views, odd leading dimensions): separate |max| launches, then the repacking split
+    if (do_a) {
         int64_t blocks = (n_rows + 7) / 8;
         if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
         absmax_rows_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(a_src, g.M, n_rows, g.K, g.lda, g.sA, row_max);
@@ -1649,7 +1929,7 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
     if (do_b) {
         const bool vec4 = (g.N % 4 == 0) && sb.s.vec;
         const int64_t bx = vec4 ? (g.N / 4 + 255) / 256 : (g.N + 255) / 256;
-        int64_t by = ((old_prepass ? 8 : 2) * ctx().num_sms + bx * bb - 1) / (bx * bb);   // row segments: ~2 blocks per SM in total
+        int64_t by = (2 * ctx().num_sms + bx * bb - 1) / (bx * bb);   // row segments: ~2 blocks per SM in total
         if (by < 1) by = 1;
         if (by > (g.K + 7) / 8) by = (g.K + 7) / 8;
         if (by > 65535) by = 65535;
@@ -1659,25 +1939,10 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
             absmax_cols_kernel<<<dim3((unsigned)bx, (unsigned)by, (unsigned)bb), 256, 0, ctx().stream>>>(b_src, g.K, g.N, g.ldb, g.sB, col_max);
         NB_LAUNCH_CHECK();
     }
-    if (sa.s.groups + sb.s.groups == 0) return NB200_OK;
-    if (flat) {
-        Prep16 q;
-        q.a = sa; q.b = sb;
-        q.gb = sb.s.groups >> 1;
-        q.ga = fuse_a ? 0 : sa.s.groups >> 1;
-        q.group_blocks = (q.gb + q.ga + 255) / 256;
-        q.a_rows = fuse_a ? n_rows : 0;
-        q.row_max_out = row_max;
-        const int64_t blocks = q.group_blocks + (q.a_rows + 7) / 8;
-        if (blocks > 0x7FFFFFFF) return set_error(NB200_EINVAL, "sgemm: operand too large for the FP16x3 pre-pass");
-        prep16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(q, nonfinite_flag(), ctx().nonfinite_gen);
-        NB_LAUNCH_CHECK();
-    } else {
-        int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
-        if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-        split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
-        NB_LAUNCH_CHECK();
-    }
+    int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
+    if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
+    split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
+    NB_LAUNCH_CHECK();
     return NB200_OK;
 }
 
@@ -1702,32 +1967,57 @@ static int gemm_fp16x3(const GemmArgs &g) {
     const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
     const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);   // 16-byte aligned sub-arrays
     const int64_t na32 = raw_ok ? round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)) : 0, nb32 = raw_ok ? round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N)) : 0;
+    // Control blocks (16-byte slot: [0] A records, [1] B records, [2] pre-pass barrier; then col_max) live at the start of the
+    // workspace, double-buffered by call parity.  A single-chunk call uses block `parity` and its pre-pass zeroes the other one for
+    // the next call (Ctx::ctl_ready), so steady-state calls enqueue no memset; multi-chunk calls use block 0 with explicit memsets.
+    const int64_t ctl_stride = (16 + cols_layout * 4 + 255) & ~int64_t(255);
+    const bool single = chunk >= g.batch;
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;   // matrices of each operand in this chunk
         const int64_t fix_bytes = 2 * (int64_t)FIX_CAP * (int64_t)sizeof(int4);
-        int rc = ensure_gemm_ws((na + nbb) * 4 + 16 + (rows_layout + cols_layout) * 4 + (na32 + nb32) * 4 + fix_bytes + 1024);
+        Ctx &cx = ctx();
+        const void *ws_before = cx.gemm_ws;
+        const int64_t stride_before = cx.ctl_stride;
+        int rc = ensure_gemm_ws(2 * ctl_stride + (na + nbb) * 4 + rows_layout * 4 + (na32 + nb32) * 4 + fix_bytes + 1024);
         if (rc != NB200_OK) return rc;
-        __nv_bfloat16 *ws = static_cast<__nv_bfloat16 *>(ctx().gemm_ws);   // (16-bit storage; the contents are IEEE half)
+        if (cx.gemm_ws != ws_before || stride_before != ctl_stride || !single) cx.ctl_ready[0] = cx.ctl_ready[1] = 0;   // unknown contents
+        cx.ctl_stride = ctl_stride;
+        const int mine = single ? cx.ctl_parity : 0;
+        char *wsb = static_cast<char *>(cx.gemm_ws);
+        unsigned int *fix_cnt = reinterpret_cast<unsigned int *>(wsb + mine * ctl_stride);
+        unsigned int *other_ctl = reinterpret_cast<unsigned int *>(wsb + (1 - mine) * ctl_stride);
+        unsigned int *col_max = fix_cnt + 4;
+        __nv_bfloat16 *ws = reinterpret_cast<__nv_bfloat16 *>(wsb + 2 * ctl_stride);   // (16-bit storage; the contents are IEEE half)
         __nv_bfloat16 *a_hi = ws, *a_lo = ws + na, *b_hi = ws + 2 * na, *b_lo = ws + 2 * na + nbb;
-        unsigned int *fix_cnt = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);   // [0] A records, [1] B records (16-byte slot)
-        unsigned int *col_max = fix_cnt + 4;                                               // zeroed together with the counters
-        unsigned int *row_max = col_max + cols_layout;
+        unsigned int *row_max = reinterpret_cast<unsigned int *>(ws + 2 * na + 2 * nbb);
         float *a_lo32 = reinterpret_cast<float *>(row_max + rows_layout);
         float *b_lo32 = a_lo32 + na32;
         int4 *recs = reinterpret_cast<int4 *>(b_lo32 + nb32);
         FixList fix_a{fix_cnt, recs}, fix_b{fix_cnt + 1, recs + FIX_CAP};
         const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
         const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);   // a shared operand is prepared once (its records persist)
-        // one memset: both record counters and the column maxima (atomicMax targets) when B is prepared, else A's counter only
-        if (do_b) NB_CUDA(cudaMemsetAsync(do_a ? fix_cnt : fix_cnt + 1, 0, (size_t)(do_a ? 16 : 12) + (size_t)(bb * g.N) * 4, ctx().stream));
-        else if (do_a) NB_CUDA(cudaMemsetAsync(fix_cnt, 0, 4, ctx().stream));
+        const int64_t need = 16 + bb * g.N * 4;                          // counters + barrier + the column maxima (atomicMax targets)
+        if (single) {
+            if (cx.ctl_ready[mine] < need) NB_CUDA(cudaMemsetAsync(fix_cnt, 0, (size_t)need, cx.stream));
+            cx.ctl_ready[mine] = 0;                                      // in use from here on
+        } else if (do_b) {
+            NB_CUDA(cudaMemsetAsync(do_a ? fix_cnt : fix_cnt + 1, 0, (size_t)(do_a ? 16 : 12) + (size_t)(bb * g.N) * 4, cx.stream));
+        } else if (do_a) {
+            NB_CUDA(cudaMemsetAsync(fix_cnt, 0, 4, cx.stream));
+        }
         SplitSpanF16 sa, sb;
         sa.s = make_span(a_src, a_hi, a_lo, do_a ? ba : 0, g.M, g.K, g.lda, g.sA);
         sa.max_bits = row_max; sa.by_col = 0; sa.fix = fix_a;
         sb.s = make_span(b_src, b_hi, b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
         sb.max_bits = col_max; sb.by_col = 1; sb.fix = fix_b;
-        if ((rc = launch_fp16_prepass(a_src, b_src, g, ba, bb, do_a, do_b, sa, sb, row_max, col_max)) != NB200_OK) return rc;
+        bool zeroed_other = false;
+        if ((rc = launch_fp16_prepass(a_src, b_src, g, ba, bb, do_a, do_b, sa, sb, row_max, col_max, fix_cnt + 2, other_ctl, single ? need / 4 : 0,
+                                      &zeroed_other)) != NB200_OK) return rc;
+        if (single) {
+            if (zeroed_other) cx.ctl_ready[1 - mine] = need;
+            cx.ctl_parity = 1 - mine;
+        }
         // (1) FP16x3 product, runs unless the split marked the call ineligible
         GemmArgs c = g;
         c.batch = nb;
@@ -1745,10 +2035,21 @@ static int gemm_fp16x3(const GemmArgs &g) {
         //     ineligible: TF32 lo parts of BOTH raw operands of this chunk (a shared operand is split again with every chunk:
         //     an earlier chunk's fallback split may never have run)
         const int64_t s_a = span(ba, g.sA, g.M, g.lda, g.K), s_b = span(bb, g.sB, g.K, g.ldb, g.N);
-        fp16_post_kernel<<<(unsigned)(ctx().num_sms * 4), 256, 0, ctx().stream>>>(g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb,
-                                                                                  g.ldc, g.sA, g.sB, g.sC, fix_a, fix_b, raw_ok ? a_lo32 : nullptr, s_a,
-                                                                                  raw_ok ? b_lo32 : nullptr, s_b, nonfinite_flag(), ctx().nonfinite_gen);
-        NB_LAUNCH_CHECK();
+        {
+            cudaLaunchConfig_t pc = {};
+            pc.gridDim = dim3((unsigned)(ctx().num_sms * 4));
+            pc.blockDim = dim3(256);
+            pc.stream = ctx().stream;
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pa[0].val.programmaticStreamSerializationAllowed = 1;
+            pc.attrs = pa;
+            pc.numAttrs = pdl_enabled() ? 1 : 0;
+            NB_CUDA(cudaLaunchKernelEx(&pc, fp16_post_kernel, g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
+                                       fix_a, fix_b, raw_ok ? a_lo32 : (float *)nullptr, s_a, raw_ok ? b_lo32 : (float *)nullptr, s_b, nonfinite_flag(),
+                                       ctx().nonfinite_gen, ctx().trace));
+            ctx().launches++;
+        }
         // (3) the gated fallback, runs only if the call was marked: TF32x3 on the raw operands, bit-identical to a TF32X3 call
         if (raw_ok) {
             GemmArgs f = g;
@@ -1911,7 +2212,7 @@ extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, 
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
     precision = gemm_resolve_precision(precision, K);
     int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024
-                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * (round4(M) + round4(N)) + 4 * (round4(M * K) + round4(K * N)) + 16 + 2 * (int64_t)FIX_CAP * 16 + 1024
+                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * round4(M) + 2 * ((16 + 4 * round4(N) + 255) & ~int64_t(255)) + 4 * (round4(M * K) + round4(K * N)) + 2 * (int64_t)FIX_CAP * 16 + 1024
                                                  : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = gemm_ws_budget();

@@ -357,7 +357,8 @@ def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
     inf/NaN propagation, ragged shapes, batch with a shared operand.  NB200_FP16_TILE is read per call."""
     monkeypatch.setenv("NB200_FP16_TILE", tile)
     r = _rng(1000 + int(tile))
-    for (m, k, n) in ((256, 512, 256), (512, 1024, 768), (1000, 520, 776), (300, 136, 264), (257, 1001, 267)):
+    # (K = 512 / 1024: one warp per row of A in the pre-pass, 2048: one CTA per row, 9000: two-pass rows; 1001: repacking split)
+    for (m, k, n) in ((256, 512, 256), (512, 1024, 768), (1000, 520, 776), (300, 136, 264), (257, 1001, 267), (384, 2048, 520), (136, 9000, 264)):
         _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.GEMM_AUTO, RTOL)
     # coherent: one product repeated K times, values next to rounding boundaries of the 11-bit / 8-bit parts
     for val in (1.00390613, 1.0004883, 0.33333334, 1.9990234):
