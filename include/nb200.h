@@ -204,6 +204,48 @@ int nb200_gemv(float *y, const float *A, const float *x, int64_t rows, int64_t c
 /* out[cols,rows] = in[rows,cols]^T, out != in — replaces cuda_float_transpose (cuda_math.h:77). */
 int nb200_transpose2d(float *out, const float *in, int64_t rows, int64_t cols);
 
+/* ---- multi-GPU shards (SURVEY.md §8 e) -------------------------------------------------------
+ * ONE host process drives the G GPUs of a box.  The reference's only multi-GPU affordance is NDArray::setDevice
+ * (numpower.c:615-635 -> cudaSetDevice): it has no collective and no sharded operation, so everything here is new surface, not a
+ * replacement.  An array is split along its first axis into G contiguous shards ("units" = rows, matrices of a batch or elements);
+ * shard s is resident on devices[s] and every entry point takes one pointer per shard.  Calls are asynchronous on the per-device
+ * context streams (nb200_shard_synchronize joins them) unless they return a host value.  nb200_set_device keeps working: each
+ * device has its own context, allocator pool and workspace. */
+enum nb200_transport {
+    NB200_XFER_NCCL = 0,   /* one grouped ncclSend / ncclRecv per call (single-process communicators, ncclCommInitAll; NCCL is
+                            * loaded at run time with dlopen("libnccl.so.2") on first use) */
+    NB200_XFER_P2P = 1     /* cudaMemcpyPeerAsync over NVLink peer access, one stream per peer (copy engines) */
+};
+int nb200_shard_init(int ndev, const int *devices);   /* devices == NULL: 0 .. ndev-1 */
+int nb200_shard_finalize(void);
+int nb200_shard_count(int *ndev);
+int nb200_shard_device(int shard, int *device);
+/* balanced contiguous split of `units`: the first units % G shards own one unit more */
+int nb200_shard_range(int64_t units, int shard, int64_t *first, int64_t *count);
+int nb200_shard_split(int64_t units, int nshards, int shard, int64_t *first, int64_t *count);   /* same rule, pure host arithmetic */
+int nb200_shard_synchronize(void);
+/* (rows, row_elems) fp32 array on devices[root] <-> row shards (shard_ptrs[s] on devices[s]; shard_ptrs[root] may point into the
+ * root array itself: no copy).  Ordered after / before the work on the context streams involved. */
+int nb200_shard_scatter(float *const *shard_ptrs, const float *root_src, int64_t rows, int64_t row_elems, int root, int transport);
+int nb200_shard_gather(float *root_dst, const float *const *shard_ptrs, int64_t rows, int64_t row_elems, int root, int transport);
+/* resident shards, same-shape operands: one launch per device, no collective (arithmetics.c:160-926 per shard) */
+int nb200_shard_ew_binary(int op, float *const *out, const float *const *a, const float *const *b, int64_t rows, int64_t row_elems);
+int nb200_shard_ew_mul_add(float *const *out, const float *const *a, const float *const *b, const float *const *c, int64_t rows,
+                           int64_t row_elems);
+int nb200_shard_ew_unary(int op, float *const *out, const float *const *in, int64_t rows, int64_t row_elems, float p0, float p1);
+/* full reductions over the concatenation of the shards (n_total elements split by nb200_shard_range): per-shard partials folded on
+ * the host in shard order; NDArray_Min/Max NaN rule and float_argmax/argmin first-occurrence / NaN rules (calculation.c:9-59)
+ * applied to the GLOBAL index space; the argmax index is exact before the final (float) conversion. */
+int nb200_shard_reduce_full(int op, float *host_out, const float *const *in, int64_t n_total);
+int nb200_shard_argminmax(int is_max, float *host_out, const float *const *in, int64_t n_total);
+/* batched nd::matmul, batch dimension sharded.  _sharded: resident shards.  _scatter_gather: operands and result on devices[root];
+ * scatter + products + gather pipelined per `chunk` matrices per shard (chunk i multiplies while chunk i+1 lands and chunk i-1
+ * returns; the root multiplies its own share in place).  elapsed_ms != NULL: synchronises and reports the device time. */
+int nb200_sgemm_batched_sharded(float *const *C, const float *const *A, const float *const *B, int64_t batch, int64_t M, int64_t N, int64_t K,
+                                int precision);
+int nb200_sgemm_batched_scatter_gather(float *C_root, const float *A_root, const float *B_root, int64_t batch, int64_t M, int64_t N, int64_t K,
+                                       int precision, int root, int transport, int64_t chunk, float *elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

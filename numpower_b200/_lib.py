@@ -58,6 +58,20 @@ ABI = {
     "nb200_gemm_resolve_precision": (C.c_int, [C.c_int, i64]),
     "nb200_gemv": (C.c_int, [fp, fp, fp, i64, i64]),
     "nb200_transpose2d": (C.c_int, [fp, fp, i64, i64]),
+    # multi-GPU shards: pointer arrays are (c_void_p * G)
+    "nb200_shard_init": (C.c_int, [C.c_int, C.POINTER(C.c_int)]), "nb200_shard_finalize": (C.c_int, []),
+    "nb200_shard_count": (C.c_int, [C.POINTER(C.c_int)]), "nb200_shard_device": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "nb200_shard_range": (C.c_int, [i64, C.c_int, i64p, i64p]),
+    "nb200_shard_split": (C.c_int, [i64, C.c_int, C.c_int, i64p, i64p]), "nb200_shard_synchronize": (C.c_int, []),
+    "nb200_shard_scatter": (C.c_int, [C.c_void_p, fp, i64, i64, C.c_int, C.c_int]),
+    "nb200_shard_gather": (C.c_int, [fp, C.c_void_p, i64, i64, C.c_int, C.c_int]),
+    "nb200_shard_ew_binary": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, i64, i64]),
+    "nb200_shard_ew_mul_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i64]),
+    "nb200_shard_ew_unary": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, i64, i64, C.c_float, C.c_float]),
+    "nb200_shard_reduce_full": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_void_p, i64]),
+    "nb200_shard_argminmax": (C.c_int, [C.c_int, C.POINTER(C.c_float), C.c_void_p, i64]),
+    "nb200_sgemm_batched_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i64, i64, i64, i64, C.c_int]),
+    "nb200_sgemm_batched_scatter_gather": (C.c_int, [fp, fp, fp, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, i64, C.POINTER(C.c_float)]),
     # host mirror (include/nb200_host.h)
     "NB_last_error": (C.c_char_p, []),
     "NB_NDArray_FromHost": (ndp, [C.c_void_p, C.c_int, i64p]),

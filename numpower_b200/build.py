@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libnb200.so")
-SOURCES = ["abi.cu", "ew.cu", "reduce.cu", "sgemm_tcgen05.cu", "misc.cu", "host_pipeline.cu", "legacy.cu", "host/ndarray_host.cpp"]
+SOURCES = ["abi.cu", "ew.cu", "reduce.cu", "sgemm_tcgen05.cu", "misc.cu", "host_pipeline.cu", "shard.cu", "legacy.cu", "host/ndarray_host.cpp"]
 # bring-up probes (scripts/tcgen05_probe.py): a separate library on top of libnb200.so, never loaded by the product
 DEBUG_LIB = os.path.join(HERE, "libnb200_debug.so")
 DEBUG_SOURCES = ["sgemm_debug.cu"]

@@ -9,15 +9,17 @@
 
 namespace nb200 {
 
-static Ctx g_ctx;
-static std::unordered_map<void *, int64_t> g_ledger;  // live device blocks handed to the host (vmalloc leak counter, gpu_alloc.c:12,31)
+// One context per device.  The reference keeps a process-global "current device" (NDArray::setDevice -> cudaSetDevice,
+// numpower.c:615-635); nb200_set_device switches the current context WITHOUT tearing the others down, so a single host process can
+// drive several GPUs (include/nb200.h "multi-GPU shards").  Scratch, workspace, streams, the allocation ledger and the caching pool
+// all belong to their device; a block freed while another device is current goes back to its owner's pool.
+static Ctx g_ctxs[NB200_MAX_DEVICES];
+static int g_current = 0;
 // Caching allocator behind nb200_alloc / vmalloc (SURVEY.md §8 f, N3).  The reference pays a cudaMalloc and a
 // device-synchronising cudaFree for every result array (gpu_alloc.c:11-34); here freed blocks go to a size-keyed pool
 // and are reused by later requests of a similar size.  Reuse is safe without synchronisation because every kernel of
-// this library runs on the single context stream (a block handed out again is only touched by later work on that
+// this library on a device runs on that device's context stream (a block handed out again is only touched by later work on that
 // stream).  NB200_NO_CACHE=1 restores plain cudaMalloc/cudaFree.
-static std::multimap<int64_t, void *> g_pool;   // capacity -> free block
-static int64_t g_pool_bytes = 0;
 static int g_cache_enabled = -1;
 static bool cache_enabled() {
     if (g_cache_enabled < 0) g_cache_enabled = getenv("NB200_NO_CACHE") ? 0 : 1;
@@ -28,14 +30,15 @@ static int64_t round_capacity(int64_t bytes) {
     if (bytes < ((int64_t)1 << 20)) return (bytes + 511) & ~int64_t(511);
     return (bytes + ((int64_t)2 << 20) - 1) & ~(((int64_t)2 << 20) - 1);   // 2 MiB granules
 }
-static void pool_release_all() {
-    for (auto &kv : g_pool) cudaFree(kv.second);
-    g_pool.clear();
-    g_pool_bytes = 0;
+static void pool_release_all(Ctx &c) {
+    for (auto &kv : c.pool) cudaFree(kv.second);
+    c.pool.clear();
+    c.pool_bytes = 0;
 }
 static thread_local char g_err[512] = "";
 
-Ctx &ctx() { return g_ctx; }
+Ctx &ctx() { return g_ctxs[g_current]; }
+Ctx *ctx_of(int device) { return (device >= 0 && device < NB200_MAX_DEVICES) ? &g_ctxs[device] : nullptr; }
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;
@@ -53,14 +56,15 @@ static int init_device(int device) {
         return set_error(NB200_ENODEV, "no CUDA device available (%s); libnb200 has no CPU fallback",
                          e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     }
-    if (device < 0 || device >= count) return set_error(NB200_EINVAL, "device %d out of range [0,%d)", device, count);
+    if (device < 0 || device >= count || device >= NB200_MAX_DEVICES)
+        return set_error(NB200_EINVAL, "device %d out of range [0,%d)", device, count < NB200_MAX_DEVICES ? count : NB200_MAX_DEVICES);
     cudaDeviceProp prop;
     NB_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
         return set_error(NB200_ENODEV, "device %d is sm_%d%d; libnb200 is built for sm_100a only", device, prop.major,
                          prop.minor);
     NB_CUDA(cudaSetDevice(device));
-    Ctx &c = g_ctx;
+    Ctx &c = g_ctxs[device];
     c.device = device;
     c.num_sms = prop.multiProcessorCount;
     NB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -80,12 +84,13 @@ static int init_device(int device) {
 }
 
 int ensure_ready() {
-    if (g_ctx.ready) return NB200_OK;
-    return init_device(0);
+    if (ctx().ready) return NB200_OK;
+    const int rc = init_device(g_current);
+    return rc;
 }
 
 int ensure_scratch(int64_t bytes) {
-    Ctx &c = g_ctx;
+    Ctx &c = ctx();
     if (bytes <= c.scratch_bytes) return NB200_OK;
     if (c.scratch) {
         NB_CUDA(cudaStreamSynchronize(c.stream));
@@ -103,7 +108,7 @@ int ensure_scratch(int64_t bytes) {
 }
 
 int ensure_gemm_ws(int64_t bytes) {
-    Ctx &c = g_ctx;
+    Ctx &c = ctx();
     c.ctl_stride = -1;   // whoever asks for the workspace may overwrite the FP16x3 control blocks; gemm_fp16x3 re-validates its own layout
     if (bytes <= c.gemm_ws_bytes) return NB200_OK;
     if (c.gemm_ws) {
@@ -120,24 +125,14 @@ int ensure_gemm_ws(int64_t bytes) {
     return NB200_OK;
 }
 
-}  // namespace nb200
+void host_pipeline_release(int device);   // host_pipeline.cu: staging buffers, streams and events of that device
 
-using namespace nb200;
-
-extern "C" int nb200_init(int device) {
-    if (ctx().ready) {
-        if (ctx().device == device) return NB200_OK;
-        int rc = nb200_shutdown();
-        if (rc != NB200_OK) return rc;
-    }
-    return init_device(device);
-}
-
-extern "C" int nb200_shutdown(void) {
-    Ctx &c = ctx();
-    if (!c.ready) return NB200_OK;
-    cudaSetDevice(c.device);
+static void shutdown_device(int device) {
+    Ctx &c = g_ctxs[device];
+    if (!c.ready) return;
+    cudaSetDevice(device);
     cudaStreamSynchronize(c.stream);
+    host_pipeline_release(device);
     if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
     if (c.scratch) cudaFree(c.scratch);
     if (c.gemm_ws) cudaFree(c.gemm_ws);
@@ -145,10 +140,36 @@ extern "C" int nb200_shutdown(void) {
     if (c.domain_flag) cudaFree(c.domain_flag);
     if (c.dev_result) cudaFree(c.dev_result);
     if (c.host_result) cudaFreeHost(c.host_result);
-    pool_release_all();
-    int64_t launches = c.launches;
+    pool_release_all(c);
+    // blocks the host still holds stay allocated (the host frees them, or leaks them, exactly as with vmalloc); the ledger is
+    // dropped so that a later nb200_free of such a block releases it with cudaFree instead of pooling it in a new context
+    c.ledger.clear();
+    const int64_t launches = c.launches;
     c = Ctx();
     c.launches = launches;
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+extern "C" int nb200_init(int device) { return nb200_set_device(device); }
+
+extern "C" int nb200_set_device(int device) {
+    if (device < 0 || device >= NB200_MAX_DEVICES) return set_error(NB200_EINVAL, "device %d out of range", device);
+    if (!g_ctxs[device].ready) {
+        const int rc = init_device(device);
+        if (rc != NB200_OK) return rc;
+    } else {
+        NB_CUDA(cudaSetDevice(device));
+    }
+    g_current = device;
+    return NB200_OK;
+}
+
+extern "C" int nb200_shutdown(void) {
+    for (int d = 0; d < NB200_MAX_DEVICES; d++) shutdown_device(d);
+    g_current = 0;
     return NB200_OK;
 }
 
@@ -162,8 +183,6 @@ extern "C" int nb200_device_count(int *count) {
     }
     return NB200_OK;
 }
-
-extern "C" int nb200_set_device(int device) { return nb200_init(device); }
 
 extern "C" int nb200_get_device(int *device) {
     NB_READY();
@@ -192,7 +211,11 @@ extern "C" int nb200_set_stream(void *cuda_stream) {
     return NB200_OK;
 }
 
-extern "C" int64_t nb200_launch_count(void) { return ctx().launches; }
+extern "C" int64_t nb200_launch_count(void) {
+    int64_t n = 0;
+    for (int d = 0; d < NB200_MAX_DEVICES; d++) n += g_ctxs[d].launches;
+    return n;
+}
 
 extern "C" int nb200_trace_enable(unsigned long long *dev_slots) {
     NB_READY();
@@ -217,57 +240,71 @@ extern "C" int nb200_alloc(void **dev_ptr, int64_t bytes) {
     NB_READY();
     if (!dev_ptr || bytes < 0) return set_error(NB200_EINVAL, "nb200_alloc: bad argument");
     *dev_ptr = nullptr;
+    Ctx &c = ctx();
     const int64_t cap = round_capacity(bytes);
     if (cache_enabled()) {
-        auto it = g_pool.lower_bound(cap);
-        if (it != g_pool.end() && it->first <= cap + cap / 4) {   // accept up to 25 % slack
+        auto it = c.pool.lower_bound(cap);
+        if (it != c.pool.end() && it->first <= cap + cap / 4) {   // accept up to 25 % slack
             *dev_ptr = it->second;
-            g_pool_bytes -= it->first;
-            g_ledger[*dev_ptr] = it->first;
-            g_pool.erase(it);
-            ctx().live_allocs++;
-            ctx().live_bytes += g_ledger[*dev_ptr];
+            c.pool_bytes -= it->first;
+            c.ledger[*dev_ptr] = it->first;
+            c.live_allocs++;
+            c.live_bytes += it->first;
+            c.pool.erase(it);
             return NB200_OK;
         }
     }
     if (cudaMalloc(dev_ptr, (size_t)cap) != cudaSuccess) {
         cudaGetLastError();
-        pool_release_all();   // give cached blocks back to the driver and retry once
+        pool_release_all(c);   // give cached blocks back to the driver and retry once
         if (cudaMalloc(dev_ptr, (size_t)cap) != cudaSuccess) {
             cudaGetLastError();
             *dev_ptr = nullptr;
             return set_error(NB200_ENOMEM, "device memory allocation failed");  // gpu_alloc.c:15 message
         }
     }
-    ctx().live_allocs++;
-    ctx().live_bytes += cap;
-    g_ledger[*dev_ptr] = cap;
+    c.live_allocs++;
+    c.live_bytes += cap;
+    c.ledger[*dev_ptr] = cap;
     return NB200_OK;
 }
 
 extern "C" int nb200_free(void *dev_ptr) {
     NB_READY();
     if (!dev_ptr) return NB200_OK;
-    // cudaFree synchronises the device, so no kernel on the context stream can still use the block
-    auto it = g_ledger.find(dev_ptr);
-    if (it == g_ledger.end()) return set_error(NB200_EINVAL, "nb200_free: pointer %p was not allocated by nb200_alloc", dev_ptr);
-    const int64_t cap = it->second;
-    g_ledger.erase(it);
-    ctx().live_allocs--;
-    ctx().live_bytes -= cap;
-    // keep at most 32 GiB cached; larger pools are trimmed by releasing the biggest blocks first
+    // the block belongs to the device it was allocated on, which need not be the current one
+    Ctx *owner = nullptr;
+    if (ctx().ledger.count(dev_ptr)) owner = &ctx();
+    for (int d = 0; d < NB200_MAX_DEVICES && !owner; d++)
+        if (g_ctxs[d].ready && g_ctxs[d].ledger.count(dev_ptr)) owner = &g_ctxs[d];
+    if (!owner) {
+        // not in any ledger: a block that outlived its context (nb200_shutdown / re-init) is released, anything else is an error
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, dev_ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            NB_CUDA(cudaFree(dev_ptr));
+            return NB200_OK;
+        }
+        cudaGetLastError();
+        return set_error(NB200_EINVAL, "nb200_free: pointer %p was not allocated by nb200_alloc", dev_ptr);
+    }
+    Ctx &c = *owner;
+    const int64_t cap = c.ledger[dev_ptr];
+    c.ledger.erase(dev_ptr);
+    c.live_allocs--;
+    c.live_bytes -= cap;
+    // keep at most 32 GiB cached per device; larger pools are trimmed by releasing the biggest blocks first
     if (cache_enabled() && cap <= ((int64_t)8 << 30)) {
-        g_pool.emplace(cap, dev_ptr);
-        g_pool_bytes += cap;
-        while (g_pool_bytes > ((int64_t)32 << 30) && !g_pool.empty()) {
-            auto big = std::prev(g_pool.end());
+        c.pool.emplace(cap, dev_ptr);
+        c.pool_bytes += cap;
+        while (c.pool_bytes > ((int64_t)32 << 30) && !c.pool.empty()) {
+            auto big = std::prev(c.pool.end());
             NB_CUDA(cudaFree(big->second));
-            g_pool_bytes -= big->first;
-            g_pool.erase(big);
+            c.pool_bytes -= big->first;
+            c.pool.erase(big);
         }
         return NB200_OK;
     }
-    NB_CUDA(cudaFree(dev_ptr));
+    NB_CUDA(cudaFree(dev_ptr));   // (synchronises the device: no kernel can still use the block)
     return NB200_OK;
 }
 

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <map>
+#include <unordered_map>
 #include "../../include/nb200.h"
 
 #ifndef NB200_NUM_SMS_DEFAULT
@@ -38,10 +40,16 @@ struct Ctx {
     int64_t live_allocs = 0;
     int64_t live_bytes = 0;
     int64_t launches = 0;
+    // allocation ledger + caching pool of THIS device (abi.cu): live blocks handed to the host, and freed blocks by capacity
+    std::unordered_map<void *, int64_t> ledger;
+    std::multimap<int64_t, void *> pool;
+    int64_t pool_bytes = 0;
     unsigned long long *trace = nullptr;  // optional device buffer for %globaltimer stamps of the GEMM pipeline (nb200_trace_enable)
 };
 
-Ctx &ctx();
+constexpr int NB200_MAX_DEVICES = 16;
+Ctx &ctx();                      // context of the current device (nb200_set_device)
+Ctx *ctx_of(int device);         // nullptr if out of range; ->ready tells whether the device was initialised
 int set_error(int code, const char *fmt, ...);
 int ensure_ready();
 int ensure_scratch(int64_t bytes);

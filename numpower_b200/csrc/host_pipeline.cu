@@ -16,8 +16,7 @@ struct Pipe {
     int device = -1;
     static constexpr int MAXB = 64;
     cudaEvent_t ev_in[MAXB], ev_done[MAXB], ev_b = nullptr;
-    bool events = false;
-} g_pipe;
+} g_pipes[NB200_MAX_DEVICES];   // one per device: streams, events and staging buffers cannot follow nb200_set_device
 
 int grow(float **p, int64_t *cap, int64_t elems) {
     if (elems <= *cap) return NB200_OK;
@@ -32,6 +31,20 @@ int grow(float **p, int64_t *cap, int64_t elems) {
     return NB200_OK;
 }
 }  // namespace
+
+void host_pipeline_release(int device) {
+    if (device < 0 || device >= NB200_MAX_DEVICES) return;
+    Pipe &P = g_pipes[device];
+    if (P.device < 0) return;
+    if (P.s_in) cudaStreamDestroy(P.s_in);
+    if (P.s_out) cudaStreamDestroy(P.s_out);
+    for (int i = 0; i < Pipe::MAXB; i++) { cudaEventDestroy(P.ev_in[i]); cudaEventDestroy(P.ev_done[i]); }
+    if (P.ev_b) cudaEventDestroy(P.ev_b);
+    if (P.dA) cudaFree(P.dA);
+    if (P.dB) cudaFree(P.dB);
+    if (P.dC) cudaFree(P.dC);
+    P = Pipe();
+}
 }  // namespace nb200
 
 using namespace nb200;
@@ -44,8 +57,8 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
     precision = gemm_resolve_precision(precision, K);
     if (precision == NB200_GEMM_FP16X3) precision = NB200_GEMM_TF32X3;   // this path is PCIe-bound; it keeps the two-kernel TF32x3 pipeline
     if (M == 0 || N == 0) return NB200_OK;
-    Pipe &P = g_pipe;
     Ctx &c = ctx();
+    Pipe &P = g_pipes[c.device];
     if (P.device != c.device) {
         NB_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
         NB_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));

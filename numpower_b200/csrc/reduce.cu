@@ -419,7 +419,8 @@ __device__ __forceinline__ float unpack_index(unsigned long long best) {
 template <bool IS_MAX>
 __global__ void __launch_bounds__(RED_THREADS) arg_rows_kernel(float *__restrict__ out, const float *__restrict__ in,
                                                                int64_t len, int S, unsigned long long *__restrict__ partials,
-                                                               unsigned int *__restrict__ ticket) {
+                                                               unsigned int *__restrict__ ticket,
+                                                               unsigned long long *__restrict__ packed_out = nullptr) {
     __shared__ unsigned long long smem[RED_THREADS / 32];
     __shared__ bool is_last;
     const int64_t r = blockIdx.y;
@@ -432,7 +433,10 @@ __global__ void __launch_bounds__(RED_THREADS) arg_rows_kernel(float *__restrict
     if (l0 < len) v = arg_run<IS_MAX>(row + l0, l1 - l0, (unsigned)l0, threadIdx.x, RED_THREADS);
     v = block_max64<RED_THREADS>(v, smem);
     if (S == 1) {
-        if (threadIdx.x == 0) out[r] = isnan(row[0]) ? 0.f : unpack_index(v);  // calculation.c:14-17, :41-44
+        if (threadIdx.x == 0) {
+            out[r] = isnan(row[0]) ? 0.f : unpack_index(v);  // calculation.c:14-17, :41-44
+            if (packed_out) packed_out[r] = v;                // sharded callers combine the exact (key, index) words themselves
+        }
         return;
     }
     if (threadIdx.x == 0) {
@@ -449,6 +453,7 @@ __global__ void __launch_bounds__(RED_THREADS) arg_rows_kernel(float *__restrict
     a = block_max64<RED_THREADS>(a, smem);
     if (threadIdx.x == 0) {
         out[r] = isnan(row[0]) ? 0.f : unpack_index(a);
+        if (packed_out) packed_out[r] = a;
         ticket[r] = 0;
     }
 }
@@ -674,6 +679,26 @@ static int argminmax_dispatch(float *out, const float *in, int64_t outer, int64_
         arg_cols_kernel<IS_MAX, 8><<<grid, block, 0, st>>>(out + o0 * inner, in + o0 * len * inner, len, inner);
         NB_LAUNCH_CHECK();
     }
+    return NB200_OK;
+}
+
+// One shard of a sharded argmax / argmin (shard.cu): the packed candidate of in[0..n) - high word = ordering key (larger is better;
+// NaN is 0 for argmax, 0xFFFFFFFF for argmin), low word = 0xFFFFFFFF - index of its first occurrence - WITHOUT the "leading NaN
+// wins" rule, which applies to global element 0 only.  Also writes the float index next to it (unused).
+int argminmax_packed(int is_max, unsigned long long *dev_out, const float *in, int64_t n) {
+    if (n <= 0 || n >= (int64_t)0xFFFFFFFFll) return set_error(NB200_EINVAL, "argminmax: shard length %lld out of range", (long long)n);
+    int S = pick_split(1, n);
+    unsigned long long *partials = nullptr;
+    if (S > 1) {
+        int rc = ensure_scratch((int64_t)S * sizeof(unsigned long long));
+        if (rc != NB200_OK) return rc;
+        partials = static_cast<unsigned long long *>(ctx().scratch);
+    }
+    float *fout = ctx().dev_result + 1;
+    dim3 grid((unsigned)S, 1u);
+    if (is_max) arg_rows_kernel<true><<<grid, RED_THREADS, 0, ctx().stream>>>(fout, in, n, S, partials, ctx().ticket, dev_out);
+    else arg_rows_kernel<false><<<grid, RED_THREADS, 0, ctx().stream>>>(fout, in, n, S, partials, ctx().ticket, dev_out);
+    NB_LAUNCH_CHECK();
     return NB200_OK;
 }
 

@@ -25,6 +25,24 @@ def test_shard_range_partitions_exactly():
             assert max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
 
 
+def test_c_abi_shard_split_matches_the_python_rule():
+    """nb200_shard_split (pure host arithmetic, callable without a GPU) == sharding.shard_range."""
+    import ctypes as C
+    import numpower_b200 as nb
+    from numpower_b200.sharding import shard_range
+    lib = nb.lib()
+    for n in (0, 1, 7, 8, 1023, 1024, 1025, 2 ** 28 + 3):
+        for w in (1, 2, 3, 4, 8, 16):
+            for r in range(w):
+                lo, cnt = C.c_int64(), C.c_int64()
+                assert lib.nb200_shard_split(n, w, r, C.byref(lo), C.byref(cnt)) == 0
+                assert (lo.value, lo.value + cnt.value) == shard_range(n, w, r)
+    lo, cnt = C.c_int64(), C.c_int64()
+    assert lib.nb200_shard_split(10, 0, 0, C.byref(lo), C.byref(cnt)) != 0
+    n = C.c_int(-1)
+    assert lib.nb200_shard_count(C.byref(n)) == 0 and n.value == 0          # no group without nb200_shard_init
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -72,6 +90,28 @@ def _worker(rank, world, port, q):
     li = int(oracle.port.argminmax(True, ys))
     gi = sh.allreduce_argminmax(float(ys[li]), li, lo2, True)
     ok = ok and gi == 10.0
+    # NaN at a shard boundary.  Reference rule over the GLOBAL array (oracle on the whole array): a NaN sticks only at
+    # global index 0; [.., | NaN, -100] must still find -100, and a NaN at index 0 must win.
+    blo, _ = sh.shard_range(1000, world, world - 1)
+    z = x.copy()
+    z[blo] = np.nan
+    z[blo + 1] = -100.0
+    for zz in (z, np.concatenate([[np.float32(np.nan)], z[1:]]).astype(np.float32)):
+        zs = zz[lo2:hi2]
+        for op in ("min", "max"):
+            part = sh.local_minmax_partial(lambda off, cnt: float(oracle.port.reduce_full(op, zs[off:off + cnt])), len(zs), rank)
+            got = sh.allreduce_partials(part, op)
+            exp = float(oracle.port.reduce_full(op, zz))
+            ok = ok and (got == exp or (got != got and exp != exp))
+        # argmax / argmin: NaN-position-neutral local candidates (what the packed device word carries), combined with the global rules
+        for is_max in (True, False):
+            nanmask = np.isnan(zs)
+            if is_max:
+                li = int(np.nanargmax(zs)) if not nanmask.all() else 0
+            else:
+                li = int(np.argmax(nanmask)) if nanmask.any() else int(np.argmin(zs))
+            gi = sh.allreduce_argminmax(float(zs[li]), li, lo2, is_max, first_value=float(zs[0]))
+            ok = ok and gi == float(oracle.port.argminmax(is_max, zz))
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
