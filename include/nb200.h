@@ -193,6 +193,10 @@ int nb200_sgemm_batched(float *C, const float *A, const float *B, int64_t batch,
  * H2D and D2H copies overlap each other (full-duplex PCIe) and the compute.  Blocking; C_host complete on return.
  * Host buffers should be pinned (nb200_host_alloc) for full PCIe speed; pageable memory works but is staged. */
 int nb200_sgemm_host(float *C_host, const float *A_host, const float *B_host, int64_t M, int64_t N, int64_t K, int precision);
+/* Batch of independent products with HOST operands (contiguous [batch][M][K], [batch][K][N] -> [batch][M][N]): chunks of matrices
+ * upload, multiply (nb200_sgemm_batched, any precision) and download on three streams.  Blocking. */
+int nb200_sgemm_batched_host(float *C_host, const float *A_host, const float *B_host, int64_t batch, int64_t M, int64_t N, int64_t K,
+                             int precision);
 /* scratch the 3xTF32 split needs for an (M,N,K,batch) problem; allocated lazily from the
  * context and reused (bytes reported for capacity planning). */
 int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, int precision, int64_t *bytes);

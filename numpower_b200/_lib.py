@@ -54,6 +54,7 @@ ABI = {
     "nb200_sgemm": (C.c_int, [fp, fp, fp, i64, i64, i64, i64, i64, i64, C.c_int]),
     "nb200_sgemm_batched": (C.c_int, [fp, fp, fp, i64, i64, i64, i64, i64, i64, i64, C.c_int]),
     "nb200_sgemm_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, i64, i64, i64, C.c_int]),
+    "nb200_sgemm_batched_host": (C.c_int, [fp, fp, fp, i64, i64, i64, i64, C.c_int]),
     "nb200_sgemm_workspace_bytes": (C.c_int, [i64, i64, i64, i64, C.c_int, i64p]),
     "nb200_gemm_resolve_precision": (C.c_int, [C.c_int, i64]),
     "nb200_gemv": (C.c_int, [fp, fp, fp, i64, i64]),

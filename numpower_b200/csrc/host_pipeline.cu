@@ -71,14 +71,19 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
     }
     // shapes the tensor path cannot serve (tiny / K,N not multiples of 4): plain three-step path
     const bool pipelined = (K % 4 == 0) && (N % 4 == 0) && K >= 32 && N >= 32 && M >= 256 && M * N * K >= (int64_t)1 << 24;
-    // row block: ~8 blocks, multiple of 256 rows (one CTA-pair tile), at most MAXB blocks
+    // row blocks: ~NB200_HOST_BLOCKS (default 8) of them, multiples of 256 rows (one CTA-pair tile), at most MAXB.  A short tail
+    // (fewer than 128 rows, which the tensor path might refuse: tensor_path_ok wants rows * N * K >= 64^3) joins the previous block.
+    static const int64_t want_blocks = getenv("NB200_HOST_BLOCKS") ? atoll(getenv("NB200_HOST_BLOCKS")) : 8;
     int64_t rb = M;
     if (pipelined) {
-        rb = ((M / 8 + 255) / 256) * 256;
+        const int64_t wb = want_blocks < 1 ? 1 : want_blocks;
+        rb = ((M / wb + 255) / 256) * 256;
         if (rb < 256) rb = 256;
         while ((M + rb - 1) / rb > Pipe::MAXB) rb += 256;
     }
-    const int64_t nblk = (M + rb - 1) / rb;
+    int64_t nblk = (M + rb - 1) / rb;
+    if (nblk > 1 && M - (nblk - 1) * rb < 128) nblk--;   // the last block then has rb + (M mod rb) rows
+    auto blk_rows = [&](int64_t i) { return i == nblk - 1 ? M - i * rb : rb; };
     int rc;
     if ((rc = grow(&P.dA, &P.capA, M * K)) != NB200_OK) return rc;
     if ((rc = grow(&P.dB, &P.capB, K * N)) != NB200_OK) return rc;
@@ -105,23 +110,33 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
         P.dAlo = static_cast<float *>(c.gemm_ws);
         P.dBlo = P.dAlo + M * K;
     }
+    // NB200_HOST_TRACE=1: per-block timeline on stderr (timing events; diagnostics only)
+    static const bool trace = getenv("NB200_HOST_TRACE") != nullptr;
+    cudaEvent_t tr0 = nullptr, trB = nullptr, trIn[Pipe::MAXB], trDone[Pipe::MAXB], trOut[Pipe::MAXB];
+    if (trace) {
+        cudaEventCreate(&tr0); cudaEventCreate(&trB);
+        for (int64_t i = 0; i < nblk; i++) { cudaEventCreate(&trIn[i]); cudaEventCreate(&trDone[i]); cudaEventCreate(&trOut[i]); }
+        cudaEventRecord(tr0, c.stream);
+    }
     // everything enqueued below must come after whatever the caller already has on the compute stream
     NB_CUDA(cudaEventRecord(P.ev_b, c.stream));
     NB_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_b, 0));
     NB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_b, 0));
     NB_CUDA(cudaMemcpyAsync(P.dB, B_host, (size_t)K * N * 4, cudaMemcpyHostToDevice, P.s_in));
     NB_CUDA(cudaEventRecord(P.ev_b, P.s_in));
+    if (trace) cudaEventRecord(trB, P.s_in);
     for (int64_t i = 0; i < nblk; i++) {
-        const int64_t r0 = i * rb, rows = (r0 + rb <= M) ? rb : M - r0;
+        const int64_t r0 = i * rb, rows = blk_rows(i);
         NB_CUDA(cudaMemcpyAsync(P.dA + r0 * K, A_host + r0 * K, (size_t)rows * K * 4, cudaMemcpyHostToDevice, P.s_in));
         NB_CUDA(cudaEventRecord(P.ev_in[i], P.s_in));
+        if (trace) cudaEventRecord(trIn[i], P.s_in);
     }
     NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_b, 0));
     if ((x3 || b3) && (rc = gemm_reset_nonfinite()) != NB200_OK) return rc;
     if (x3 && (rc = gemm_split_operand(P.dB, P.dBlo, K * N)) != NB200_OK) return rc;
     if (b3 && (rc = gemm_bf16_split(P.dB, bh, bl, K, N)) != NB200_OK) return rc;
     for (int64_t i = 0; i < nblk; i++) {
-        const int64_t r0 = i * rb, rows = (r0 + rb <= M) ? rb : M - r0;
+        const int64_t r0 = i * rb, rows = blk_rows(i);
         NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_in[i], 0));
         if (x3 && (rc = gemm_split_operand(P.dA + r0 * K, P.dAlo + r0 * K, rows * K)) != NB200_OK) return rc;
         if (b3) {
@@ -131,10 +146,82 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
                                 K, N, N, precision)) != NB200_OK)
             return rc;
         NB_CUDA(cudaEventRecord(P.ev_done[i], c.stream));
+        if (trace) cudaEventRecord(trDone[i], c.stream);
         NB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_done[i], 0));
         NB_CUDA(cudaMemcpyAsync(C_host + r0 * N, P.dC + r0 * N, (size_t)rows * N * 4, cudaMemcpyDeviceToHost, P.s_out));
+        if (trace) cudaEventRecord(trOut[i], P.s_out);
     }
     // rejoin: the compute stream (the one callers time / order on) completes only after the last D2H
+    NB_CUDA(cudaEventRecord(P.ev_b, P.s_out));
+    NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_b, 0));
+    NB_CUDA(cudaStreamSynchronize(c.stream));
+    if (trace) {
+        float t;
+        cudaEventElapsedTime(&t, tr0, trB);
+        fprintf(stderr, "[nb200_sgemm_host] B in %.3f ms;", t);
+        for (int64_t i = 0; i < nblk; i++) {
+            float a, d, o;
+            cudaEventElapsedTime(&a, tr0, trIn[i]); cudaEventElapsedTime(&d, tr0, trDone[i]); cudaEventElapsedTime(&o, tr0, trOut[i]);
+            fprintf(stderr, " blk%lld in %.3f done %.3f out %.3f;", (long long)i, a, d, o);
+            cudaEventDestroy(trIn[i]); cudaEventDestroy(trDone[i]); cudaEventDestroy(trOut[i]);
+        }
+        fprintf(stderr, "\n");
+        cudaEventDestroy(tr0); cudaEventDestroy(trB);
+    }
+    return NB200_OK;
+}
+
+// Batch of independent products with HOST operands (config #5's per-GPU share fed from host memory): chunks of matrices move
+// through the same three streams - chunk i+1 uploads (A block, B block) while chunk i is multiplied (nb200_sgemm_batched, any
+// precision) and chunk i-1 downloads.  Replaces `$a->gpu(); $b->gpu(); nd::matmul per matrix; ->cpu()` (NDArray_ToGPU / ToCPU,
+// ndarray.c:1037-1093: blocking pageable copies, then compute).  Blocking; C_host complete on return.
+extern "C" int nb200_sgemm_batched_host(float *C_host, const float *A_host, const float *B_host, int64_t batch, int64_t M, int64_t N, int64_t K,
+                                        int precision) {
+    NB_READY();
+    if (!C_host || !A_host || !B_host || batch < 0 || M < 0 || N < 0 || K < 0) return set_error(NB200_EINVAL, "nb200_sgemm_batched_host: bad argument");
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3) return set_error(NB200_EINVAL, "unknown precision %d", precision);
+    if (batch == 0 || M == 0 || N == 0) return NB200_OK;
+    Ctx &c = ctx();
+    Pipe &P = g_pipes[c.device];
+    if (P.device != c.device) {
+        NB_CUDA(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+        NB_CUDA(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < Pipe::MAXB; i++) {
+            NB_CUDA(cudaEventCreateWithFlags(&P.ev_in[i], cudaEventDisableTiming));
+            NB_CUDA(cudaEventCreateWithFlags(&P.ev_done[i], cudaEventDisableTiming));
+        }
+        NB_CUDA(cudaEventCreateWithFlags(&P.ev_b, cudaEventDisableTiming));
+        P.device = c.device;
+    }
+    int rc;
+    if ((rc = grow(&P.dA, &P.capA, batch * M * K)) != NB200_OK) return rc;
+    if ((rc = grow(&P.dB, &P.capB, batch * K * N)) != NB200_OK) return rc;
+    if ((rc = grow(&P.dC, &P.capC, batch * M * N)) != NB200_OK) return rc;
+    // ~8 chunks (at least one matrix each, at most MAXB chunks): small enough that the first product starts early and the last
+    // download is short, large enough that a chunk fills the GPU
+    static const int64_t want_chunks = getenv("NB200_HOST_BLOCKS") ? atoll(getenv("NB200_HOST_BLOCKS")) : 8;
+    int64_t per = (batch + (want_chunks < 1 ? 1 : want_chunks) - 1) / (want_chunks < 1 ? 1 : want_chunks);
+    if (per < 1) per = 1;
+    while ((batch + per - 1) / per > Pipe::MAXB) per++;
+    const int64_t nchunk = (batch + per - 1) / per;
+    NB_CUDA(cudaEventRecord(P.ev_b, c.stream));
+    NB_CUDA(cudaStreamWaitEvent(P.s_in, P.ev_b, 0));
+    NB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_b, 0));
+    for (int64_t i = 0; i < nchunk; i++) {
+        const int64_t b0 = i * per, nb = b0 + per <= batch ? per : batch - b0;
+        NB_CUDA(cudaMemcpyAsync(P.dA + b0 * M * K, A_host + b0 * M * K, (size_t)(nb * M * K) * 4, cudaMemcpyHostToDevice, P.s_in));
+        NB_CUDA(cudaMemcpyAsync(P.dB + b0 * K * N, B_host + b0 * K * N, (size_t)(nb * K * N) * 4, cudaMemcpyHostToDevice, P.s_in));
+        NB_CUDA(cudaEventRecord(P.ev_in[i], P.s_in));
+    }
+    for (int64_t i = 0; i < nchunk; i++) {
+        const int64_t b0 = i * per, nb = b0 + per <= batch ? per : batch - b0;
+        NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_in[i], 0));
+        if ((rc = nb200_sgemm_batched(P.dC + b0 * M * N, P.dA + b0 * M * K, P.dB + b0 * K * N, nb, M, N, K, M * K, K * N, M * N, precision)) != NB200_OK)
+            return rc;
+        NB_CUDA(cudaEventRecord(P.ev_done[i], c.stream));
+        NB_CUDA(cudaStreamWaitEvent(P.s_out, P.ev_done[i], 0));
+        NB_CUDA(cudaMemcpyAsync(C_host + b0 * M * N, P.dC + b0 * M * N, (size_t)(nb * M * N) * 4, cudaMemcpyDeviceToHost, P.s_out));
+    }
     NB_CUDA(cudaEventRecord(P.ev_b, P.s_out));
     NB_CUDA(cudaStreamWaitEvent(c.stream, P.ev_b, 0));
     NB_CUDA(cudaStreamSynchronize(c.stream));

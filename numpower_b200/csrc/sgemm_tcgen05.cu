@@ -1746,12 +1746,12 @@ static bool tensor_path_ok(const GemmArgs &g) {
 }
 
 static inline int64_t round8(int64_t x) { return (x + 7) & ~int64_t(7); }
-// Batched x3 calls process the batch in chunks whose operand parts fit this much workspace (default 4 GiB;
+// Batched x3 calls process the batch in chunks whose operand parts fit this much workspace (default 16 GiB of the 180 GB;
 // NB200_GEMM_WS_BUDGET_MB overrides it, read per call so that tests can force several chunks on small problems).
 static int64_t gemm_ws_budget() {
     const char *e = getenv("NB200_GEMM_WS_BUDGET_MB");
     const int64_t mb = e ? atoll(e) : 0;
-    return mb > 0 ? mb << 20 : (int64_t)4 << 30;
+    return mb > 0 ? mb << 20 : (int64_t)16 << 30;
 }
 static SplitSpan make_span(const float *in, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t batch, int64_t rows, int64_t cols,
                            int64_t ld_in, int64_t stride_in) {
