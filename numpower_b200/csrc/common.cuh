@@ -40,6 +40,7 @@ struct Ctx {
     int64_t live_allocs = 0;
     int64_t live_bytes = 0;
     int64_t launches = 0;
+    int gemm_sm_reserve = 0;              // SMs the persistent GEMM grids leave free (NCCL transfer kernels running beside them, shard.cu)
     // allocation ledger + caching pool of THIS device (abi.cu): live blocks handed to the host, and freed blocks by capacity
     std::unordered_map<void *, int64_t> ledger;
     std::multimap<int64_t, void *> pool;

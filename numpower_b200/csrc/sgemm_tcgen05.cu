@@ -1670,7 +1670,8 @@ static int launch_gemm(const GemmArgs &g) {
         NB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    int64_t clusters = ctx().num_sms / Cfg::CG;
+    int64_t clusters = (ctx().num_sms - ctx().gemm_sm_reserve) / Cfg::CG;   // persistent: one CTA (pair) per SM, minus the SMs left to concurrent transfer kernels
+    if (clusters < 1) clusters = 1;
     if (clusters > p.total_tiles) clusters = p.total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * Cfg::CG));

@@ -470,9 +470,10 @@ extern "C" int nb200_sgemm_batched_sharded(float *const *C, const float *const *
 
 // Operands and result on ONE device (`root`): scatter + compute + gather, pipelined per chunk of `chunk` matrices per shard.
 // Step t of the schedule enqueues, in this order:  transfer-in of chunk t (A and B blocks to every peer), the products of chunk t
-// on every device (they wait for their inputs through events), transfer-out of chunk t (C blocks back to the root).  Inbound and
-// outbound transfers use different streams per device, so chunk t+1 lands and chunk t-1 returns while chunk t is multiplied; the
-// root multiplies its own share in place, without any copy.  With NCCL each step's sends / receives form one group per direction.
+// on every device (they wait for their inputs through events), transfer-out of chunk t (C blocks back to the root).  P2P: inbound
+// and outbound copies use different streams per device (copy engines), so chunk t+1 lands and chunk t-1 returns while chunk t is
+// multiplied.  NCCL: one group per step carries both directions (chunk t out, chunk t-2 back) and the GEMMs leave 16 SMs to the
+// transfer kernels.  The root multiplies its own share in place, without any copy.
 // elapsed_ms (optional): device time from the first transfer to the arrival of the last result block on the root (synchronises).
 extern "C" int nb200_sgemm_batched_scatter_gather(float *C_root, const float *A_root, const float *B_root, int64_t batch, int64_t M, int64_t N,
                                                   int64_t K, int precision, int root, int transport, int64_t chunk, float *elapsed_ms) {
@@ -504,6 +505,7 @@ extern "C" int nb200_sgemm_batched_scatter_gather(float *C_root, const float *A_
         }
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
+        for (int s = 0; s < G; s++) ctx_of(g.dev[s])->gemm_sm_reserve = 0;
     };
     for (auto &e : ev_in) e = nullptr;
     for (auto &e : ev_done) e = nullptr;
@@ -522,6 +524,10 @@ extern "C" int nb200_sgemm_batched_scatter_gather(float *C_root, const float *A_
             SG_CUDA(cudaEventCreateWithFlags(&ev_done[s * (steps + 1) + t], cudaEventDisableTiming));
         }
     }
+    // NCCL's send / receive kernels need SMs of their own: a persistent GEMM grid that owns every SM would serialise them behind
+    // the products (measured at N = 2: 25.7 ms against 8.0 ms with the copy-engine transport).  The GEMMs of this call leave 16 SMs free.
+    const int reserve = transport == NB200_XFER_NCCL ? 16 : 0;
+    for (int s = 0; s < G; s++) ctx_of(g.dev[s])->gemm_sm_reserve = reserve;
     Ctx *rctx = ctx_of(g.dev[root]);
     SG_CUDA(cudaSetDevice(g.dev[root]));
     SG_CUDA(cudaEventCreate(&t0));
@@ -542,69 +548,116 @@ extern "C" int nb200_sgemm_batched_scatter_gather(float *C_root, const float *A_
         SG_TRY(nb200_sgemm_batched(C_root + lo[root] * M * N, A_root + lo[root] * M * K, B_root + lo[root] * K * N, cnt[root], M, N, K, M * K, K * N,
                                    M * N, precision));
     }
-    for (int64_t t = 0; t < steps; t++) {
-        // (1) transfer-in of chunk t
-        if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupStart());
-        for (int s = 0; s < G; s++) {
-            if (s == root) continue;
-            const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
-            if (cn <= 0) continue;
-            const float *srcA = A_root + (lo[s] + c0) * M * K, *srcB = B_root + (lo[s] + c0) * K * N;
-            if (transport == NB200_XFER_P2P) {
-                SG_CUDA(cudaSetDevice(g.dev[s]));
-                SG_CUDA(cudaMemcpyPeerAsync(sa[s] + c0 * M * K, g.dev[s], srcA, g.dev[root], (size_t)(cn * M * K * 4), g.xin[s]));
-                SG_CUDA(cudaMemcpyPeerAsync(sb[s] + c0 * K * N, g.dev[s], srcB, g.dev[root], (size_t)(cn * K * N * 4), g.xin[s]));
-            } else {
-                SG_NCCL(g.api.Send(srcA, (size_t)(cn * M * K * 4), ncclChar, s, g.comm[root], g.xout[root]));
-                SG_NCCL(g.api.Send(srcB, (size_t)(cn * K * N * 4), ncclChar, s, g.comm[root], g.xout[root]));
-                SG_NCCL(g.api.Recv(sa[s] + c0 * M * K, (size_t)(cn * M * K * 4), ncclChar, root, g.comm[s], g.xin[s]));
-                SG_NCCL(g.api.Recv(sb[s] + c0 * K * N, (size_t)(cn * K * N * 4), ncclChar, root, g.comm[s], g.xin[s]));
+    if (transport == NB200_XFER_NCCL) {
+        // NCCL orders the operations of one communicator even across streams, so both directions of a step go into ONE group (one
+        // kernel per device: the root sends the A / B blocks of chunk t and receives the C blocks of chunk t-2 at the same time), all
+        // on the devices' inbound transfer streams.  Chunk t-2 was multiplied while chunk t-1 travelled.
+        for (int64_t t = 0; t < steps + 2; t++) {
+            // the C blocks of chunk t-2 leave only after their products
+            if (t >= 2)
+                for (int s = 0; s < G; s++) {
+                    if (s == root || cnt[s] - (t - 2) * chunk <= 0) continue;
+                    SG_CUDA(cudaSetDevice(g.dev[s]));
+                    SG_CUDA(cudaStreamWaitEvent(g.xin[s], ev_done[s * (steps + 1) + (t - 2)], 0));
+                }
+            SG_NCCL(g.api.GroupStart());
+            for (int s = 0; s < G; s++) {
+                if (s == root) continue;
+                if (t < steps) {
+                    const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
+                    if (cn > 0) {
+                        SG_NCCL(g.api.Send(A_root + (lo[s] + c0) * M * K, (size_t)(cn * M * K * 4), ncclChar, s, g.comm[root], g.xin[root]));
+                        SG_NCCL(g.api.Send(B_root + (lo[s] + c0) * K * N, (size_t)(cn * K * N * 4), ncclChar, s, g.comm[root], g.xin[root]));
+                        SG_NCCL(g.api.Recv(sa[s] + c0 * M * K, (size_t)(cn * M * K * 4), ncclChar, root, g.comm[s], g.xin[s]));
+                        SG_NCCL(g.api.Recv(sb[s] + c0 * K * N, (size_t)(cn * K * N * 4), ncclChar, root, g.comm[s], g.xin[s]));
+                    }
+                }
+                if (t >= 2) {
+                    const int64_t c0 = (t - 2) * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
+                    if (cn > 0) {
+                        SG_NCCL(g.api.Send(sc[s] + c0 * M * N, (size_t)(cn * M * N * 4), ncclChar, root, g.comm[s], g.xin[s]));
+                        SG_NCCL(g.api.Recv(C_root + (lo[s] + c0) * M * N, (size_t)(cn * M * N * 4), ncclChar, s, g.comm[root], g.xin[root]));
+                    }
+                }
             }
+            SG_NCCL(g.api.GroupEnd());
+            // products of chunk t on the peers, after this step's transfer
+            if (t < steps)
+                for (int s = 0; s < G; s++) {
+                    if (s == root) continue;
+                    const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
+                    if (cn <= 0) continue;
+                    SG_TRY(nb200_set_device(g.dev[s]));
+                    Ctx &cs = ctx();
+                    SG_CUDA(cudaEventRecord(ev_in[s * (steps + 1) + t], g.xin[s]));
+                    SG_CUDA(cudaStreamWaitEvent(cs.stream, ev_in[s * (steps + 1) + t], 0));
+                    SG_TRY(nb200_sgemm_batched(sc[s] + c0 * M * N, sa[s] + c0 * M * K, sb[s] + c0 * K * N, cn, M, N, K, M * K, K * N, M * N, precision));
+                    SG_CUDA(cudaEventRecord(ev_done[s * (steps + 1) + t], cs.stream));
+                }
         }
-        if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupEnd());
-        // (2) products of chunk t on the peers (after their inputs), (3) transfer-out of chunk t (after the products)
-        for (int s = 0; s < G; s++) {
-            if (s == root) continue;
-            const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
-            if (cn <= 0) continue;
-            SG_TRY(nb200_set_device(g.dev[s]));
-            Ctx &cs = ctx();
-            SG_CUDA(cudaEventRecord(ev_in[s * (steps + 1) + t], g.xin[s]));
-            SG_CUDA(cudaStreamWaitEvent(cs.stream, ev_in[s * (steps + 1) + t], 0));
-            SG_TRY(nb200_sgemm_batched(sc[s] + c0 * M * N, sa[s] + c0 * M * K, sb[s] + c0 * K * N, cn, M, N, K, M * K, K * N, M * N, precision));
-            SG_CUDA(cudaEventRecord(ev_done[s * (steps + 1) + t], cs.stream));
-        }
-        if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupStart());
-        for (int s = 0; s < G; s++) {
-            if (s == root) continue;
-            const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
-            if (cn <= 0) continue;
-            float *dst = C_root + (lo[s] + c0) * M * N;
-            if (transport == NB200_XFER_P2P) {
-                SG_CUDA(cudaSetDevice(g.dev[s]));
-                SG_CUDA(cudaStreamWaitEvent(g.xout[s], ev_done[s * (steps + 1) + t], 0));
-                SG_CUDA(cudaMemcpyPeerAsync(dst, g.dev[root], sc[s] + c0 * M * N, g.dev[s], (size_t)(cn * M * N * 4), g.xout[s]));
-            } else {
-                SG_CUDA(cudaSetDevice(g.dev[s]));
-                SG_CUDA(cudaStreamWaitEvent(g.xout[s], ev_done[s * (steps + 1) + t], 0));
-                SG_NCCL(g.api.Send(sc[s] + c0 * M * N, (size_t)(cn * M * N * 4), ncclChar, root, g.comm[s], g.xout[s]));
-                SG_NCCL(g.api.Recv(dst, (size_t)(cn * M * N * 4), ncclChar, s, g.comm[root], g.xin[root]));
+    } else {
+        for (int64_t t = 0; t < steps; t++) {
+            // (1) transfer-in of chunk t
+            if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupStart());
+            for (int s = 0; s < G; s++) {
+                if (s == root) continue;
+                const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
+                if (cn <= 0) continue;
+                const float *srcA = A_root + (lo[s] + c0) * M * K, *srcB = B_root + (lo[s] + c0) * K * N;
+                if (transport == NB200_XFER_P2P) {
+                    SG_CUDA(cudaSetDevice(g.dev[s]));
+                    SG_CUDA(cudaMemcpyPeerAsync(sa[s] + c0 * M * K, g.dev[s], srcA, g.dev[root], (size_t)(cn * M * K * 4), g.xin[s]));
+                    SG_CUDA(cudaMemcpyPeerAsync(sb[s] + c0 * K * N, g.dev[s], srcB, g.dev[root], (size_t)(cn * K * N * 4), g.xin[s]));
+                } else {
+                    SG_NCCL(g.api.Send(srcA, (size_t)(cn * M * K * 4), ncclChar, s, g.comm[root], g.xout[root]));
+                    SG_NCCL(g.api.Send(srcB, (size_t)(cn * K * N * 4), ncclChar, s, g.comm[root], g.xout[root]));
+                    SG_NCCL(g.api.Recv(sa[s] + c0 * M * K, (size_t)(cn * M * K * 4), ncclChar, root, g.comm[s], g.xin[s]));
+                    SG_NCCL(g.api.Recv(sb[s] + c0 * K * N, (size_t)(cn * K * N * 4), ncclChar, root, g.comm[s], g.xin[s]));
+                }
             }
+            if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupEnd());
+            // (2) products of chunk t on the peers (after their inputs), (3) transfer-out of chunk t (after the products)
+            for (int s = 0; s < G; s++) {
+                if (s == root) continue;
+                const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
+                if (cn <= 0) continue;
+                SG_TRY(nb200_set_device(g.dev[s]));
+                Ctx &cs = ctx();
+                SG_CUDA(cudaEventRecord(ev_in[s * (steps + 1) + t], g.xin[s]));
+                SG_CUDA(cudaStreamWaitEvent(cs.stream, ev_in[s * (steps + 1) + t], 0));
+                SG_TRY(nb200_sgemm_batched(sc[s] + c0 * M * N, sa[s] + c0 * M * K, sb[s] + c0 * K * N, cn, M, N, K, M * K, K * N, M * N, precision));
+                SG_CUDA(cudaEventRecord(ev_done[s * (steps + 1) + t], cs.stream));
+            }
+            if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupStart());
+            for (int s = 0; s < G; s++) {
+                if (s == root) continue;
+                const int64_t c0 = t * chunk, cn = cnt[s] - c0 < chunk ? cnt[s] - c0 : chunk;
+                if (cn <= 0) continue;
+                float *dst = C_root + (lo[s] + c0) * M * N;
+                if (transport == NB200_XFER_P2P) {
+                    SG_CUDA(cudaSetDevice(g.dev[s]));
+                    SG_CUDA(cudaStreamWaitEvent(g.xout[s], ev_done[s * (steps + 1) + t], 0));
+                    SG_CUDA(cudaMemcpyPeerAsync(dst, g.dev[root], sc[s] + c0 * M * N, g.dev[s], (size_t)(cn * M * N * 4), g.xout[s]));
+                } else {
+                    SG_CUDA(cudaSetDevice(g.dev[s]));
+                    SG_CUDA(cudaStreamWaitEvent(g.xout[s], ev_done[s * (steps + 1) + t], 0));
+                    SG_NCCL(g.api.Send(sc[s] + c0 * M * N, (size_t)(cn * M * N * 4), ncclChar, root, g.comm[s], g.xout[s]));
+                    SG_NCCL(g.api.Recv(dst, (size_t)(cn * M * N * 4), ncclChar, s, g.comm[root], g.xin[root]));
+                }
+            }
+            if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupEnd());
         }
-        if (transport == NB200_XFER_NCCL) SG_NCCL(g.api.GroupEnd());
-    }
+}
     // join: the root's context stream continues after every result block has arrived (and after its own share)
     SG_CUDA(cudaSetDevice(g.dev[root]));
     if (transport == NB200_XFER_NCCL) {
         SG_CUDA(cudaEventRecord(ev_done[root * (steps + 1) + steps], g.xin[root]));
         SG_CUDA(cudaStreamWaitEvent(rctx->stream, ev_done[root * (steps + 1) + steps], 0));
-        SG_CUDA(cudaEventRecord(ev_in[root * (steps + 1) + steps], g.xout[root]));
-        SG_CUDA(cudaStreamWaitEvent(rctx->stream, ev_in[root * (steps + 1) + steps], 0));
     }
     for (int s = 0; s < G; s++) {
         if (s == root) continue;
         SG_CUDA(cudaSetDevice(g.dev[s]));
-        SG_CUDA(cudaEventRecord(ev_done[s * (steps + 1) + steps], g.xout[s]));
+        SG_CUDA(cudaEventRecord(ev_done[s * (steps + 1) + steps], transport == NB200_XFER_NCCL ? g.xin[s] : g.xout[s]));
         SG_CUDA(cudaStreamWaitEvent(ctx_of(g.dev[s])->stream, ev_done[s * (steps + 1) + steps], 0));   // staging reuse stays ordered
         SG_CUDA(cudaSetDevice(g.dev[root]));
         SG_CUDA(cudaStreamWaitEvent(rctx->stream, ev_done[s * (steps + 1) + steps], 0));

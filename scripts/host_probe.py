@@ -33,3 +33,12 @@ def d2h():
 def both(): h2d(); d2h()
 gb = pin.numel() * 4 / 1e9
 print(json.dumps({"h2d_GBps": gb / timed(h2d), "d2h_GBps": gb / timed(d2h), "duplex_each_GBps": gb / timed(both)}), file=sys.stderr)
+# batched host pipeline: 16 x 2048^2
+nb_, m = 16, 2048
+hA, hB, hC = (torch.rand(nb_, m, m).pin_memory() for _ in range(3))
+for i in range(3):
+    assert lib.nb200_sgemm_batched_host(hC.data_ptr(), hA.data_ptr(), hB.data_ptr(), nb_, m, m, m, 3) == 0
+t0 = time.perf_counter()
+for i in range(5):
+    lib.nb200_sgemm_batched_host(hC.data_ptr(), hA.data_ptr(), hB.data_ptr(), nb_, m, m, m, 3)
+print("sgemm_batched_host ms/call (wall):", (time.perf_counter() - t0) / 5 * 1e3, file=sys.stderr)
