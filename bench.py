@@ -127,15 +127,18 @@ def ncu_lookup(traffic, *fragments, near=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (every rank samples its own GPU)."""
+    """nvidia-smi clocks / power / throttle reasons of ONE GPU (every rank samples its own).  nvidia-smi needs the better part of a
+    second to start, so the sampler is started well before the timed region and every sample carries its own timestamp: stop()
+    keeps the samples that fall inside the [t0, t1] window the caller marks around the timed region (mark_start / mark_end)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -147,30 +150,51 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons, power = [], None, set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None,
-                "power_w_median": statistics.median(power) if power else None}
+
+        def summarise(lines):
+            sm, mx, reasons, power = [], None, set(), []
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2]))
+                    mx = float(f[3])
+                    power.append(float(f[4]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": mx,
+                    "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None,
+                    "power_w_median": statistics.median(power) if power else None}
+        if self.t0 is None:
+            return summarise(self.lines)
+        t1 = self.t1 if self.t1 is not None else time.time()
+        # a sample printed at time t describes the ~20 ms before it
+        inside = [x for x in self.lines if self.t0 <= x[0] <= t1 + 0.03]
+        out = summarise(inside)
+        out["window_s"] = t1 - self.t0
+        if out["samples"] == 0:        # region shorter than nvidia-smi's period: fall back to the nearest samples around it
+            near = sorted(self.lines, key=lambda x: abs(x[0] - (self.t0 + t1) / 2))[:3]
+            out = summarise(near)
+            out["window_s"] = t1 - self.t0
+            out["note"] = "timed region shorter than the sampling period: nearest samples"
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -337,6 +361,8 @@ def run_single(args):
 
     sampler = ClockSampler(0)
     sampler.start()
+    time.sleep(0.6)                 # nvidia-smi start-up
+    sampler.mark_start()
     auto_mode = int(lib.nb200_gemm_resolve_precision(GEMM_AUTO, n))        # the mode nd::matmul runs at this K
     auto_name, auto_dtype, auto_kind = MODES[auto_mode]
     for _ in range(args.warmup):
@@ -370,6 +396,7 @@ def run_single(args):
 
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = B.time_steps(e2e_step, e2e_steps, 3)
+    sampler.mark_end()
     clocks = sampler.stop()   # sampled across the timed matmul / other-mode / e2e regions (the headline loop alone is shorter than one nvidia-smi period)
     # raw PCIe ceilings for the e2e number: 256 MiB pinned copies, each direction alone and both at once
     pin = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
@@ -456,6 +483,16 @@ def run_single(args):
     t = B.time_steps(lambda: B.check(lib.nb200_ew_binary(0, so.data_ptr(), s.data_ptr(), s2.data_ptr(), 1, s1, st1, st1)), 50, 5)
     per["add_1024sq_l2_warm"] = {"config": "configs[0] nd::add 1024x1024 on the GPU, back to back (L2-resident: launch-latency bound, reported, not a target)",
                                  "bound": "launch latency", "ms": t, "achieved": 3 * (1 << 22) / t / 1e6, "unit": "GB/s", "algorithmic_bytes": 3 << 22}
+    # the launch-latency path: 50 nd::add calls recorded once (nb200_graph_begin / end) and replayed with one launch
+    gexec = C.c_void_p()
+    B.check(lib.nb200_graph_begin())
+    for _ in range(50):
+        B.check(lib.nb200_ew_binary(0, so.data_ptr(), s.data_ptr(), s2.data_ptr(), 1, s1, st1, st1))
+    B.check(lib.nb200_graph_end(C.byref(gexec)))
+    tg = B.time_steps(lambda: B.check(lib.nb200_graph_launch(gexec)), 20, 3) / 50
+    B.check(lib.nb200_graph_destroy(gexec))
+    per["add_1024sq_graph_replay"] = {"config": "configs[0] nd::add 1024x1024: 50 calls captured into one CUDA graph (nb200_graph_*), per-op time of a replay",
+                                      "bound": "launch latency", "ms": tg, "achieved": 3 * (1 << 22) / tg / 1e6, "unit": "GB/s", "algorithmic_bytes": 3 << 22}
     host["add_a"], host["add_b"] = s.cpu().numpy(), s2.cpu().numpy()
 
     # configs[4]'s per-GPU share on ONE GPU (weak-scaling base for bench.py --gpus N): 128 x (2048x2048)
@@ -568,6 +605,8 @@ def run_multi(args):
     def device_barrier():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()                 # (nvidia-smi needs ~0.5 s to start: the window is marked around the timed region below)
     for _ in range(args.warmup):
         step()
     # ---- scaling base: the same per-GPU workload on ONE GPU of this box while the others idle (rank 0; same steps)
@@ -579,16 +618,16 @@ def run_multi(args):
     # ---- the timed region: every rank multiplies its resident shard
     for _ in range(2):
         step()
-    sampler = ClockSampler(local)
-    sampler.start()
     device_barrier()
     launches0 = lib.nb200_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_start()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     device_barrier()
+    sampler.mark_end()
     my_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
     launches = lib.nb200_launch_count() - launches0

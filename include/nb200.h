@@ -125,6 +125,13 @@ void *nb200_stream(void);
 int nb200_set_stream(void *cuda_stream);
 /* Number of kernels this library has launched since init (bench.py "gpu_launches"). */
 int64_t nb200_launch_count(void);
+/* CUDA graphs: record everything the nb200_* calls between begin and end enqueue on the context stream, replay it with one launch.
+ * The launch-latency path for sequences of small (L2-resident) operations; no allocation and no `*_host` entry point inside a
+ * capture.  The reference synchronises after every kernel (cuda_math.cu wrappers: cudaDeviceSynchronize). */
+int nb200_graph_begin(void);
+int nb200_graph_end(void **graph_exec);
+int nb200_graph_launch(void *graph_exec);
+int nb200_graph_destroy(void *graph_exec);
 /* Diagnostics: when `dev_slots` (>= 16 device uint64 words; "first" slots preset to ~0, "last" slots to 0) is set, the kernels
  * of the matmul pipeline stamp %globaltimer nanoseconds into it (slot map: csrc/common.cuh); NULL switches it off.
  * scripts/gemm_timeline.py turns the stamps into profiles/r2_gemm_timeline.json. */
@@ -159,7 +166,8 @@ int nb200_ew_binary_scalar(int op, float *out, const float *a, float scalar, int
 int nb200_ew_mul_add(float *out, const float *a, const float *b, const float *c, int ndim,
                      const int64_t *out_shape, const int64_t *a_strides, const int64_t *b_strides,
                      const int64_t *c_strides);
-/* out[i] = f(in[i]); out may alias in (the legacy cuda_float_<op> are in-place). */
+/* out[i] = f(in[i]); out may BE in (same pointer: the legacy cuda_float_<op> are in-place; dispatched to kernels without
+ * __restrict__ / non-coherent loads).  Partially overlapping ranges are not supported.  The same holds for flat nb200_ew_binary. */
 int nb200_ew_unary(int op, float *out, const float *in, int64_t n, float p0, float p1);
 int nb200_fill(float *out, float value, int64_t n);   /* cuda_fill_float, cuda_math.h:36 */
 

@@ -33,6 +33,8 @@ ABI = {
     "nb200_last_error": (C.c_char_p, []), "nb200_stream": (C.c_void_p, []),
     "nb200_set_stream": (C.c_int, [C.c_void_p]), "nb200_launch_count": (i64, []),
     "nb200_trace_enable": (C.c_int, [C.c_void_p]),
+    "nb200_graph_begin": (C.c_int, []), "nb200_graph_end": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "nb200_graph_launch": (C.c_int, [C.c_void_p]), "nb200_graph_destroy": (C.c_int, [C.c_void_p]),
     "nb200_poll_domain_error": (C.c_int, [C.POINTER(C.c_int)]),
     "nb200_alloc": (C.c_int, [C.POINTER(C.c_void_p), i64]), "nb200_free": (C.c_int, [C.c_void_p]),
     "nb200_copy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, i64]),

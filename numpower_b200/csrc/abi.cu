@@ -217,6 +217,41 @@ extern "C" int64_t nb200_launch_count(void) {
     return n;
 }
 
+// ---- CUDA graphs: launch-latency path for sequences of small operations -------------------------------------------------------
+// A 1024^2 nd::add moves 12 MiB that live in L2: the kernel takes ~2.5 us, a stream launch costs about as much again and the host
+// call path more.  Capturing a sequence of nb200_* calls once and replaying it removes both per-op costs.  Everything enqueued on the
+// context stream between begin and end is recorded (no allocation, no host-returning entry point inside a capture).
+extern "C" int nb200_graph_begin(void) {
+    NB_READY();
+    NB_CUDA(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
+    return NB200_OK;
+}
+
+extern "C" int nb200_graph_end(void **graph_exec) {
+    NB_READY();
+    if (!graph_exec) return set_error(NB200_EINVAL, "null argument");
+    cudaGraph_t graph = nullptr;
+    NB_CUDA(cudaStreamEndCapture(ctx().stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return set_error(NB200_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    *graph_exec = exec;
+    return NB200_OK;
+}
+
+extern "C" int nb200_graph_launch(void *graph_exec) {
+    NB_READY();
+    if (!graph_exec) return set_error(NB200_EINVAL, "null argument");
+    NB_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), ctx().stream));
+    return NB200_OK;
+}
+
+extern "C" int nb200_graph_destroy(void *graph_exec) {
+    if (graph_exec) NB_CUDA(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec)));
+    return NB200_OK;
+}
+
 extern "C" int nb200_trace_enable(unsigned long long *dev_slots) {
     NB_READY();
     ctx().trace = dev_slots;

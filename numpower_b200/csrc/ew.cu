@@ -146,10 +146,11 @@ __device__ __forceinline__ float4 apply4(const T &f, const float4 &a, const floa
 }
 
 // Flat contiguous operands, all 16-byte aligned.  n4 float4 groups + (n & 3) tail elements.
-template <int NIN, class F>
-__global__ void __launch_bounds__(EW_THREADS) ew_flat_vec(float *__restrict__ out, const float *__restrict__ a,
-                                                          const float *__restrict__ b, const float *__restrict__ c,
-                                                          int64_t n, F f) {
+// NC = true: non-coherent loads (ld.global.nc) - only legal when `out` aliases no input, which the __restrict__ kernels below
+// promise.  The in-place kernels (out == an input: the legacy cuda_float_<op> wrappers, `$a += $b`) use plain coherent loads and no
+// __restrict__; each thread still reads its own elements before it writes them, so aliasing the SAME range is well defined.
+template <int NIN, class F, bool NC>
+__device__ __forceinline__ void flat_vec_body(float *out, const float *a, const float *b, const float *c, int64_t n, F f) {
     const int64_t n4 = n >> 2;
     const float4 *a4 = reinterpret_cast<const float4 *>(a);
     const float4 *b4 = reinterpret_cast<const float4 *>(b);
@@ -162,10 +163,10 @@ __global__ void __launch_bounds__(EW_THREADS) ew_flat_vec(float *__restrict__ ou
         for (int u = 0; u < EW_UNROLL; u++) {
             int64_t i = base + (int64_t)u * EW_THREADS + threadIdx.x;
             if (i < n4) {
-                if (NIN > 0) va[u] = ld_ew(a4 + i);
+                if (NIN > 0) va[u] = NC ? ld_ew(a4 + i) : a4[i];
                 else va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (NIN > 1) vb[u] = ld_ew(b4 + i);
-                if (NIN > 2) vc[u] = ld_ew(c4 + i);
+                if (NIN > 1) vb[u] = NC ? ld_ew(b4 + i) : b4[i];
+                if (NIN > 2) vc[u] = NC ? ld_ew(c4 + i) : c4[i];
             }
         }
 #pragma unroll
@@ -179,12 +180,27 @@ __global__ void __launch_bounds__(EW_THREADS) ew_flat_vec(float *__restrict__ ou
         out[i] = f(NIN > 0 ? a[i] : 0.f, NIN > 1 ? b[i] : 0.f, NIN > 2 ? c[i] : 0.f);
     }
 }
+template <int NIN, class F>
+__global__ void __launch_bounds__(EW_THREADS) ew_flat_vec(float *__restrict__ out, const float *__restrict__ a,
+                                                          const float *__restrict__ b, const float *__restrict__ c,
+                                                          int64_t n, F f) {
+    flat_vec_body<NIN, F, true>(out, a, b, c, n, f);
+}
+template <int NIN, class F>
+__global__ void __launch_bounds__(EW_THREADS) ew_flat_vec_inplace(float *out, const float *a, const float *b, const float *c, int64_t n, F f) {
+    flat_vec_body<NIN, F, false>(out, a, b, c, n, f);
+}
 
 // Flat, no alignment assumption (views such as $a[i] are only 4-byte aligned).
 template <int NIN, class F>
 __global__ void __launch_bounds__(EW_THREADS) ew_flat_scalar(float *__restrict__ out, const float *__restrict__ a,
                                                              const float *__restrict__ b, const float *__restrict__ c,
                                                              int64_t n, F f) {
+    for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS)
+        out[i] = f(NIN > 0 ? a[i] : 0.f, NIN > 1 ? b[i] : 0.f, NIN > 2 ? c[i] : 0.f);
+}
+template <int NIN, class F>
+__global__ void __launch_bounds__(EW_THREADS) ew_flat_scalar_inplace(float *out, const float *a, const float *b, const float *c, int64_t n, F f) {
     for (int64_t i = (int64_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS)
         out[i] = f(NIN > 0 ? a[i] : 0.f, NIN > 1 ? b[i] : 0.f, NIN > 2 ? c[i] : 0.f);
 }
@@ -303,12 +319,16 @@ static int launch_flat(float *out, const float *a, const float *b, const float *
     if (n == 0) return NB200_OK;
     cudaStream_t s = ctx().stream;
     bool vec = aligned16(out) && (NIN < 1 || aligned16(a)) && (NIN < 2 || aligned16(b)) && (NIN < 3 || aligned16(c));
+    // out == an input (in place): the kernels without __restrict__ / non-coherent loads
+    const bool inplace = (NIN > 0 && out == a) || (NIN > 1 && out == b) || (NIN > 2 && out == c);
     if (vec && n >= 4) {
         int grid = grid_for(n >> 2, (int64_t)EW_THREADS * EW_UNROLL);
-        ew_flat_vec<NIN, F><<<grid, EW_THREADS, 0, s>>>(out, a, b, c, n, f);
+        if (inplace) ew_flat_vec_inplace<NIN, F><<<grid, EW_THREADS, 0, s>>>(out, a, b, c, n, f);
+        else ew_flat_vec<NIN, F><<<grid, EW_THREADS, 0, s>>>(out, a, b, c, n, f);
     } else {
         int grid = grid_for(n, EW_THREADS);
-        ew_flat_scalar<NIN, F><<<grid, EW_THREADS, 0, s>>>(out, a, b, c, n, f);
+        if (inplace) ew_flat_scalar_inplace<NIN, F><<<grid, EW_THREADS, 0, s>>>(out, a, b, c, n, f);
+        else ew_flat_scalar<NIN, F><<<grid, EW_THREADS, 0, s>>>(out, a, b, c, n, f);
     }
     NB_LAUNCH_CHECK();
     return NB200_OK;

@@ -1972,7 +1972,10 @@ static int gemm_fp16x3(const GemmArgs &g) {
     // workspace, double-buffered by call parity.  A single-chunk call uses block `parity` and its pre-pass zeroes the other one for
     // the next call (Ctx::ctl_ready), so steady-state calls enqueue no memset; multi-chunk calls use block 0 with explicit memsets.
     const int64_t ctl_stride = (16 + cols_layout * 4 + 255) & ~int64_t(255);
-    const bool single = chunk >= g.batch;
+    // (inside a stream capture the recorded call is replayed many times: it must carry its own memset and leave the cross-call state alone)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    NB_CUDA(cudaStreamIsCapturing(ctx().stream, &cap));
+    const bool single = chunk >= g.batch && cap == cudaStreamCaptureStatusNone;
     for (int64_t b0 = 0; b0 < g.batch; b0 += chunk) {
         const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
         const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;   // matrices of each operand in this chunk

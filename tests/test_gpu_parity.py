@@ -790,6 +790,42 @@ def test_sgemm_batched_host_pipeline(nb):
             assert rel_err(c[i], ORACLE.matmul(a[i], b[i])).max() <= RTOL, (batch, i)
 
 
+def test_cuda_graph_capture_replays_a_sequence_of_calls(nb):
+    """nb200_graph_begin / end / launch: a chain of small elementwise calls and one nd::matmul recorded once, replayed on new data;
+    every replay matches the oracle (the recorded FP16x3 call carries its own control-block memset)."""
+    import ctypes as C
+    lib = nb.lib()
+    r = _rng(55)
+    n = 1 << 16
+    a, b = r.random(n, dtype=np.float32), r.random(n, dtype=np.float32)
+    m1, m2 = r.random((256, 384), dtype=np.float32), r.random((384, 264), dtype=np.float32)
+    da, db, dt, do = _dev(nb, a), _dev(nb, b), _dev(nb, np.zeros(n, np.float32)), _dev(nb, np.zeros(n, np.float32))
+    dm1, dm2, dmo = _dev(nb, m1), _dev(nb, m2), _dev(nb, np.zeros((256, 264), np.float32))
+    shp, st = (C.c_int64 * 1)(n), (C.c_int64 * 1)(1)
+    assert lib.nb200_sgemm(dmo, dm1, dm2, 256, 264, 384, 384, 264, 264, nb.GEMM_AUTO) == 0      # warm-up: workspace allocated outside the capture
+    assert lib.nb200_synchronize() == 0
+    assert lib.nb200_graph_begin() == 0, lib.nb200_last_error()
+    assert lib.nb200_ew_binary(2, dt, da, db, 1, shp, st, st) == 0            # t = a * b
+    assert lib.nb200_ew_binary(0, do, dt, da, 1, shp, st, st) == 0            # o = t + a
+    assert lib.nb200_ew_unary(1, do, do, n, 0.0, 0.0) == 0                    # o = sqrt(o)
+    assert lib.nb200_sgemm(dmo, dm1, dm2, 256, 264, 384, 384, 264, 264, nb.GEMM_AUTO) == 0
+    g = C.c_void_p()
+    assert lib.nb200_graph_end(C.byref(g)) == 0, lib.nb200_last_error()
+    for rep in range(3):
+        a2 = r.random(n, dtype=np.float32)
+        m1b = r.random((256, 384), dtype=np.float32)
+        assert lib.nb200_copy_h2d(da, a2.ctypes.data, a2.nbytes) == 0
+        assert lib.nb200_copy_h2d(dm1, m1b.ctypes.data, m1b.nbytes) == 0
+        assert lib.nb200_graph_launch(g) == 0, lib.nb200_last_error()
+        assert lib.nb200_synchronize() == 0
+        exp = ORACLE.unary("sqrt", ORACLE.binary("add", ORACLE.binary("mul", a2, b), a2))
+        np.testing.assert_array_equal(_fetch(nb, do, (n,)), exp)
+        assert rel_err(_fetch(nb, dmo, (256, 264)), ORACLE.matmul(m1b, m2)).max() <= RTOL
+    assert lib.nb200_graph_destroy(g) == 0
+    for p in (da, db, dt, do, dm1, dm2, dmo):
+        lib.nb200_free(p)
+
+
 # --------------------------------------------------------------------- comparisons (SURVEY §8 f, N2)
 @pytest.mark.parametrize("op", ["equal", "not_equal", "greater", "greater_equal", "less", "less_equal"])
 def test_comparisons_vs_oracle(nb, op):
