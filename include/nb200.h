@@ -89,26 +89,28 @@ enum nb200_reduce_op { NB200_SUM = 0, NB200_PROD = 1, NB200_MIN = 2, NB200_MAX =
 enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
 
 /* nd::matmul precision.
- * TF32X3: error-compensated 3-pass TF32 on the tcgen05 tensor pipe; guaranteed error bound
- *   ~3*2^-22 per product (+ chunked round-to-nearest accumulation): meets 1e-5 vs cblas_sgemm
- *   for every input.  This is what AUTO (and therefore nd::matmul) runs.
- * TF32X1: single pass, fast mode (~7e-4).
- * BF16X3: operands split into two bfloat16 parts each, three kind::f16 MMAs per k-step at twice
- *   the TF32 rate (1.8x faster end to end).  Statistical accuracy: per-product error up to
- *   2^-16 + 2*2^-17, zero-mean - measured max rel. error 1.2-2.5e-6 vs fp64 on random data from
- *   K = 77 to 8192, but coherent inputs (constant matrices) can reach ~3e-5.  Opt-in per call, or
- *   NB200_GEMM_AUTO_MODE=bf16x3 lets AUTO choose it for K >= 128.  Accepts any alignment / ld.
- * FP16X3 (experimental, opt-in; also NB200_GEMM_AUTO_MODE=fp16x3): the same pipeline with IEEE-half
- *   parts of A scaled per row and B scaled per column by powers of two (lo parts stored x2^11; the
- *   epilogue undoes all scaling exactly).  Every non-zero element within 2^-28 of its row / column
- *   maximum keeps a 2^-22 relative split error: TF32X3-class guaranteed bound, no coherent-input
- *   problem.  The split pre-pass checks that window ON THE DEVICE: a few elements outside it are
- *   taken out of the GEMM and added back by a sparse fp32 repair kernel; if there are too many, the
- *   gated TF32X3 fallback enqueued with the call produces the result instead (bit-identical to a
- *   TF32X3 call).  Needs operands the TF32 path can read (16-byte aligned, ld % 4 == 0).
- * AUTO: see above. */
+ * AUTO (what nd::matmul passes): the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every
+ *   input - a scaled half-precision split (FP16X3 or H16B16X3, see nb200_gemm_resolve_precision) for K >= 128,
+ *   TF32X3 below (pre-pass not worth it) and for shapes too small for the tensor path.
+ * TF32X3: error-compensated 3-pass TF32 on the tcgen05 tensor pipe; guaranteed bound ~3*2^-22 per product
+ *   (+ chunked round-to-nearest accumulation).  Also what the FP16X3 / H16B16X3 device-side fallback runs.
+ * TF32X1: single pass, fast mode (~7e-4); not a parity mode.
+ * BF16X3: operands split into two bfloat16 parts each, three kind::f16 MMAs per k-step at twice the TF32 rate.
+ *   Statistical accuracy only: per-product error up to 2^-16 + 2*2^-17, zero-mean - measured 1.2-2.5e-6 on random
+ *   data, but coherent inputs (constant matrices) can reach ~3e-5.  Opt-in per call (or NB200_GEMM_AUTO_MODE=bf16x3).
+ * FP16X3: IEEE-half parts of A scaled per row and B scaled per column by powers of two (lo parts stored x2^11; the
+ *   epilogue undoes all scaling exactly).  Every non-zero element within 2^-28 of its row / column maximum keeps a
+ *   2^-22 relative split error: TF32X3-class guaranteed bound, no coherent-input problem.  The split pre-pass checks
+ *   that window ON THE DEVICE: a few elements outside it are taken out of the GEMM and added back by a sparse fp32
+ *   repair kernel; if there are too many, the gated TF32X3 fallback enqueued with the call produces the result
+ *   instead (bit-identical to a TF32X3 call).  Any alignment / leading dimension (the pre-pass repacks).
+ * H16B16X3: FP16X3 with the lo parts stored as UNSCALED bfloat16 (hi: IEEE half, 11 bits; lo: bfloat16, 8 bits; split
+ *   error <= 2^-19 per element, <= 2^-18 + 2^-22 per product = 4.1e-6 worst case, every input).  All three products
+ *   then carry one scale, so a whole 256-long k-chunk accumulates into ONE TMEM accumulator and the 256x256 tile of
+ *   BF16X3 applies: ~8 % less tensor time than FP16X3's 256x128 tile, and a 2x shorter truncating accumulation (smaller
+ *   systematic bias).  Same window rule, repair and fallback as FP16X3. */
 enum nb200_gemm_precision { NB200_GEMM_TF32X3 = 0, NB200_GEMM_TF32X1 = 1, NB200_GEMM_BF16X3 = 2, NB200_GEMM_AUTO = 3,
-                            NB200_GEMM_FP16X3 = 4 };
+                            NB200_GEMM_FP16X3 = 4, NB200_GEMM_H16B16X3 = 5 };
 
 /* ---- context / device -------------------------------------------------------- */
 /* Replaces the process-global cudaSetDevice of NDArray::setDevice (numpower.c:615-635). */

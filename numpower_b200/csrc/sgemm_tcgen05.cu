@@ -37,8 +37,15 @@
 namespace nb200 {
 
 // ------------------------------------------------------------------ configuration
-template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false, bool MERGED_ = false, bool SCALED_ = false>
+template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false, bool MERGED_ = false, bool SCALED_ = false, bool MIXLO_ = false>
 struct GemmCfg {
+    // MIXLO (H16B16x3 = SCALED with bfloat16 lo parts): hi = rn_f16(a') as in FP16x3, lo = rn_bf16(a' - hi) UNSCALED - bfloat16 has
+    // fp32's exponent range, so the lo parts need no 2^11 factor and all three products of a k-block carry the same scale.  The
+    // cross products multiply an f16 operand with a bf16 one: tcgen05.mma.kind::f16 takes the A and B formats from separate fields
+    // of the instruction descriptor.  One accumulator per chunk => the MERGED 256x256 tile works exactly as for BF16x3 (K = 256
+    // chunks, no scale-input-d).  Split error per element <= 2^-11 * 2^-8 = 2^-19 (FP16x3: 2^-22; BF16x3: 2^-16).
+    static constexpr bool MIXLO = MIXLO_;
+    static_assert(!MIXLO_ || SCALED_, "bf16 lo parts belong to the scaled half-precision mode");
     // SCALED (FP16x3): the 16-bit operand parts are IEEE half (11-bit significands, TF32x3-class split error) of
     // A scaled per row and B scaled per column by powers of two (so that every row / column uses the top of fp16's
     // exponent range); the epilogue undoes the scaling with one exact scalbnf per output element.
@@ -50,7 +57,8 @@ struct GemmCfg {
     //  * SCALED + MERGED (256x256 tiles, ONE accumulator per chunk): a chunk is a single k-block (K = 64); its cross
     //    products are issued first and the first a_hi.b_hi MMA of the chunk carries tcgen05.mma's scale-input-d = 11
     //    (D = A.B + D * 2^-11, exact), so the chunk accumulator ends up holding hh + 2^-11 (lh + hl).
-    static constexpr float CROSS_SCALE = (SCALED_ && !MERGED_) ? 1.0f / 2048.0f : 1.0f;
+    static constexpr float CROSS_SCALE = (SCALED_ && !MERGED_ && !MIXLO_) ? 1.0f / 2048.0f : 1.0f;
+    static constexpr bool SCALE_D = SCALED_ && MERGED_ && !MIXLO_;   // fold 2^11-scaled cross products with scale-input-d, one k-block per chunk
     // MERGED (BF16x3, BN = 256): all three products of a chunk accumulate into ONE 256-column TMEM accumulator (2-deep
     // ring = all 512 columns) and the running total lives in the registers of eight epilogue warps.  Twice the flops
     // per staged byte and no cross-accumulator hand-off between tiles; costs 48 instead of 32 truncating accumulation
@@ -90,7 +98,7 @@ struct GemmCfg {
     // accumulator.  TMEM columns: [0,BN) [BN,2BN) main ring | [2BN,3BN) cross terms | [3BN,4BN) running total.
     static constexpr bool CHUNKED = PASSES == 3;
     // K elements per accumulation chunk (32 MMA k-steps; MERGED: 16 x 3 products; SCALED + MERGED: one k-block, see above)
-    static constexpr int KC = (SCALED_ && MERGED_) ? BK : (BF16_ && !MERGED_) ? 512 : 256;
+    static constexpr int KC = SCALE_D ? BK : (BF16_ && !MERGED_) ? 512 : 256;
     static constexpr int KB_PER_CHUNK = KC / BK;
     static constexpr int TMEM_COLS = (CHUNKED && !MERGED_) ? 4 * BN : ACC_STAGES * BN;   // 256 or 512 (power of two)
     static_assert(!CHUNKED || MERGED_ || BN == 128, "chunked x3 uses 128-column tiles (4 x 128 TMEM columns)");
@@ -98,7 +106,7 @@ struct GemmCfg {
     static constexpr int EPI_WARPS = MERGED_ ? 8 : 4;
     // MERGED epilogue: accumulator columns per tcgen05.ld (each load is followed by a wait of a few hundred cycles).  One k-block
     // per chunk (SCALED) drains a 256-column accumulator every 12 MMAs: 64 columns per load, two waits per chunk.
-    static constexpr int EPI_LD = (SCALED_ && MERGED_) ? 64 : 16;
+    static constexpr int EPI_LD = SCALE_D ? 64 : 16;
     // MERGED: 12 warps = 3 warpgroups.  Warpgroup 0 = TMA producer, MMA issuer and two idle warps (TMEM allocation); warpgroups
     // 1-2 = eight epilogue warps that keep 128 running totals + the TMEM load in flight in registers: setmaxnreg moves registers
     // from warpgroup 0 (72 per thread) to the epilogue warpgroups (216 per thread; 128 * 72 + 256 * 216 <= 64 Ki).  A 10-warp CTA
@@ -639,7 +647,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             tmem_ld_32x32(t_cross + (uint32_t)(c * 32), m);
                             if (!first) tmem_ld_32x32(t_total + (uint32_t)(c * 32), x);
                             tmem_ld_wait();
-                            if constexpr (Cfg::SCALED) {   // the lo parts are stored times 2^11 (exact power-of-two factor)
+                            if constexpr (Cfg::SCALED && !Cfg::MIXLO) {   // the lo parts are stored times 2^11 (exact power-of-two factor)
 #pragma unroll
                                 for (int q = 0; q < 32; q++) m[q] = __float_as_uint(__uint_as_float(m[q]) * Cfg::CROSS_SCALE);
                             }
@@ -734,6 +742,7 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
             constexpr uint32_t FMT = Cfg::SCALED ? 0u : (Cfg::BF16 ? 1u : 2u);   // operand format: f16 / bf16 (kind::f16), tf32
+            constexpr uint32_t FMT_LO = Cfg::MIXLO ? 1u : FMT;                   // format of the lo parts (MIXLO: bf16 next to f16 hi parts)
             constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
@@ -768,6 +777,9 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
                     // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
                     const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite) == p.nonfinite_gen) ? 1 : 0;
+                    // per-product instruction descriptors (they differ only when the lo parts have their own format)
+                    const uint32_t idesc_lh = make_idesc(BM * CG, nn, FMT_LO, hi_part ? FMT_LO : FMT);
+                    const uint32_t idesc_hl = make_idesc(BM * CG, nn, hi_part ? FMT_LO : FMT, FMT_LO);
                     const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
                     for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
                         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
@@ -785,19 +797,19 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc_lh, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, 1u);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc_hl, 1u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 0) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, 0) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    if constexpr (Cfg::SCALED && Cfg::MERGED) {   // chunk == this k-block: fold its cross products (x 2^11) first
+                                    if constexpr (Cfg::SCALE_D) {   // chunk == this k-block: fold its cross products (x 2^11) first
                                         if (k == 0) umma_f16_scale_d11<CG>(d_main, da, db, idesc);
                                         else umma_tf32<CG, true>(d_main, da, db, idesc, 1u);
                                     } else {
@@ -1112,6 +1124,8 @@ struct FixList {
     unsigned int *count;                   // device counter (reset by the host before the operand is split)
     int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
 };
+// MIX: the lo part is an UNSCALED bfloat16, lo = rn_bf16(a' - hi) (GemmCfg::MIXLO): remainder <= 2^-19 |a'|, same window rule.
+template <bool MIX>
 __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, unsigned short &l, int *nonfinite, int gen,
                                           const FixList &fix, int64_t row, int64_t col) {
     const unsigned int ab = __float_as_uint(a) & 0x7FFFFFFFu;
@@ -1124,7 +1138,8 @@ __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, uns
     const float x = scale_pow2(a, e);
     const __half hh = __float2half_rn(x);
     h = __half_as_ushort(hh);
-    l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.0f));
+    if constexpr (MIX) l = __bfloat16_as_ushort(__float2bfloat16_rn(x - __half2float(hh)));
+    else l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.0f));
     if (ab != 0u && fabsf(x) < 6.103515625e-05f) {  // below 2^-14: hi would be a subnormal half -> repair record
         // The element leaves the GEMM entirely (hi = lo = 0) and is carried by the record in full fp32: a lo-only
         // representation would multiply it with the partner's hi part alone, i.e. with 11 bits (measured 4.7e-4).
@@ -1142,6 +1157,7 @@ struct SplitSpanF16 {
     FixList fix;
 };
 // General operands (any alignment / leading dimension; rows are repacked to ld_out = cols rounded up to 8): four elements per thread.
+template <bool MIX>
 __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, const SplitSpanF16 s1, int *__restrict__ nonfinite, int gen) {
     pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < s0.s.groups + s1.s.groups; i += (int64_t)gridDim.x * 256) {
@@ -1164,7 +1180,7 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const SplitSpanF16 s0, c
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int ex = sp.by_col ? (c + e < s.cols ? scale_exp(sp.max_bits[b * s.cols + c + e]) : 0) : e_row;
-            split_f16(v[e], ex, h[e], l[e], nonfinite, gen, sp.fix, r, c + e);
+            split_f16<MIX>(v[e], ex, h[e], l[e], nonfinite, gen, sp.fix, r, c + e);
         }
         const int64_t o = r * s.ld_out + c;
         uint2 hv, lv;
@@ -1184,14 +1200,15 @@ __device__ __forceinline__ Pow2Pair scale_factors(int e) {
     return {__int_as_float((e1 + 127) << 23), __int_as_float((e2 + 127) << 23)};
 }
 // returns {hi.x, hi.y, lo.x, lo.y} by value (pointer outputs would pin the caller's fast-path results to local memory)
+template <bool MIX>
 __device__ __noinline__ uint4 split4_careful(float4 v, int e0, int e1, int e2, int e3, int *nonfinite, int gen,
                                              unsigned int *fix_count, int4 *fix_recs, int64_t r, int64_t c) {
     const FixList fix{fix_count, fix_recs};
     unsigned short h[4], l[4];
-    split_f16(v.x, e0, h[0], l[0], nonfinite, gen, fix, r, c);
-    split_f16(v.y, e1, h[1], l[1], nonfinite, gen, fix, r, c + 1);
-    split_f16(v.z, e2, h[2], l[2], nonfinite, gen, fix, r, c + 2);
-    split_f16(v.w, e3, h[3], l[3], nonfinite, gen, fix, r, c + 3);
+    split_f16<MIX>(v.x, e0, h[0], l[0], nonfinite, gen, fix, r, c);
+    split_f16<MIX>(v.y, e1, h[1], l[1], nonfinite, gen, fix, r, c + 1);
+    split_f16<MIX>(v.z, e2, h[2], l[2], nonfinite, gen, fix, r, c + 2);
+    split_f16<MIX>(v.w, e3, h[3], l[3], nonfinite, gen, fix, r, c + 3);
     return make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
                       (uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
@@ -1200,15 +1217,21 @@ __device__ __forceinline__ bool outside_window(float x) {
     const unsigned int b = __float_as_uint(x) & 0x7FFFFFFFu;
     return (b - 0x38800000u) >= 0x47000000u && b != 0u;
 }
+template <bool MIX>
 __device__ __forceinline__ bool split4_fast(const float4 &v, const Pow2Pair &s0, const Pow2Pair &s1, const Pow2Pair &s2, const Pow2Pair &s3,
                                             uint2 &hi, uint2 &lo) {
     const float x0 = v.x * s0.f1 * s0.f2, x1 = v.y * s1.f1 * s1.f2, x2 = v.z * s2.f1 * s2.f2, x3 = v.w * s3.f1 * s3.f2;
     const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn((x0 - f01.x) * 2048.0f, (x1 - f01.y) * 2048.0f);
-    const __half2 l23 = __floats2half2_rn((x2 - f23.x) * 2048.0f, (x3 - f23.y) * 2048.0f);
     hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
-    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+    if constexpr (MIX) {
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2bfloat162_rn(x2 - f23.x, x3 - f23.y);
+        lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+    } else {
+        const __half2 l01 = __floats2half2_rn((x0 - f01.x) * 2048.0f, (x1 - f01.y) * 2048.0f);
+        const __half2 l23 = __floats2half2_rn((x2 - f23.x) * 2048.0f, (x3 - f23.y) * 2048.0f);
+        lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+    }
     return outside_window(x0) | outside_window(x1) | outside_window(x2) | outside_window(x3);
 }
 
@@ -1244,17 +1267,18 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
 }
 __device__ __forceinline__ unsigned int abs8_bits(const float4 &a, const float4 &b) { return max(abs4_bits(a), abs4_bits(b)); }
 // one 8-element group of a row of A (both quads share the row's factors) -> 16-byte stores
+template <bool MIX>
 __device__ __forceinline__ void store_group_a(const float4 &a, const float4 &b, int e, const Pow2Pair &sc, uint4 *hi, uint4 *lo, int *nonfinite,
                                               int gen, const FixList &fix, int64_t r, int64_t c, uint64_t pol) {
     uint2 h0, l0, h1, l1;
-    const bool bad0 = split4_fast(a, sc, sc, sc, sc, h0, l0), bad1 = split4_fast(b, sc, sc, sc, sc, h1, l1);
-    if (bad0) { const uint4 w = split4_careful(a, e, e, e, e, nonfinite, gen, fix.count, fix.recs, r, c); h0 = make_uint2(w.x, w.y); l0 = make_uint2(w.z, w.w); }
-    if (bad1) { const uint4 w = split4_careful(b, e, e, e, e, nonfinite, gen, fix.count, fix.recs, r, c + 4); h1 = make_uint2(w.x, w.y); l1 = make_uint2(w.z, w.w); }
+    const bool bad0 = split4_fast<MIX>(a, sc, sc, sc, sc, h0, l0), bad1 = split4_fast<MIX>(b, sc, sc, sc, sc, h1, l1);
+    if (bad0) { const uint4 w = split4_careful<MIX>(a, e, e, e, e, nonfinite, gen, fix.count, fix.recs, r, c); h0 = make_uint2(w.x, w.y); l0 = make_uint2(w.z, w.w); }
+    if (bad1) { const uint4 w = split4_careful<MIX>(b, e, e, e, e, nonfinite, gen, fix.count, fix.recs, r, c + 4); h1 = make_uint2(w.x, w.y); l1 = make_uint2(w.z, w.w); }
     st_l2(hi, make_uint4(h0.x, h0.y, h1.x, h1.y), pol);
     st_l2(lo, make_uint4(l0.x, l0.y, l1.x, l1.y), pol);
 }
 // Rows of A held in registers: TPR threads per row, 256 / TPR rows per CTA pass, up to two groups per thread (row length <= 16 * TPR).
-template <int TPR>
+template <int TPR, bool MIX>
 __device__ __forceinline__ void prep_a_rows(const PrepCoop &q, int rank, int n_ctas, int *nonfinite, int gen, unsigned int (*red)[8], uint64_t pol) {
     constexpr int RPC = 256 / TPR;                         // rows per CTA pass
     const int t = threadIdx.x % TPR, rg = threadIdx.x / TPR, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1290,11 +1314,12 @@ __device__ __forceinline__ void prep_a_rows(const PrepCoop &q, int rank, int n_c
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int64_t g = t + u * TPR;
-            if (g < n8) store_group_a(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
+            if (g < n8) store_group_a<MIX>(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
         }
     }
 }
 // rows longer than 4096: one CTA per row, pass 1 reduces the |max|, pass 2 re-reads the row (L1 / L2: this CTA just read it) and splits
+template <bool MIX>
 __device__ __forceinline__ void prep_a_rows_long(const PrepCoop &q, int rank, int n_ctas, int *nonfinite, int gen, unsigned int (*red)[8], uint64_t pol) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int64_t n8 = q.a.s.cols >> 3;
@@ -1333,11 +1358,12 @@ __device__ __forceinline__ void prep_a_rows_long(const PrepCoop &q, int rank, in
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int64_t g = g0 + t + u * 256;
-                if (g < n8) store_group_a(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
+                if (g < n8) store_group_a<MIX>(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
             }
         }
     }
 }
+template <bool MIX>
 __global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, int *__restrict__ nonfinite, int gen) {
     __shared__ unsigned int red[2][8];
     const int t = threadIdx.x;
@@ -1356,11 +1382,11 @@ __global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, i
         const int rank = i - b_before, n_a = G - q.n_b;
         const int64_t n8 = q.a.s.cols >> 3;
         if (q.a_rows > 0) {
-            if (n8 <= 64) prep_a_rows<32>(q, rank, n_a, nonfinite, gen, red, pol);
-            else if (n8 <= 128) prep_a_rows<64>(q, rank, n_a, nonfinite, gen, red, pol);
-            else if (n8 <= 256) prep_a_rows<128>(q, rank, n_a, nonfinite, gen, red, pol);
-            else if (n8 <= 512) prep_a_rows<256>(q, rank, n_a, nonfinite, gen, red, pol);
-            else prep_a_rows_long(q, rank, n_a, nonfinite, gen, red, pol);
+            if (n8 <= 64) prep_a_rows<32, MIX>(q, rank, n_a, nonfinite, gen, red, pol);
+            else if (n8 <= 128) prep_a_rows<64, MIX>(q, rank, n_a, nonfinite, gen, red, pol);
+            else if (n8 <= 256) prep_a_rows<128, MIX>(q, rank, n_a, nonfinite, gen, red, pol);
+            else if (n8 <= 512) prep_a_rows<256, MIX>(q, rank, n_a, nonfinite, gen, red, pol);
+            else prep_a_rows_long<MIX>(q, rank, n_a, nonfinite, gen, red, pol);
         }
         if (t == 0) { trace_max(q.trace, 1); trace_max(q.trace, 4); }
         return;
@@ -1450,8 +1476,8 @@ __global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, i
             for (int u = 0; u < 4; u++) {
                 const int64_t rr = r - u * TY;
                 uint2 h, l;
-                if (split4_fast(v[u], s0, s1, s2, s3, h, l)) {
-                    const uint4 w = split4_careful(v[u], e0, e1, e2, e3, nonfinite, gen, q.b.fix.count, q.b.fix.recs, mat * K + rr, c4 * 4);
+                if (split4_fast<MIX>(v[u], s0, s1, s2, s3, h, l)) {
+                    const uint4 w = split4_careful<MIX>(v[u], e0, e1, e2, e3, nonfinite, gen, q.b.fix.count, q.b.fix.recs, mat * K + rr, c4 * 4);
                     h = make_uint2(w.x, w.y); l = make_uint2(w.z, w.w);
                 }
                 st_l2(hi + rr * n4, h, pol);
@@ -1461,8 +1487,8 @@ __global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, i
         for (; r >= r0; r -= TY) {
             const float4 v = ldg_stream_l2(src + r * n4, pol);
             uint2 h, l;
-            if (split4_fast(v, s0, s1, s2, s3, h, l)) {
-                const uint4 w = split4_careful(v, e0, e1, e2, e3, nonfinite, gen, q.b.fix.count, q.b.fix.recs, mat * K + r, c4 * 4);
+            if (split4_fast<MIX>(v, s0, s1, s2, s3, h, l)) {
+                const uint4 w = split4_careful<MIX>(v, e0, e1, e2, e3, nonfinite, gen, q.b.fix.count, q.b.fix.recs, mat * K + r, c4 * 4);
                 h = make_uint2(w.x, w.y); l = make_uint2(w.z, w.w);
             }
             st_l2(hi + r * n4, h, pol);
@@ -1867,7 +1893,7 @@ static int fp16_pair_bn(int64_t batch, int64_t M, int64_t N) {
 }
 static int launch_fp16_prepass(const float *a_src, const float *b_src, const GemmArgs &g, int64_t ba, int64_t bb, bool do_a, bool do_b,
                                SplitSpanF16 &sa, SplitSpanF16 &sb, unsigned int *row_max, unsigned int *col_max, unsigned int *barrier,
-                               unsigned int *zero_ptr, int64_t zero_words, bool *zeroed_other) {
+                               unsigned int *zero_ptr, int64_t zero_words, bool *zeroed_other, bool mix) {
     *zeroed_other = false;
     const int64_t n_rows = ba * g.M;
     if (sa.s.groups + sb.s.groups == 0) return NB200_OK;
@@ -1878,7 +1904,10 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
         const int dev = ctx().device;
         int occ = (dev >= 0 && dev < 64) ? per_sm[dev] : 0;
         if (occ == 0) {
-            NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prep16_coop_kernel, 256, 0));
+            int occ0 = 0, occ1 = 0;   // (both instantiations: the grid must be co-resident whichever runs)
+            NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, prep16_coop_kernel<false>, 256, 0));
+            NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, prep16_coop_kernel<true>, 256, 0));
+            occ = occ0 < occ1 ? occ0 : occ1;
             if (occ < 1) return set_error(NB200_ECUDA, "sgemm: the FP16x3 pre-pass kernel does not fit on an SM");
             if (dev >= 0 && dev < 64) per_sm[dev] = occ;
         }
@@ -1915,7 +1944,8 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
         pa[0].val.programmaticStreamSerializationAllowed = 1;
         pc.attrs = pa;
         pc.numAttrs = pdl_enabled() ? 1 : 0;
-        NB_CUDA(cudaLaunchKernelEx(&pc, prep16_coop_kernel, q, nonfinite_flag(), ctx().nonfinite_gen));
+        if (mix) NB_CUDA(cudaLaunchKernelEx(&pc, prep16_coop_kernel<true>, q, nonfinite_flag(), ctx().nonfinite_gen));
+        else NB_CUDA(cudaLaunchKernelEx(&pc, prep16_coop_kernel<false>, q, nonfinite_flag(), ctx().nonfinite_gen));
         ctx().launches++;
         *zeroed_other = zero_words > 0;
         return NB200_OK;
@@ -1942,12 +1972,13 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
     }
     int64_t blocks = (sa.s.groups + sb.s.groups + 255) / 256;
     if (blocks > 0x7FFFFFFF) blocks = 0x7FFFFFFF;
-    split_f16_kernel<<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
+    if (mix) split_f16_kernel<true><<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
+    else split_f16_kernel<false><<<(unsigned)blocks, 256, 0, ctx().stream>>>(sa, sb, nonfinite_flag(), ctx().nonfinite_gen);
     NB_LAUNCH_CHECK();
     return NB200_OK;
 }
 
-static int gemm_fp16x3(const GemmArgs &g) {
+static int gemm_fp16x3(const GemmArgs &g, bool mix) {
     const bool raw_ok = tensor_path_ok(g);                       // the TF32x3 fallback can read the raw operands
     const int64_t lda = round8(g.K), ldb = round8(g.N);
     const int64_t per_a = g.M * lda, per_b = g.K * ldb;          // 16-bit elements per matrix
@@ -1962,7 +1993,8 @@ static int gemm_fp16x3(const GemmArgs &g) {
     { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
     const int v = gemm_variant();
     const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
-    const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? fp16_pair_bn(chunk, g.M, g.N) : 128);
+    // H16B16x3 (mix): one accumulator per chunk, so the merged 256x256 tile is chosen exactly as for BF16x3 (wave quantisation)
+    const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? (mix ? bf16_pair_bn(chunk, g.M, g.N) : fp16_pair_bn(chunk, g.M, g.N)) : 128);
     const bool merged = cg == 2 && bn == 256;
     // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
     const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
@@ -2017,7 +2049,7 @@ static int gemm_fp16x3(const GemmArgs &g) {
         sb.max_bits = col_max; sb.by_col = 1; sb.fix = fix_b;
         bool zeroed_other = false;
         if ((rc = launch_fp16_prepass(a_src, b_src, g, ba, bb, do_a, do_b, sa, sb, row_max, col_max, fix_cnt + 2, other_ctl, single ? need / 4 : 0,
-                                      &zeroed_other)) != NB200_OK) return rc;
+                                      &zeroed_other, mix)) != NB200_OK) return rc;
         if (single) {
             if (zeroed_other) cx.ctl_ready[1 - mine] = need;
             cx.ctl_parity = 1 - mine;
@@ -2032,7 +2064,10 @@ static int gemm_fp16x3(const GemmArgs &g) {
         c.C = g.C + b0 * g.sC;
         c.row_max = row_max; c.col_max = col_max;
         c.gate_want = 0;
-        if (merged) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
+        if (mix) {
+            if (merged) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true, true>>(c);
+            else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true, true>>(c);
+        } else if (merged) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
         else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
         if (rc != NB200_OK) return rc;
         // (2) eligible: sparse repair of the recorded out-of-window elements (normally none: returns at once);
@@ -2085,7 +2120,8 @@ int gemm_resolve_precision(int precision, int64_t K) {
     if (precision != NB200_GEMM_AUTO) return precision;
     static const char *mode = getenv("NB200_GEMM_AUTO_MODE");
     static const int fast = !mode ? NB200_GEMM_FP16X3 : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
-                                  : strcmp(mode, "tf32x3") == 0 ? NB200_GEMM_TF32X3 : NB200_GEMM_FP16X3;
+                                  : strcmp(mode, "tf32x3") == 0 ? NB200_GEMM_TF32X3
+                                  : strcmp(mode, "h16b16x3") == 0 ? NB200_GEMM_H16B16X3 : NB200_GEMM_FP16X3;
     return K >= 128 ? fast : NB200_GEMM_TF32X3;
 }
 
@@ -2102,11 +2138,12 @@ static int gemm_impl(GemmArgs g, int precision) {
     const bool bf16_ok = g.M * g.N * g.K >= (int64_t)64 * 64 * 64 && g.K >= 32 && g.N >= 32;
     static const bool force_simt = getenv("NB200_GEMM_FORCE_SIMT") != nullptr;   // debugging switch, read once
     if (precision == NB200_GEMM_BF16X3 && bf16_ok && !force_simt) return gemm_bf16x3(g);
-    if (precision == NB200_GEMM_FP16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g);
+    if (precision == NB200_GEMM_FP16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g, false);
+    if (precision == NB200_GEMM_H16B16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g, true);
     // TF32X3 asked for on operands the TF32 path cannot read (4-byte aligned views, ld % 4 != 0): the FP16x3 pre-pass
     // repacks them, same class of guaranteed bound, so they stay on the tensor pipe instead of the fp32 SIMT kernel
-    if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g);
-    if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
+    if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g, false);
+    if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_H16B16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
         if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
@@ -2191,7 +2228,7 @@ extern "C" int nb200_sgemm_batched(float *C, const float *A, const float *B, int
     NB_READY();
     if (!C || !A || !B || batch < 0 || M < 0 || N < 0 || K < 0 || strideA < 0 || strideB < 0 || strideC < 0)
         return set_error(NB200_EINVAL, "nb200_sgemm_batched: bad argument");
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_H16B16X3)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, batch, M, N, K, K, N, N, strideA, strideB, strideC};
     return gemm_impl(g, precision);
@@ -2203,7 +2240,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
     if (!C || !A || !B || M < 0 || N < 0 || K < 0 || lda < K || ldb < N || ldc < N)
         return set_error(NB200_EINVAL, "Shape mismatch for matmul (M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
                          (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_H16B16X3)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
     return gemm_impl(g, precision);
@@ -2216,7 +2253,7 @@ extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, 
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
     precision = gemm_resolve_precision(precision, K);
     int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024
-                : precision == NB200_GEMM_FP16X3 ? 4 * (M * round8(K) + K * round8(N)) + 4 * round4(M) + 2 * ((16 + 4 * round4(N) + 255) & ~int64_t(255)) + 4 * (round4(M * K) + round4(K * N)) + 2 * (int64_t)FIX_CAP * 16 + 1024
+                : (precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_H16B16X3) ? 4 * (M * round8(K) + K * round8(N)) + 4 * round4(M) + 2 * ((16 + 4 * round4(N) + 255) & ~int64_t(255)) + 4 * (round4(M * K) + round4(K * N)) + 2 * (int64_t)FIX_CAP * 16 + 1024
                                                  : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = gemm_ws_budget();

@@ -277,3 +277,71 @@ def test_fp16x3_merged_scale_input_d_matches_the_split_model(k):
     b[:] = 0.7501221
     exact = a.astype(np.float64) @ b.astype(np.float64)
     assert (np.abs(fp16x3_merged_model(a, b) - exact) / exact).max() <= 3 * 2.0 ** -22 + (k / 64 + 2) * 2.0 ** -24
+
+
+# ------------------------------------------------------------------ H16B16x3: half hi parts + UNSCALED bfloat16 lo parts
+def split_h16b16_scaled(x, e):
+    """split_f16<MIX = true>() in sgemm_tcgen05.cu: hi = rn_f16(x * 2^e), lo = rn_bf16(x * 2^e - hi), no 2^11 factor."""
+    xs = np.ldexp(x.astype(np.float64), e)
+    hi = xs.astype(np.float32).astype(np.float16)
+    lo = rn_bf16((xs - hi.astype(np.float64)).astype(np.float32))      # xs - hi is exact in fp32
+    eligible = bool(((xs == 0) | (np.abs(xs) >= 2.0 ** -14)).all())
+    return hi.astype(np.float64), lo.astype(np.float64), eligible
+
+
+def h16b16x3_model(a, b):
+    ea = scale_exp(np.abs(a).max(axis=1))[:, None]
+    eb = scale_exp(np.abs(b).max(axis=0))[None, :]
+    ah, al, ok_a = split_h16b16_scaled(a, ea)
+    bh, bl, ok_b = split_h16b16_scaled(b, eb)
+    if not (ok_a and ok_b):
+        return None
+    return np.ldexp(ah @ bh + ah @ bl + al @ bh, -(ea + eb))
+
+
+def test_h16b16_split_remainder_bound():
+    """11-bit hi + 8-bit lo: |lo| <= 2^-11 |x|, remainder <= 2^-19 |x| for every element inside the window."""
+    r = np.random.default_rng(21)
+    x = ((r.random(1 << 16, dtype=np.float32) + 0.5) * np.exp2(r.integers(-27, 1, 1 << 16)).astype(np.float32)).astype(np.float32)
+    x[0] = 1.4999999                                                  # the row maximum: the exponent brings it to [2^14, 2^15)
+    hi, lo, ok = split_h16b16_scaled(x[None, :], scale_exp(np.abs(x).max(keepdims=True))[:, None])
+    assert ok
+    xs = np.ldexp(x.astype(np.float64), int(scale_exp(np.abs(x).max(keepdims=True))[0]))
+    assert (np.abs(lo[0]) <= np.abs(xs) * 2.0 ** -11).all()
+    assert (np.abs(xs - hi[0] - lo[0]) <= np.abs(xs) * 2.0 ** -19).all()
+
+
+def test_h16b16x3_coherent_inputs_stay_inside_1e5():
+    """One product repeated K times (what breaks BF16x3): the per-product error is bounded by 2^-18 + 2^-22 = 4.1e-6 for
+    EVERY pair of values, i.e. the 1e-5 contract holds with a factor 2.4 to spare before accumulation effects."""
+    r = np.random.default_rng(7)
+    n = 100_000
+    a = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
+    b = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
+    exact = a.astype(np.float64) * b.astype(np.float64)
+    got = np.array([h16b16x3_model(a[i:i + 1, None], b[None, i:i + 1])[0, 0] for i in range(0, n, 20)])
+    err = np.abs(got - exact[::20]) / exact[::20]
+    assert err.max() <= 2.0 ** -18 + 2.0 ** -22 < 1e-5
+    assert err.max() > 2.0 ** -21                                     # (it IS coarser than FP16x3's 2^-20 class: documented trade)
+
+
+@pytest.mark.parametrize("k", [8, 256, 2048])
+def test_h16b16x3_random_dynamic_range_and_gather(k):
+    r = np.random.default_rng(300 + k)
+    a, b = r.random((64, k), dtype=np.float32), r.random((k, 48), dtype=np.float32)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    err = np.abs(h16b16x3_model(a, b) - exact) / exact
+    assert err.max() <= 2.0 ** -18
+    if k >= 256:
+        assert err.max() <= 5e-7                                      # zero-mean split errors average out over K
+    a2 = (a * np.exp2(r.integers(-60, 61, size=(64, 1))).astype(np.float32)).astype(np.float32)
+    b2 = (b * np.exp2(r.integers(-60, 61, size=(1, 48))).astype(np.float32)).astype(np.float32)
+    exact2 = a2.astype(np.float64) @ b2.astype(np.float64)
+    assert (np.abs(h16b16x3_model(a2, b2) - exact2) / np.abs(exact2)).max() <= 2.0 ** -18
+    # gather: every output is ONE input element with its own split error (<= 2^-19), also 2^-26 below the row maximum
+    g = ((r.random((32, 128), dtype=np.float32) + 0.5) * np.exp2(r.integers(-26, 1, size=(32, 128))).astype(np.float32)).astype(np.float32)
+    perm = r.permutation(128)
+    pm = np.zeros((128, 128), np.float32)
+    pm[perm, np.arange(128)] = 1.0
+    got = h16b16x3_model(g, pm)
+    assert (np.abs(got - g[:, perm].astype(np.float64)) / g[:, perm]).max() <= 2.0 ** -19

@@ -337,7 +337,7 @@ def test_matmul_auto_is_the_guaranteed_mode(nb):
     for every input.  BF16X3 is opt-in (include/nb200.h); on a constant matrix pair its coherent split error shows, AUTO's
     does not."""
     r = _rng(77)
-    for (m, k, n), mode in (((256, 512, 256), nb.FP16X3), ((256, 96, 256), nb.TF32X3)):
+    for (m, k, n), mode in (((256, 512, 256), nb.lib().nb200_gemm_resolve_precision(nb.GEMM_AUTO, 512)), ((256, 96, 256), nb.TF32X3)):
         a, b = r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32)
         A, B = nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()
         np.testing.assert_array_equal(nb.nd.matmul(A, B).toArray(), nb.nd.matmul(A, B, mode).toArray())
@@ -350,42 +350,39 @@ def test_matmul_auto_is_the_guaranteed_mode(nb):
     assert rel_err(nb.nd.matmul(A, B, nb.BF16X3).toArray(), exp).max() <= 5e-5    # documented statistical mode
 
 
-@pytest.mark.parametrize("tile", ["128", "256"])
-def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
-    """The two FP16x3 tile shapes (256x128 with the separate cross accumulator; merged 256x256 whose per-k-block accumulator
-    folds the 2^11-scaled cross products with tcgen05.mma's scale-input-d) through AUTO: random, coherent, row/column dynamic range, signed (norm-wise),
-    inf/NaN propagation, ragged shapes, batch with a shared operand.  NB200_FP16_TILE is read per call."""
-    monkeypatch.setenv("NB200_FP16_TILE", tile)
-    r = _rng(1000 + int(tile))
+def _matmul_contract_cases(nb, prec, seed, gather_tol):
+    """Everything the 1e-5 contract has to survive, through one precision mode: random, coherent, row/column dynamic range, signed
+    (norm-wise), inf/NaN propagation, ragged shapes, out-of-window repair / fallback, batch with a shared operand."""
+    r = _rng(seed)
     # (K = 512 / 1024: one warp per row of A in the pre-pass, 2048: one CTA per row, 9000: two-pass rows; 1001: repacking split)
     for (m, k, n) in ((256, 512, 256), (512, 1024, 768), (1000, 520, 776), (300, 136, 264), (257, 1001, 267), (384, 2048, 520), (136, 9000, 264)):
-        _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.GEMM_AUTO, RTOL)
+        _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), prec, RTOL)
     # coherent: one product repeated K times, values next to rounding boundaries of the 11-bit / 8-bit parts
     for val in (1.00390613, 1.0004883, 0.33333334, 1.9990234):
         a = np.full((256, 640), val, np.float32)
         b = np.full((640, 512), val * 0.7501221, np.float32)
-        got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+        got = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), prec).toArray()
         assert rel_err(got, ORACLE.matmul(a, b)).max() <= RTOL
     # rows / columns scaled by 2^-60 .. 2^60
     a2 = (r.random((512, 160), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(512, 1))).astype(np.float32)).astype(np.float32)
     b2 = (r.random((160, 512), dtype=np.float32) * np.exp2(r.integers(-60, 61, size=(1, 512))).astype(np.float32)).astype(np.float32)
     exp2 = ORACLE.matmul(a2, b2)
     ok = np.isfinite(exp2) & (np.abs(exp2) > 1e-30)
-    got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu()).toArray()
+    got2 = nb.nd.matmul(nb.NDArray.array(a2).gpu(), nb.NDArray.array(b2).gpu(), prec).toArray()
     assert rel_err(got2[ok], exp2[ok]).max() <= RTOL
     # elements spread over 2^-20 .. 1 inside every row / column, gathered one by one through a permutation matrix
     g = ((r.random((256, 512), dtype=np.float32) + 0.5) * np.exp2(r.integers(-20, 1, size=(256, 512))).astype(np.float32)).astype(np.float32)
     perm = r.permutation(512)
     pm = np.zeros((512, 512), np.float32)
     pm[perm, np.arange(512)] = 1.0
-    got = nb.nd.matmul(nb.NDArray.array(g).gpu(), nb.NDArray.array(pm).gpu()).toArray()
-    assert rel_err(got, g[:, perm]).max() <= 2.0 ** -19
+    got = nb.nd.matmul(nb.NDArray.array(g).gpu(), nb.NDArray.array(pm).gpu(), prec).toArray()
+    assert rel_err(got, g[:, perm]).max() <= gather_tol
     # inf / NaN propagate like cblas_sgemm
     a3 = r.random((256, 256), dtype=np.float32)
     b3 = r.random((256, 512), dtype=np.float32)
     a3[3, 7] = np.inf; a3[100, 5] = -np.inf; b3[9, 200] = np.nan; b3[7, 50] = 0.0
     exp3 = ORACLE.matmul(a3, b3)
-    got3 = nb.nd.matmul(nb.NDArray.array(a3).gpu(), nb.NDArray.array(b3).gpu()).toArray()
+    got3 = nb.nd.matmul(nb.NDArray.array(a3).gpu(), nb.NDArray.array(b3).gpu(), prec).toArray()
     np.testing.assert_array_equal(np.isnan(got3), np.isnan(exp3))
     np.testing.assert_array_equal(np.isposinf(got3), np.isposinf(exp3))
     np.testing.assert_array_equal(np.isneginf(got3), np.isneginf(exp3))
@@ -394,7 +391,7 @@ def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
     # signed inputs, norm-wise
     a4 = (r.random((640, 1024), dtype=np.float32) * 2 - 1).astype(np.float32)
     b4 = (r.random((1024, 512), dtype=np.float32) * 2 - 1).astype(np.float32)
-    got4 = nb.nd.matmul(nb.NDArray.array(a4).gpu(), nb.NDArray.array(b4).gpu()).toArray()
+    got4 = nb.nd.matmul(nb.NDArray.array(a4).gpu(), nb.NDArray.array(b4).gpu(), prec).toArray()
     scale = (np.abs(a4).astype(np.float64) @ np.abs(b4).astype(np.float64)).max()
     assert np.abs(got4.astype(np.float64) - ORACLE.matmul(a4, b4)).max() / scale <= RTOL
     # out-of-window elements: repaired (few) / fallback (many) - the fallback is bit for bit the TF32X3 result
@@ -404,23 +401,50 @@ def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
     b5[:, 11] = 0.0
     b5[5, 11] = 1.5
     exp5 = ORACLE.matmul(a5, b5)
-    got5 = nb.nd.matmul(nb.NDArray.array(a5).gpu(), nb.NDArray.array(b5).gpu()).toArray()
+    got5 = nb.nd.matmul(nb.NDArray.array(a5).gpu(), nb.NDArray.array(b5).gpu(), prec).toArray()
     assert rel_err(got5[17, 11], exp5[17, 11]) <= RTOL and rel_err(got5, exp5).max() <= RTOL
     a6 = a5.copy()
     a6[:40, :128] *= np.float32(2.0 ** -40)
     A6, B5 = nb.NDArray.array(a6).gpu(), nb.NDArray.array(b5).gpu()
-    np.testing.assert_array_equal(nb.nd.matmul(A6, B5).toArray(), nb.nd.matmul(A6, B5, nb.TF32X3).toArray())
+    np.testing.assert_array_equal(nb.nd.matmul(A6, B5, prec).toArray(), nb.nd.matmul(A6, B5, nb.TF32X3).toArray())
     # batch with a shared B through the C-ABI
     lib = nb.lib()
     batch, M, N, K = 3, 256, 264, 200
     a7, b7 = r.random((batch, M, K), dtype=np.float32), r.random((K, N), dtype=np.float32)
     da, db, dc = _dev(nb, a7), _dev(nb, b7), _dev(nb, np.zeros((batch, M, N), np.float32))
-    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, nb.GEMM_AUTO) == 0, lib.nb200_last_error()
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, 0, M * N, prec) == 0, lib.nb200_last_error()
     got7 = _fetch(nb, dc, (batch, M, N))
     for i in range(batch):
         assert rel_err(got7[i], ORACLE.matmul(a7[i], b7)).max() <= RTOL
     for p in (da, db, dc):
         lib.nb200_free(p)
+
+
+@pytest.mark.parametrize("tile", ["128", "256"])
+def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
+    """The two FP16x3 tile shapes (256x128 with the separate cross accumulator; merged 256x256 whose per-k-block accumulator
+    folds the 2^11-scaled cross products with tcgen05.mma's scale-input-d).  NB200_FP16_TILE is read per call."""
+    monkeypatch.setenv("NB200_FP16_TILE", tile)
+    _matmul_contract_cases(nb, nb.FP16X3, 1000 + int(tile), 2.0 ** -19)
+
+
+def test_matmul_h16b16x3_all_contract_cases(nb):
+    """H16B16x3 (half hi parts + unscaled bfloat16 lo parts, mixed-format kind::f16 cross products, merged 256x256 tile): the same
+    contract cases.  A gathered element carries the split error of ONE element: <= 2^-19 (include/nb200.h)."""
+    _matmul_contract_cases(nb, nb.H16B16X3, 1500, 2.0 ** -18.9)
+
+
+def test_matmul_auto_contract_cases(nb):
+    """Whatever NB200_GEMM_AUTO resolves to (nb200_gemm_resolve_precision) passes the contract cases too."""
+    _matmul_contract_cases(nb, nb.GEMM_AUTO, 1700, 2.0 ** -18.9)
+
+
+@pytest.mark.parametrize("mkn", [(128, 128, 256), (384, 1024, 640), (1000, 520, 776), (333, 77, 129), (257, 1001, 67), (2048, 2048, 512),
+                                 (4096, 256, 4096)])
+def test_matmul_h16b16x3_vs_cblas_sgemm(nb, mkn):
+    m, k, n = mkn
+    r = _rng(m + k + n + 2)
+    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.H16B16X3, RTOL)
 
 
 def test_matmul_unaligned_operands_stay_on_the_tensor_path(nb):
