@@ -215,6 +215,15 @@ int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, int64_t K, 
 int nb200_gemm_resolve_precision(int precision, int64_t K);
 /* y[rows] = A[rows,cols]·x[cols] — replaces cuda_float_multiply_matrix_vector (cuda_math.h:62). */
 int nb200_gemv(float *y, const float *A, const float *x, int64_t rows, int64_t cols);
+/* nd::all (NDArray_All, src/logic.c:25-58): *host_out = 1 iff no element equals 0 (NaN counts as non-zero, the rule of the
+ * reference's scalar loop; its AVX2 body compares the 8-lane mask with 0x0F and so answers 0 for every array of >= 8 elements -
+ * the intended semantics are implemented, pinned by tests/logic/001-ndarray-all.phpt).  Blocking; n == 0 -> 1. */
+int nb200_all(int *host_out, const float *a, int64_t n);
+/* nd::allclose (NDArray_AllClose / float_allclose, src/logic.c:718-771; the reference refuses device arrays): *host_out = 1 iff
+ * no element has |a - b| > atol + rtol * |b| - the reference's predicate, evaluated on element i of both arrays (its loop
+ * indexes element 4i + i*stride/4, i.e. out of bounds; pinned by tests/logic/002-ndarray-allclose.phpt).  Same-shape contiguous
+ * operands of n elements.  Blocking; n == 0 -> 1. */
+int nb200_allclose(int *host_out, const float *a, const float *b, int64_t n, float rtol, float atol);
 /* out[cols,rows] = in[rows,cols]^T, out != in — replaces cuda_float_transpose (cuda_math.h:77). */
 int nb200_transpose2d(float *out, const float *in, int64_t rows, int64_t cols);
 

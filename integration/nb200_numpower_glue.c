@@ -10,6 +10,12 @@
  *   reduce()                                              -> nb200_glue_reduce   (one launch instead of one per slice)
  *   NDArray_ArgMinMaxCommon                               -> nb200_glue_argminmax (the reference throws "GPU not supported.")
  *   NDArray_Matmul                                        -> nb200_glue_matmul   (2-D and stacks of matrices -> batched kernel)
+ *   NDArray_Maximum / NDArray_Minimum                     -> nb200_glue_binary   (the reference throws "not implemented for GPU")
+ *   NDArray_MaxAxis                                       -> nb200_glue_max_axis (the reference throws "GPU NDArray_MaxAxis not implemented")
+ *   NDArray_Dot (N-D . 1-D)                               -> nb200_glue_dot      (every leading row, not only the last matrix)
+ *
+ * Unary methods need no host patch: the legacy NDArrayMathGPU_ElementWise* drivers in libnb200.so recognise the
+ * cuda_float_<op> pointer the PHP method passes (numpower.c:1648-3348) and run the op out of place.
  *
  * Every function returns NULL when the call is not a device call it serves; the reference code then runs unchanged.
  * Results are complete on return (the reference host reads them with default-stream cudaMemcpy right away).
@@ -141,5 +147,41 @@ NDArray *nb200_glue_matmul(NDArray *a, NDArray *b) {
                         : nb200_sgemm_batched(NDArray_FDATA(r), NDArray_FDATA(a), NDArray_FDATA(b), batch, M, N, K, M * K, K * N, M * N,
                                               NB200_GEMM_AUTO);
     if (rc != NB200_OK || nb200_synchronize() != NB200_OK) { glue_throw("nb200_sgemm"); NDArray_FREE(r); return NULL; }
+    return r;
+}
+
+/* NDArray_MaxAxis ndarray.c:781-844: max over one axis, shape without that axis.  The reference's CPU loop only indexes 2-D inputs
+ * correctly; on the device any ndim is served (outer x axis x inner decomposition).  NaN rule of the CPU loop (`current > best`). */
+NDArray *nb200_glue_max_axis(NDArray *target, int axis) {
+    if (NDArray_DEVICE(target) != NDARRAY_DEVICE_GPU) return NULL;
+    if (axis < 0 || axis >= NDArray_NDIM(target)) { zend_throw_error(NULL, "Invalid axis.\n"); return NULL; }
+    int64_t outer = 1, inner = 1, oshape[NB200_MAX_DIMS];
+    int j = 0;
+    if (NDArray_NDIM(target) > NB200_MAX_DIMS) return NULL;
+    for (int i = 0; i < NDArray_NDIM(target); i++) {
+        if (i < axis) outer *= NDArray_SHAPE(target)[i];
+        if (i > axis) inner *= NDArray_SHAPE(target)[i];
+        if (i != axis) oshape[j++] = NDArray_SHAPE(target)[i];
+    }
+    NDArray *r = gpu_result(oshape, NDArray_NDIM(target) - 1);
+    if (nb200_reduce_axis(NB200_MAX, NDArray_FDATA(r), NDArray_FDATA(target), outer, NDArray_SHAPE(target)[axis], inner, NB200_ORDER_TREE) != NB200_OK ||
+        nb200_synchronize() != NB200_OK) { glue_throw("nb200_reduce_axis"); NDArray_FREE(r); return NULL; }
+    return r;
+}
+
+/* NDArray_Dot linalg.c:354-393, the N-D . 1-D case: y = A x over ALL leading rows (the reference's GPU branch passes
+ * shape[ndim-2] rows to cuda_float_multiply_matrix_vector, i.e. only the first matrix of a stack is computed). */
+NDArray *nb200_glue_dot(NDArray *nda, NDArray *ndb) {
+    if (NDArray_DEVICE(nda) != NDARRAY_DEVICE_GPU || NDArray_DEVICE(ndb) != NDARRAY_DEVICE_GPU) return NULL;
+    if (NDArray_NDIM(nda) < 2 || NDArray_NDIM(ndb) != 1 || NDArray_NDIM(nda) > NB200_MAX_DIMS) return NULL;   /* other cases: reference dispatch */
+    const int nd = NDArray_NDIM(nda);
+    const int64_t cols = NDArray_SHAPE(nda)[nd - 1];
+    if (cols != NDArray_SHAPE(ndb)[0]) return NULL;
+    int64_t rows = 1, oshape[NB200_MAX_DIMS];
+    for (int i = 0; i < nd - 1; i++) { rows *= NDArray_SHAPE(nda)[i]; oshape[i] = NDArray_SHAPE(nda)[i]; }
+    NDArray *r = gpu_result(oshape, nd - 1);
+    if (nb200_gemv(NDArray_FDATA(r), NDArray_FDATA(nda), NDArray_FDATA(ndb), rows, cols) != NB200_OK || nb200_synchronize() != NB200_OK) {
+        glue_throw("nb200_gemv"); NDArray_FREE(r); return NULL;
+    }
     return r;
 }

@@ -61,6 +61,8 @@ ABI = {
     "nb200_gemm_resolve_precision": (C.c_int, [C.c_int, i64]),
     "nb200_gemv": (C.c_int, [fp, fp, fp, i64, i64]),
     "nb200_transpose2d": (C.c_int, [fp, fp, i64, i64]),
+    "nb200_all": (C.c_int, [C.POINTER(C.c_int), fp, i64]),
+    "nb200_allclose": (C.c_int, [C.POINTER(C.c_int), fp, fp, i64, C.c_float, C.c_float]),
     # multi-GPU shards: pointer arrays are (c_void_p * G)
     "nb200_shard_init": (C.c_int, [C.c_int, C.POINTER(C.c_int)]), "nb200_shard_finalize": (C.c_int, []),
     "nb200_shard_count": (C.c_int, [C.POINTER(C.c_int)]), "nb200_shard_device": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),

@@ -11,6 +11,8 @@ extern "C" {
 void zend_throw_error(void *exception_ce, const char *format, ...) __attribute__((weak));
 // src/initializers.h:31 — provided by the host objects
 struct NDArray *NDArray_Copy(struct NDArray *a, int device) __attribute__((weak));
+// src/initializers.h:27 — uninitialised array of the same shape / device (the out-of-place unary route)
+struct NDArray *NDArray_EmptyLike(struct NDArray *a) __attribute__((weak));
 }
 
 namespace {
@@ -40,11 +42,8 @@ void binary(int op, float *a, float *b, float *rtn, int n, const char *what) {
     int64_t shape[1] = {n}, st[1] = {1};
     leave(nb200_ew_binary(op, rtn, a, b, 1, shape, st, st), what);
 }
-void unary(int op, float *d, int n, float p0, float p1, const char *what) {
-    enter();
-    int rc = nb200_ew_unary(op, d, d, n, p0, p1);
-    leave(rc, what);
-    if (rc == NB200_OK && (op == NB200_UN_ARCCOS || op == NB200_UN_ARCCOSH || op == NB200_UN_ARCTANH)) {
+void domain_check(int op, const char *what) {
+    if (op == NB200_UN_ARCCOS || op == NB200_UN_ARCCOSH || op == NB200_UN_ARCTANH) {
         int flag = 0;
         if (nb200_poll_domain_error(&flag) == NB200_OK && flag) {
             // the CPU functors exit(1) here (double_math.c:145-148); the backend raises instead
@@ -52,6 +51,12 @@ void unary(int op, float *d, int n, float p0, float p1, const char *what) {
             else fprintf(stderr, "libnb200: RuntimeError: Invalid argument provided for %s\n", what);
         }
     }
+}
+void unary(int op, float *d, int n, float p0, float p1, const char *what) {
+    enter();
+    int rc = nb200_ew_unary(op, d, d, n, p0, p1);
+    leave(rc, what);
+    if (rc == NB200_OK) domain_check(op, what);
 }
 void not_implemented(const char *what) {
     if (zend_throw_error) zend_throw_error(nullptr, "%s is not implemented in the B200 backend (out of scope: SURVEY.md section 2)", what);
@@ -169,8 +174,44 @@ NB_LEGACY_UNARY(cuda_float_reciprocal, NB200_UN_RECIPROCAL)
 void cuda_float_clip(int n, float *d, float lo, float hi) { unary(NB200_UN_CLIP, d, n, lo, hi, "cuda_float_clip"); }
 void cuda_float_round(int n, float *d, float decimals) { unary(NB200_UN_ROUND, d, n, decimals, 0.f, "cuda_float_round"); }
 
-// ---- NDArray-level unary drivers (cuda_math.cu:1532-1558): copy, then the in-place op
+// ---- NDArray-level unary drivers (cuda_math.cu:1532-1558).  The reference copies the operand (NDArray_Copy: 8 B per element) and
+// then runs the in-place op on the copy (another 8 B per element).  Here the PHP method's `cuda_float_<op>` argument is recognised
+// by its address and the op runs OUT OF PLACE into a fresh array from the host's own NDArray_EmptyLike (initializers.c:406): one
+// kernel, 8 B per element, no host patch needed (numpower.c:1648-3348 stays as it is).  An op pointer that is not one of this
+// library's wrappers takes the reference's copy-then-in-place route.
+static int unary_op_of(const void *fn) {
+    static const struct { const void *fn; int op; } table[] = {
+        {(const void *)cuda_float_abs, NB200_UN_ABS}, {(const void *)cuda_float_expm1, NB200_UN_EXPM1}, {(const void *)cuda_float_exp, NB200_UN_EXP},
+        {(const void *)cuda_float_sqrt, NB200_UN_SQRT}, {(const void *)cuda_float_log, NB200_UN_LOG}, {(const void *)cuda_float_logb, NB200_UN_LOGB},
+        {(const void *)cuda_float_log2, NB200_UN_LOG2}, {(const void *)cuda_float_log1p, NB200_UN_LOG1P}, {(const void *)cuda_float_log10, NB200_UN_LOG10},
+        {(const void *)cuda_float_sin, NB200_UN_SIN}, {(const void *)cuda_float_cos, NB200_UN_COS}, {(const void *)cuda_float_tan, NB200_UN_TAN},
+        {(const void *)cuda_float_arcsin, NB200_UN_ARCSIN}, {(const void *)cuda_float_arccos, NB200_UN_ARCCOS}, {(const void *)cuda_float_arctan, NB200_UN_ARCTAN},
+        {(const void *)cuda_float_degrees, NB200_UN_DEGREES}, {(const void *)cuda_float_radians, NB200_UN_RADIANS}, {(const void *)cuda_float_sinh, NB200_UN_SINH},
+        {(const void *)cuda_float_cosh, NB200_UN_COSH}, {(const void *)cuda_float_tanh, NB200_UN_TANH}, {(const void *)cuda_float_arcsinh, NB200_UN_ARCSINH},
+        {(const void *)cuda_float_arccosh, NB200_UN_ARCCOSH}, {(const void *)cuda_float_arctanh, NB200_UN_ARCTANH}, {(const void *)cuda_float_rint, NB200_UN_RINT},
+        {(const void *)cuda_float_fix, NB200_UN_FIX}, {(const void *)cuda_float_ceil, NB200_UN_CEIL}, {(const void *)cuda_float_floor, NB200_UN_FLOOR},
+        {(const void *)cuda_float_sinc, NB200_UN_SINC}, {(const void *)cuda_float_trunc, NB200_UN_TRUNC}, {(const void *)cuda_float_negate, NB200_UN_NEGATIVE},
+        {(const void *)cuda_float_sign, NB200_UN_SIGN}, {(const void *)cuda_float_positive, NB200_UN_POSITIVE}, {(const void *)cuda_float_reciprocal, NB200_UN_RECIPROCAL},
+        {(const void *)cuda_float_clip, NB200_UN_CLIP}, {(const void *)cuda_float_round, NB200_UN_ROUND},
+    };
+    for (const auto &e : table) if (e.fn == fn) return e.op;
+    return -1;
+}
+// out-of-place route; nullptr = not served (unknown op pointer or a host without NDArray_EmptyLike)
+static struct NDArray *unary_out_of_place(struct NDArray *nd, const void *fn, float p0, float p1, const char *what) {
+    const int op = unary_op_of(fn);
+    if (op < 0 || !NDArray_EmptyLike) return nullptr;
+    HostNDArray *h = reinterpret_cast<HostNDArray *>(nd);
+    HostNDArray *r = reinterpret_cast<HostNDArray *>(NDArray_EmptyLike(nd));
+    if (!r) return nullptr;
+    enter();
+    int rc = nb200_ew_unary(op, reinterpret_cast<float *>(r->data), reinterpret_cast<const float *>(h->data), (int64_t)h->descriptor->numElements, p0, p1);
+    leave(rc, what);
+    if (rc == NB200_OK) domain_check(op, what);
+    return reinterpret_cast<struct NDArray *>(r);
+}
 struct NDArray *NDArrayMathGPU_ElementWise(struct NDArray *nd, ElementWiseFloatGPUOperation op) {
+    if (struct NDArray *r = unary_out_of_place(nd, (const void *)op, 0.f, 0.f, "NDArrayMathGPU_ElementWise")) return r;
     if (!NDArray_Copy) { not_implemented("NDArrayMathGPU_ElementWise without the host's NDArray_Copy"); return nullptr; }
     HostNDArray *h = reinterpret_cast<HostNDArray *>(nd);
     HostNDArray *r = reinterpret_cast<HostNDArray *>(NDArray_Copy(nd, h->device));
@@ -178,6 +219,7 @@ struct NDArray *NDArrayMathGPU_ElementWise(struct NDArray *nd, ElementWiseFloatG
     return reinterpret_cast<struct NDArray *>(r);
 }
 struct NDArray *NDArrayMathGPU_ElementWise1F(struct NDArray *nd, ElementWiseFloatGPUOperation1F op, float v1) {
+    if (struct NDArray *r = unary_out_of_place(nd, (const void *)op, v1, 0.f, "NDArrayMathGPU_ElementWise1F")) return r;
     if (!NDArray_Copy) { not_implemented("NDArrayMathGPU_ElementWise1F without the host's NDArray_Copy"); return nullptr; }
     HostNDArray *h = reinterpret_cast<HostNDArray *>(nd);
     HostNDArray *r = reinterpret_cast<HostNDArray *>(NDArray_Copy(nd, h->device));
@@ -185,6 +227,7 @@ struct NDArray *NDArrayMathGPU_ElementWise1F(struct NDArray *nd, ElementWiseFloa
     return reinterpret_cast<struct NDArray *>(r);
 }
 struct NDArray *NDArrayMathGPU_ElementWise2F(struct NDArray *nd, ElementWiseFloatGPUOperation2F op, float v1, float v2) {
+    if (struct NDArray *r = unary_out_of_place(nd, (const void *)op, v1, v2, "NDArrayMathGPU_ElementWise2F")) return r;
     if (!NDArray_Copy) { not_implemented("NDArrayMathGPU_ElementWise2F without the host's NDArray_Copy"); return nullptr; }
     HostNDArray *h = reinterpret_cast<HostNDArray *>(nd);
     HostNDArray *r = reinterpret_cast<HostNDArray *>(NDArray_Copy(nd, h->device));

@@ -57,8 +57,72 @@ __global__ void __launch_bounds__(256) transpose_kernel(float *__restrict__ out,
         if (c0 + ty + j < cols && r0 + tx < rows) out[(c0 + ty + j) * rows + r0 + tx] = tile[tx][ty + j];
 }
 
+// ---- boolean reductions: nd::all (src/logic.c:25-58) and nd::allclose (src/logic.c:718-771) ------------------------------------
+// Both are "does any element violate a predicate": every thread tests its elements (four 16-byte loads in flight per operand),
+// __syncthreads_or folds the CTA, and a CTA that saw a violation stores 1 into the result word (plain store of the same value:
+// no atomics, no ordering needed).  HBM-bound: 4 B (all) / 8 B (allclose) per element.
+//   all:      violation = (x == 0)                      NaN is non-zero, as in the reference's scalar loop (`array[i] == 0.0`)
+//   allclose: violation = |a - b| > atol + rtol * |b|   the reference's predicate (logic.c:730-733); a NaN difference is NOT a violation
+template <bool CLOSE>
+__global__ void __launch_bounds__(256) logic_any_kernel(int *__restrict__ violated, const float *__restrict__ a, const float *__restrict__ b,
+                                                        int64_t n, float rtol, float atol, int vec) {
+    auto bad = [&](float x, float y) { return CLOSE ? (fabsf(x - y) > atol + rtol * fabsf(y)) : (x == 0.0f); };
+    int v = 0;
+    if (vec) {
+        const float4 *a4 = reinterpret_cast<const float4 *>(a), *b4 = reinterpret_cast<const float4 *>(b);
+        const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * 256;
+        int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            float4 x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { x[u] = ldg_stream(a4 + i + u * stride); if (CLOSE) y[u] = ldg_stream(b4 + i + u * stride); else y[u] = x[u]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) v |= bad(x[u].x, y[u].x) | bad(x[u].y, y[u].y) | bad(x[u].z, y[u].z) | bad(x[u].w, y[u].w);
+        }
+        for (; i < n4; i += stride) {
+            const float4 x = ldg_stream(a4 + i), y = CLOSE ? ldg_stream(b4 + i) : x;
+            v |= bad(x.x, y.x) | bad(x.y, y.y) | bad(x.z, y.z) | bad(x.w, y.w);
+        }
+        for (int64_t e = (n4 << 2) + (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += stride) v |= bad(a[e], CLOSE ? b[e] : a[e]);
+    } else {
+        for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) v |= bad(a[e], CLOSE ? b[e] : a[e]);
+    }
+    if (__syncthreads_or(v) && threadIdx.x == 0) *violated = 1;
+}
+
+static int logic_any(bool close, int *host_out, const float *a, const float *b, int64_t n, float rtol, float atol) {
+    int *flag = reinterpret_cast<int *>(ctx().dev_result) + 12;          // byte 48 of the 64-byte result slot
+    int *hflag = reinterpret_cast<int *>(ctx().host_result) + 12;
+    NB_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), ctx().stream));
+    if (n > 0) {
+        const int vec = aligned16(a) && (!close || aligned16(b));
+        int64_t grid = (n / 4 + 1023) / 1024, cap = (int64_t)ctx().num_sms * 8;   // <= one wave of 8 CTAs per SM, >= 4 loads per thread
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        if (close) logic_any_kernel<true><<<(unsigned)grid, 256, 0, ctx().stream>>>(flag, a, b, n, rtol, atol, vec);
+        else logic_any_kernel<false><<<(unsigned)grid, 256, 0, ctx().stream>>>(flag, a, a, n, 0.f, 0.f, vec);
+        NB_LAUNCH_CHECK();
+    }
+    NB_CUDA(cudaMemcpyAsync(hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    NB_CUDA(cudaStreamSynchronize(ctx().stream));
+    *host_out = *hflag ? 0 : 1;
+    return NB200_OK;
+}
+
 }  // namespace nb200
 using namespace nb200;
+
+extern "C" int nb200_all(int *host_out, const float *a, int64_t n) {
+    NB_READY();
+    if (!host_out || (!a && n > 0) || n < 0) return set_error(NB200_EINVAL, "nb200_all: bad argument");
+    return logic_any(false, host_out, a, a, n, 0.f, 0.f);
+}
+
+extern "C" int nb200_allclose(int *host_out, const float *a, const float *b, int64_t n, float rtol, float atol) {
+    NB_READY();
+    if (!host_out || ((!a || !b) && n > 0) || n < 0) return set_error(NB200_EINVAL, "nb200_allclose: bad argument");
+    return logic_any(true, host_out, a, b, n, rtol, atol);
+}
 
 extern "C" int nb200_gemv(float *y, const float *A, const float *x, int64_t rows, int64_t cols) {
     NB_READY();

@@ -179,6 +179,25 @@ class nd:
         return a.size == 0 or nd.min(nd.equal(a, b)) == 1.0
 
     @staticmethod
+    def all(a) -> int:
+        """NDArray::all (NDArray_All, logic.c:25-58): 1 iff no element is zero (one boolean-reduction kernel, nb200_all)."""
+        a = nd._a(a)
+        out = C.c_int(0)
+        L.check(L.lib().nb200_all(C.byref(out), a.data_ptr, a.size))
+        return int(out.value)
+
+    @staticmethod
+    def allclose(a, b, rtol: float = 1e-5, atol: float = 1e-8) -> bool:
+        """NDArray::allclose (NDArray_AllClose, logic.c:748-771; the reference refuses device arrays): |a - b| <= atol + rtol * |b|
+        everywhere.  Same error behaviour: "Shape mismatch"."""
+        a, b = nd._a(a), nd._a(b)
+        if a.shape != b.shape:
+            raise RuntimeError("Shape mismatch")
+        out = C.c_int(0)
+        L.check(L.lib().nb200_allclose(C.byref(out), a.data_ptr, b.data_ptr, a.size, float(rtol), float(atol)))
+        return bool(out.value)
+
+    @staticmethod
     def mul_add(a, b, c) -> NDArray:
         """Fused ``$a * $b + $c`` (nb200_ew_mul_add): one pass, same bits as the two nd:: calls."""
         a, b, c = nd._a(a), nd._a(b), nd._a(c)

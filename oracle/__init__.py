@@ -116,6 +116,9 @@ class _Ref:
             lib.ref_dot.argtypes = [_fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
             lib.ref_matmul_nd.restype = C.c_long
             lib.ref_matmul_nd.argtypes = [_fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
+            if hasattr(lib, "ref_all"):
+                lib.ref_all.argtypes = [_fp, _ip, C.c_int]
+                lib.ref_allclose.argtypes = [_fp, _fp, _ip, C.c_int, C.c_float, C.c_float]
             self._lib = lib
         return self._lib
 
@@ -242,6 +245,20 @@ class _Ref:
         self.last_seconds = sec.value
         return out
 
+    def all(self, a) -> int:
+        """NDArray_All on the reference's object code - only trustworthy for fewer than 8 elements (see oracle/port.c)."""
+        a = _c32(a)
+        r = self.lib.ref_all(_f(a), _shape(a), a.ndim)
+        self._check(0, "all")
+        return int(r)
+
+    def allclose(self, a, b, rtol: float = 1e-5, atol: float = 1e-8) -> int:
+        """NDArray_AllClose on the reference's object code - reads out of bounds beyond the first element (see oracle/port.c)."""
+        a, b = _c32(a), _c32(b)
+        r = self.lib.ref_allclose(_f(a), _f(b), _shape(a), a.ndim, rtol, atol)
+        self._check(0, "allclose")
+        return int(r)
+
     def dot(self, a, b) -> np.ndarray:
         a, b = _c32(a), _c32(b)
         if a.ndim == 2 and b.ndim == 2:
@@ -279,6 +296,8 @@ class _Port:
             lib.port_matmul.argtypes = [_fp, _fp, _fp, C.c_long, C.c_long, C.c_long]
             lib.port_matmul_f64.argtypes = [_fp, _fp, _dp, C.c_long, C.c_long, C.c_long]
             lib.port_gemv.argtypes = [_fp, _fp, _fp, C.c_long, C.c_long]
+            lib.port_all.argtypes = [_fp, C.c_long]
+            lib.port_allclose.argtypes = [_fp, _fp, C.c_long, C.c_float, C.c_float]
             self._lib = lib
         return self._lib
 
@@ -344,6 +363,16 @@ class _Port:
         out = np.empty((a.shape[0], b.shape[1]), dtype=np.float64)
         self.lib.port_matmul_f64(_f(a), _f(b), out.ctypes.data_as(_dp), a.shape[0], a.shape[1], b.shape[1])
         return out
+
+    def all(self, a) -> int:
+        a = _c32(a)
+        return int(self.lib.port_all(_f(a), a.size))
+
+    def allclose(self, a, b, rtol: float = 1e-5, atol: float = 1e-8) -> int:
+        a, b = _c32(a), _c32(b)
+        if a.shape != b.shape:
+            raise RuntimeError("Shape mismatch")
+        return int(self.lib.port_allclose(_f(a), _f(b), a.size, rtol, atol))
 
     def gemv(self, a, x) -> np.ndarray:
         a, x = _c32(a), _c32(x)

@@ -12,7 +12,9 @@ DECL = ('\n#include <nb200.h>\n'
         'NDArray *nb200_glue_binary(int op, NDArray *a, NDArray *b);\n'
         'NDArray *nb200_glue_reduce(NDArray *array, int *axis, NDArray *(*operation)(NDArray *, NDArray *));\n'
         'NDArray *nb200_glue_argminmax(NDArray *op, int axis, bool keepdims, bool is_argmax);\n'
-        'NDArray *nb200_glue_matmul(NDArray *a, NDArray *b);\n')
+        'NDArray *nb200_glue_matmul(NDArray *a, NDArray *b);\n'
+        'NDArray *nb200_glue_max_axis(NDArray *target, int axis);\n'
+        'NDArray *nb200_glue_dot(NDArray *nda, NDArray *ndb);\n')
 
 # file -> [(regex matching the function's definition line incl. "{", code inserted after it)]
 PATCHES = {
@@ -24,9 +26,13 @@ PATCHES = {
         (r"^NDArray_Mod_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_MOD"),
         (r"^NDArray_Pow_Float\(NDArray\* a, NDArray\* b\) \{", "NB200_POW"),
     ],
-    "src/ndarray.c": [(r"^reduce\(NDArray \*array, int \*axis, NDArray \*\(\*operation\)\(NDArray \*, NDArray \*\)\) \{", "REDUCE")],
+    "src/ndarray.c": [(r"^reduce\(NDArray \*array, int \*axis, NDArray \*\(\*operation\)\(NDArray \*, NDArray \*\)\) \{", "REDUCE"),
+                      (r"^NDArray_MaxAxis\(NDArray \*target, int axis\) \{", "MAXAXIS"),
+                      (r"^NDArray_Maximum\(NDArray \*a, NDArray \*b\) \{", "NB200_MAXIMUM"),
+                      (r"^NDArray_Minimum\(NDArray \*a, NDArray \*b\) \{", "NB200_MINIMUM")],
     "src/ndmath/calculation.c": [(r"^NDArray_ArgMinMaxCommon\(NDArray \*op, int axis, bool keepdims, bool is_argmax\) \{", "ARG")],
-    "src/ndmath/linalg.c": [(r"^NDArray_Matmul\(NDArray \*a, NDArray \*b\) \{", "MATMUL")],
+    "src/ndmath/linalg.c": [(r"^NDArray_Matmul\(NDArray \*a, NDArray \*b\) \{", "MATMUL"),
+                            (r"^NDArray_Dot\(NDArray \*nda, NDArray \*ndb\) \{", "DOT")],
 }
 
 
@@ -37,6 +43,10 @@ def snippet(kind):
         return "    { NDArray *nb200_r = nb200_glue_reduce(array, axis, operation); if (nb200_r != NULL) return nb200_r; }\n"
     if kind == "ARG":
         return ("    if (NDArray_DEVICE(op) == NDARRAY_DEVICE_GPU) return nb200_glue_argminmax(op, axis, keepdims, is_argmax);\n")
+    if kind == "MAXAXIS":
+        return "    if (NDArray_DEVICE(target) == NDARRAY_DEVICE_GPU) return nb200_glue_max_axis(target, axis);\n"
+    if kind == "DOT":
+        return "    { NDArray *nb200_r = nb200_glue_dot(nda, ndb); if (nb200_r != NULL) return nb200_r; }\n"
     if kind == "MATMUL":
         return "    { NDArray *nb200_r = nb200_glue_matmul(a, b); if (nb200_r != NULL) return nb200_r; }\n"
     raise ValueError(kind)
@@ -48,8 +58,21 @@ def main(ref, out):
         lines = text.splitlines(keepends=True)
         done = 0
         res = []
-        # declarations go after the last #include of the file header block
+        # declarations go after the file's header block: the line after the last #include of the first 80 lines, moved past the
+        # #endif of a conditional block (#ifdef HAVE_GD ... in ndarray.c) the include may sit in
         last_inc = max(i for i, l in enumerate(lines[:80]) if l.startswith("#include"))
+        depth = 0
+        for l in lines[:last_inc + 1]:
+            if re.match(r"#\s*if", l):
+                depth += 1
+            elif re.match(r"#\s*endif", l):
+                depth -= 1
+        while depth > 0:
+            last_inc += 1
+            if re.match(r"#\s*if", lines[last_inc]):
+                depth += 1
+            elif re.match(r"#\s*endif", lines[last_inc]):
+                depth -= 1
         for i, l in enumerate(lines):
             res.append(l)
             if i == last_inc:

@@ -243,6 +243,25 @@ void port_matmul_f64(const float *A, const float *B, double *C, long M, long K, 
         }
     }
 }
+/* nd::all — NDArray_All, src/logic.c:25-58.  Intended semantics (the scalar loop, :43-47 / :51-56): 0 as soon as an element equals
+ * 0.0, else 1; NaN is non-zero.  The AVX2 body (:29-40) compares an 8-lane movemask with 0x0F and therefore returns 0 for every
+ * array of >= 8 elements: a bug the port does not restate.  Pinned by tests/logic/001-ndarray-all.phpt (n < 8: scalar loop). */
+int port_all(const float *a, long n) {
+    for (long i = 0; i < n; i++)
+        if (a[i] == 0.0f) return 0;
+    return 1;
+}
+/* nd::allclose — float_allclose, src/logic.c:718-738: false as soon as |a - b| > atol + rtol * |b| (a NaN difference compares
+ * false and passes).  The reference's loop reads element 4i + i * strides[0] / 4 of both arrays (:727-728), i.e. runs out of
+ * bounds for every i > 0; the port applies the predicate to element i.  Pinned by tests/logic/002-ndarray-allclose.phpt. */
+int port_allclose(const float *a, const float *b, long n, float rtol, float atol) {
+    for (long i = 0; i < n; i++) {
+        float diff = fabsf(a[i] - b[i]);
+        float tolerance = atol + rtol * fabsf(b[i]);
+        if (diff > tolerance) return 0;
+    }
+    return 1;
+}
 /* N-D . 1-D: NDArray_Dot linalg.c:378-386 -> cblas_sgemv(RowMajor, NoTrans, rows, cols, 1, A, cols, x, 1, 0, y, 1) */
 void port_gemv(const float *A, const float *x, float *y, long rows, long cols) {
     for (long i = 0; i < rows; i++) {

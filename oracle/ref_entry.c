@@ -336,3 +336,20 @@ long ref_dot(const float *a, const int *ashape, int andim, const float *b, const
     unwrap(na); unwrap(nb);
     return n;
 }
+
+/* ---- logic: NDArray_All (logic.c:25-58) / NDArray_AllClose (logic.c:748-771) -------------------------
+ * Only meaningful on the shapes the reference's own tests use (n < 8 for all; allclose reads out of bounds for larger
+ * inputs, see oracle/port.c): these entries exist to replay tests/logic/00{1,2}-*.phpt against the real object code. */
+#include "logic.h"
+int ref_all(const float *a, const int *shape, int ndim) {
+    NDArray *na = wrap_cpu(a, shape, ndim);
+    int r = (int) NDArray_All(na);
+    unwrap_cpu(na);
+    return r;
+}
+int ref_allclose(const float *a, const float *b, const int *shape, int ndim, float rtol, float atol) {
+    NDArray *na = wrap_cpu(a, shape, ndim), *nb = wrap_cpu(b, shape, ndim);
+    int r = NDArray_AllClose(na, nb, rtol, atol);
+    unwrap_cpu(na); unwrap_cpu(nb);
+    return r;
+}

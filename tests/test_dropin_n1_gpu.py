@@ -79,3 +79,47 @@ def test_matmul_2d_and_stacks():
     assert n <= 2          # lo-split + one batched GEMM launch for the whole stack
     with pytest.raises(RuntimeError, match="Stack of matrices not allowed"):
         oracle.ref.matmul_nd(a3, b3)     # the unpatched reference rejects stacks (linalg.c:240-243)
+
+
+def test_maximum_minimum_max_axis_now_run_on_the_gpu():
+    """ndarray.c:782-784, 853, 896 throw for device arrays in the reference; with the N1 lines they are one kernel each."""
+    r = _rng(6)
+    a = (r.random((48, 40), dtype=np.float32) * 4 - 2).astype(np.float32)
+    for b in ((r.random((48, 40), dtype=np.float32) * 4 - 2).astype(np.float32), (r.random(40, dtype=np.float32) * 4 - 2).astype(np.float32)):
+        for op in ("maximum", "minimum"):
+            got, n = _count(lambda: oracle.dropin_n1.binary(op, a, b))
+            eq(got, oracle.ref.binary(op, a, b))
+            assert n == 1
+    x = r.integers(-50, 50, size=(37, 29)).astype(np.float32)
+    for axis in (0, 1):
+        got, n = _count(lambda: oracle.dropin_n1.reduce_axis("max", x, axis))
+        np.testing.assert_array_equal(got, oracle.ref.reduce_axis("max", x, axis))
+        assert n <= 2
+    if oracle.dropin.available:
+        with pytest.raises(RuntimeError, match="not implemented"):
+            oracle.dropin.binary("maximum", a, a)          # the unpatched host
+
+
+def test_dot_nd_by_1d_covers_every_leading_row():
+    """linalg.c:373-381: the reference's GPU branch hands only shape[ndim-2] rows to the gemv; the N1 line serves all of them."""
+    r = _rng(7)
+    a2, v = r.random((70, 96), dtype=np.float32), r.random(96, dtype=np.float32)
+    assert rel_err(oracle.dropin_n1.dot(a2, v), oracle.ref.dot(a2, v)).max() <= 1e-5
+    a3 = r.random((5, 30, 96), dtype=np.float32)
+    got = oracle.dropin_n1.dot(a3, v)
+    assert got.shape == (5, 30)
+    exp = (a3.astype(np.float64) @ v.astype(np.float64))
+    assert rel_err(got, exp.astype(np.float32)).max() <= 1e-5
+
+
+def test_unary_methods_run_out_of_place_in_one_kernel():
+    """numpower.c:1648-3348 calls NDArrayMathGPU_ElementWise(nda, cuda_float_<op>): the reference copies the operand and runs the op in
+    place on the copy (two passes over the data); libnb200's driver recognises the op pointer and writes a fresh array directly."""
+    x = (_rng(8).random(5000, dtype=np.float32) * 8 + 0.1).astype(np.float32)
+    for op in ("abs", "sqrt", "exp", "log", "sin", "tanh", "floor", "sign", "reciprocal"):
+        got, n = _count(lambda: oracle.dropin_n1.unary(op, x))
+        assert rel_err(got, oracle.ref.unary(op, x)).max() <= 1e-5
+        assert n == 1, (op, n)
+    got, n = _count(lambda: oracle.dropin_n1.unary("clip", x, 1.0, 5.0))
+    eq(got, oracle.ref.unary("clip", x, 1.0, 5.0))
+    assert n == 1

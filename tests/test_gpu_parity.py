@@ -981,3 +981,66 @@ def test_matmul_inf_nan_propagation_and_dynamic_range(nb):
     b3 = np.full((128, 128), 2.0 ** -10, np.float32)
     got3 = nb.nd.matmul(nb.NDArray.array(a3).gpu(), nb.NDArray.array(b3).gpu(), nb.BF16X3).toArray()
     assert np.isfinite(got3).all() and rel_err(got3, ORACLE.matmul(a3, b3)).max() <= RTOL
+
+
+# --------------------------------------------------------------------- nd::all / nd::allclose / transpose (SURVEY §8 f, N2)
+@pytest.mark.parametrize("n", [1, 7, 8, 1000, 4099, (1 << 22) + 3])
+def test_all_and_allclose_vs_oracle_port(nb, n):
+    """Boolean reductions (nb200_all / nb200_allclose) against oracle/port.c, which restates the intended semantics of
+    NDArray_All / float_allclose (logic.c:25-58, 718-738) and is pinned by the reference's two logic phpt tests."""
+    r = _rng(n)
+    x = (r.random(n, dtype=np.float32) + 0.5).astype(np.float32)
+    X = nb.NDArray.array(x).gpu()
+    assert nb.nd.all(X) == oracle.port.all(x) == 1
+    for pos in {0, n // 2, n - 1}:
+        y = x.copy()
+        y[pos] = 0.0
+        assert nb.nd.all(nb.NDArray.array(y).gpu()) == oracle.port.all(y) == 0
+        y[pos] = -0.0
+        assert nb.nd.all(nb.NDArray.array(y).gpu()) == oracle.port.all(y) == 0
+        y[pos] = np.nan
+        assert nb.nd.all(nb.NDArray.array(y).gpu()) == oracle.port.all(y) == 1
+        z = x.copy()
+        z[pos] *= np.float32(1.001)
+        Z = nb.NDArray.array(z).gpu()
+        for rtol, atol in ((1e-5, 1e-8), (1e-2, 0.0), (0.0, 1e-2), (0.0, 0.0)):
+            assert nb.nd.allclose(X, Z, rtol, atol) == bool(oracle.port.allclose(x, z, rtol, atol)), (pos, rtol, atol)
+            assert nb.nd.allclose(Z, X, rtol, atol) == bool(oracle.port.allclose(z, x, rtol, atol))
+        z[pos] = np.nan
+        assert nb.nd.allclose(X, nb.NDArray.array(z).gpu()) == bool(oracle.port.allclose(x, z))
+    assert nb.nd.allclose(X, X) is True
+    if n > 4:   # 4-byte aligned views ($a[i] rows): the scalar path
+        v = nb.NDArray.array(np.stack([x, x])).gpu()
+        assert nb.nd.all(v[1]) == 1
+
+
+def test_all_allclose_golden_and_errors(nb):
+    import json
+    import os
+    for rec in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "logic_vectors.json")))["vectors"]:
+        args = [nb.NDArray.array(np.asarray(a, np.float32)).gpu() for a in rec["args"]]
+        assert int(getattr(nb.nd, rec["op"])(*args)) == rec["expect"], rec
+    with pytest.raises(RuntimeError, match="Shape mismatch"):
+        nb.nd.allclose(np.zeros((2, 3), np.float32), np.zeros((3, 2), np.float32))
+    assert nb.nd.all(np.zeros((0,), np.float32)) == 1
+
+
+@pytest.mark.parametrize("rc", [(1, 1), (3, 5), (32, 32), (33, 65), (257, 1031), (1000, 1), (1, 777), (2048, 4100)])
+def test_transpose2d_and_the_legacy_in_place_call(nb, rc):
+    """nb200_transpose2d and cuda_float_transpose (cuda_math.h:77) as the host calls it: d_in == d_out (manipulation.c:124),
+    (width, height) = (cols, rows).  Bit-exact (index work)."""
+    import ctypes as C
+    lib = nb.lib()
+    rows, cols = rc
+    x = _rng(rows * 31 + cols).random((rows, cols), dtype=np.float32)
+    dx, do = _dev(nb, x), _dev(nb, np.zeros((cols, rows), np.float32))
+    assert lib.nb200_transpose2d(do, dx, rows, cols) == 0, lib.nb200_last_error()
+    np.testing.assert_array_equal(_fetch(nb, do, (cols, rows)), x.T)
+    assert lib.nb200_transpose2d(dx, dx, rows, cols) != 0          # out == in is refused by the 64-bit entry point
+    f = lib.cuda_float_transpose                                    # legacy symbol of the same library (include/nb200_legacy.h)
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    f.restype = None
+    f(0, 0, dx, dx, cols, rows)                                     # in place through the legacy symbol
+    np.testing.assert_array_equal(_fetch(nb, dx, (cols, rows)), x.T)
+    for p in (dx, do):
+        lib.nb200_free(p)

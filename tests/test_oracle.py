@@ -155,3 +155,44 @@ def test_port_vs_ref_comparisons(op):
         # nda/ndb instead of a_broad/b_broad) and read out of bounds when shapes differ: broadcast parity is
         # only defined for the other four predicates.
         np.testing.assert_array_equal(oracle.port.binary(op, a.reshape(17, 59), b[:59]), oracle.ref.binary(op, a.reshape(17, 59), b[:59]))
+
+
+# ------------------------------------------------------------------ nd::all / nd::allclose (SURVEY §8 f, N2)
+def _logic_vectors():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "logic_vectors.json")))["vectors"]
+
+
+@pytest.mark.parametrize("rec", _logic_vectors(), ids=lambda r: f"{r['op']}-{r['expect']}")
+def test_all_allclose_golden_vectors(rec):
+    """tests/logic/001-ndarray-all.phpt and 002-ndarray-allclose.phpt: the port and (where built) the reference's object code."""
+    args = [np.asarray(a, np.float32) for a in rec["args"]]
+    fn = getattr(oracle.port, rec["op"])
+    assert fn(*args) == rec["expect"]
+    if oracle.ref.available and hasattr(oracle.ref.lib, "ref_all"):
+        if len(args) == 2 and np.array_equal(args[0], args[1]):
+            args[1] = args[0]      # the phpt passes the SAME object twice: the reference's out-of-bounds reads then see equal memory
+        assert getattr(oracle.ref, rec["op"])(*args) == rec["expect"]
+
+
+def test_all_allclose_intended_semantics_where_the_reference_loops_are_broken():
+    """oracle/port.c documents the two reference bugs; this pins what the port (and the kernels checked against it) do instead."""
+    x = np.arange(1, 41, dtype=np.float32)
+    assert oracle.port.all(x) == 1                                  # the reference's AVX2 body answers 0 for any n >= 8
+    if oracle.ref.available and hasattr(oracle.ref.lib, "ref_all"):
+        assert oracle.ref.all(x) == 0                               # (documented bug: mask compared with 0x0F, logic.c:33)
+        assert oracle.ref.all(x[:7]) == 1                           # scalar loop: correct
+    x[17] = 0.0
+    assert oracle.port.all(x) == 0
+    x[17] = np.nan
+    assert oracle.port.all(x) == 1                                  # NaN is non-zero (scalar loop rule, numpy's rule)
+    a = np.linspace(1, 2, 33, dtype=np.float32)
+    b = a.copy()
+    b[20] += np.float32(1e-3)
+    assert oracle.port.allclose(a, a) == 1 and oracle.port.allclose(a, b) == 0
+    assert oracle.port.allclose(a, b, rtol=1e-2) == 1 and oracle.port.allclose(a, b, rtol=0.0, atol=2e-3) == 1
+    b[20] = np.nan
+    assert oracle.port.allclose(a, b) == 1                          # `diff > tolerance` is false for NaN (logic.c:732)
+    with pytest.raises(RuntimeError, match="Shape mismatch"):
+        oracle.port.allclose(a, a[:5])
