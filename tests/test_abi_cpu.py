@@ -76,3 +76,25 @@ def test_gemm_auto_resolves_to_the_guaranteed_mode_by_default(monkeypatch):
     assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 16) == nb.TF32X3
     for mode in (nb.TF32X3, nb.TF32X1, nb.BF16X3, nb.FP16X3):
         assert lib.nb200_gemm_resolve_precision(mode, 4096) == mode
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("NB200_REFERENCE_DIR", "/root/reference")), reason="reference tree absent")
+def test_with_b200_build_patch_applies_to_the_reference_build_files(tmp_path):
+    """integration/b200_build_patch.py: the --with-b200 switch lands after PHP_ARG_WITH(cuda) (config.m4:7-8), gpu_alloc.c leaves the
+    source list in favour of the glue file, and Makefile.frag gains build-b200 / install-b200 next to install-cuda.  (The rule
+    itself is exercised by oracle/build_dropin_n1.sh, which builds the Level-1 drop-in library through it.)"""
+    import subprocess
+    import sys
+    ref = os.environ.get("NB200_REFERENCE_DIR", "/root/reference")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "integration", "b200_build_patch.py"), ref, str(tmp_path)], stdout=subprocess.DEVNULL)
+    m4 = (tmp_path / "config.m4").read_text()
+    assert m4.index("PHP_ARG_WITH(cuda") < m4.index("PHP_ARG_WITH(b200") < m4.index('if test "$PHP_CUDA" != "no"')
+    assert "PHP_ADD_LIBRARY_WITH_PATH(nb200" in m4 and "AC_DEFINE(HAVE_CUBLAS,1" in m4 and "PHP_CUDA=no" in m4
+    assert "src/gpu_alloc.c \\" not in m4 and "$NDARRAY_GPU_ALLOC_SRC $NDARRAY_NB200_GLUE_SRC \\" in m4
+    frag = (tmp_path / "Makefile.frag").read_text()
+    assert frag.index("install-cuda:") < frag.index("build-b200:") < frag.index("install-b200: build-b200")
+    assert "-lnb200" in frag and "cuda_math.cu" not in frag[frag.index("build-b200:"):]
+    out = subprocess.run(["make", "-n", "-f", str(tmp_path / "Makefile.frag"), "build-b200", "TARGET_SIZE=64", "NB200_HOST_SRCS=src/types.c"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and "-DHAVE_CUBLAS=1" in out.stdout and "-lnb200" in out.stdout, out.stderr
