@@ -43,8 +43,8 @@ MODES = {
     2: ("bf16x3", "bf16x3 (fp32 in/out, operands split into 2 bf16 parts, 3 MMAs, fp32 accumulate)", "bf16"),
     4: ("fp16x3", "fp16x3 (fp32 in/out, row/column-scaled operands split into 2 half parts, 3 kind::f16 MMAs, fp32 accumulate; "
                   "sparse repair / TF32x3 fallback decided on the device)", "bf16"),
-    5: ("h16b16x3", "h16b16x3 (fp32 in/out, row/column-scaled operands split into a half hi part and a bfloat16 lo part, 3 kind::f16 MMAs "
-                    "(mixed-format cross products), fp32 accumulate; sparse repair / TF32x3 fallback decided on the device)", "bf16"),
+    5: ("fp16x3u", "fp16x3u (fp32 in/out, row/column-scaled operands split into 2 half parts with the lo part unscaled, 3 kind::f16 MMAs into "
+                   "one accumulator per chunk (merged 256x256 tile), fp32 accumulate; sparse repair / TF32x3 fallback decided on the device)", "bf16"),
 }
 METRIC = "nd::matmul useful TFLOP/s (fp32 in/out)"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
@@ -374,14 +374,14 @@ def run_single(args):
     ms = B.time_steps(lambda: mm(GEMM_AUTO), args.steps, 0)
     launches_timed = lib.nb200_launch_count() - launches0
     mode_ms = {auto_name: ms}
-    for name, prec in (("tf32x3", 0), ("bf16x3", 2), ("fp16x3", 4), ("h16b16x3", 5), ("tf32x1", 1)):
+    for name, prec in (("tf32x3", 0), ("bf16x3", 2), ("fp16x3", 4), ("fp16x3u", 5), ("tf32x1", 1)):
         if name not in mode_ms:
             mode_ms[name] = B.time_steps(lambda: mm(prec), args.steps, args.warmup)
     # accuracy of each mode against an fp64 product of 64 sampled rows (reported, the parity tests assert it)
     rows = torch.randperm(n, device="cuda", generator=g)[:64]
     truth = a[rows].double() @ b.double()
     mode_err = {}
-    for name, prec in (("tf32x3", 0), ("bf16x3", 2), ("fp16x3", 4), ("h16b16x3", 5), ("tf32x1", 1)):
+    for name, prec in (("tf32x3", 0), ("bf16x3", 2), ("fp16x3", 4), ("fp16x3u", 5), ("tf32x1", 1)):
         mm(prec)
         mode_err[name] = float(((c[rows].double() - truth) / truth).abs().max())
     del truth
@@ -522,8 +522,8 @@ def run_single(args):
                    "error: fine on random data, up to ~3e-5 on coherent inputs)", bf16_peak),
         "fp16x3": ("NB200_GEMM_FP16X3: half parts of row/column-scaled operands (22-bit elements inside a 2^28 window, "
                    "guaranteed bound), one persistent pre-pass launch, PDL chain pre-pass -> GEMM -> repair/fallback", bf16_peak),
-        "h16b16x3": ("NB200_GEMM_H16B16X3: FP16x3 with unscaled bfloat16 lo parts (19-bit elements, per-product bound 2^-18 + 2^-22 = 4.1e-6 for "
-                     "every input), one accumulator per 256-long chunk -> the merged 256x256 tile", bf16_peak),
+        "fp16x3u": ("NB200_GEMM_FP16X3U: FP16x3 with unscaled lo parts (split error max(2^-22 |a'|, 2^-25); per-product bound 2^-18 + 2^-22 = 4.1e-6 for "
+                    "every input inside the 2^-20 window), one accumulator per 256-long chunk -> the merged 256x256 tile", bf16_peak),
     }
     modes = {}
     for name, (note, pk) in mode_notes.items():
@@ -534,7 +534,7 @@ def run_single(args):
                        "frac_tf32_peak": flops / mode_ms["tf32x1"] / 1e9 / tf32_peak, "max_rel_err_vs_fp64": mode_err["tf32x1"],
                        "note": "single-pass TF32 fast mode (not a parity mode)"}
     gemm_kernels = {"fp16x3": [("prep16_coop_kernel",), ("sgemm_tf32_kernel", "GemmCfg<2, 128, 3, 0, 1, 0, 1>")],
-                    "h16b16x3": [("prep16_coop_kernel",), ("sgemm_tf32_kernel", "GemmCfg<2, 256, 3, 0, 1, 1, 1, 1>")],
+                    "fp16x3u": [("prep16_coop_kernel",), ("sgemm_tf32_kernel", "GemmCfg<2, 256, 3, 0, 1, 1, 1, 1>")],
                     "tf32x3": [("split_tf32_kernel",), ("sgemm_tf32_kernel", "GemmCfg<2, 128, 3>")],
                     "bf16x3": [("split_bf16_flat_kernel",), ("sgemm_tf32_kernel", "GemmCfg<2, 256, 3, 0, 1, 1>")]}[auto_name]
     tb, tsrc, pipe_active = ncu_lookup(traffic, *gemm_kernels)
@@ -574,7 +574,7 @@ def run_single(args):
         "e2e": {"value": flops / ms_e2e / 1e9, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": ms_e2e, "steps": e2e_steps, "api": "nb200_sgemm_host (pinned host buffers, pipelined H2D/compute/D2H)",
                 "max_rel_diff_vs_resident": e2e_err, "pcie_measured": pcie,
-                "mode": "NB200_GEMM_AUTO (" + ("the host pipeline keeps the TF32x3 kernels: PCIe-bound, per-row-block splits" if auto_name in ("fp16x3", "h16b16x3") else auto_name) + ")",
+                "mode": "NB200_GEMM_AUTO (" + ("the host pipeline keeps the TF32x3 kernels: PCIe-bound, per-row-block splits" if auto_name in ("fp16x3", "fp16x3u") else auto_name) + ")",
                 "pcie_bound_ms": 2 * nbytes / pcie["h2d_GBps"] / 1e6,
                 "pcie_bound_duplex_ms": nbytes / pcie["h2d_GBps"] / 1e6 + nbytes / pcie["duplex_each_GBps"] / 1e6,
                 "note": "H2D of A and B (128 MiB) is the floor; the D2H of C overlaps the second half of it, where the link runs at its measured "

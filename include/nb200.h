@@ -90,10 +90,10 @@ enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
 
 /* nd::matmul precision.
  * AUTO (what nd::matmul passes): the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every
- *   input - a scaled half-precision split (FP16X3 or H16B16X3, see nb200_gemm_resolve_precision) for K >= 128,
+ *   input - a scaled half-precision split (FP16X3 or FP16X3U, see nb200_gemm_resolve_precision) for K >= 128,
  *   TF32X3 below (pre-pass not worth it) and for shapes too small for the tensor path.
  * TF32X3: error-compensated 3-pass TF32 on the tcgen05 tensor pipe; guaranteed bound ~3*2^-22 per product
- *   (+ chunked round-to-nearest accumulation).  Also what the FP16X3 / H16B16X3 device-side fallback runs.
+ *   (+ chunked round-to-nearest accumulation).  Also what the FP16X3 / FP16X3U device-side fallback runs.
  * TF32X1: single pass, fast mode (~7e-4); not a parity mode.
  * BF16X3: operands split into two bfloat16 parts each, three kind::f16 MMAs per k-step at twice the TF32 rate.
  *   Statistical accuracy only: per-product error up to 2^-16 + 2*2^-17, zero-mean - measured 1.2-2.5e-6 on random
@@ -104,13 +104,14 @@ enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
  *   that window ON THE DEVICE: a few elements outside it are taken out of the GEMM and added back by a sparse fp32
  *   repair kernel; if there are too many, the gated TF32X3 fallback enqueued with the call produces the result
  *   instead (bit-identical to a TF32X3 call).  Any alignment / leading dimension (the pre-pass repacks).
- * H16B16X3: FP16X3 with the lo parts stored as UNSCALED bfloat16 (hi: IEEE half, 11 bits; lo: bfloat16, 8 bits; split
- *   error <= 2^-19 per element, <= 2^-18 + 2^-22 per product = 4.1e-6 worst case, every input).  All three products
- *   then carry one scale, so a whole 256-long k-chunk accumulates into ONE TMEM accumulator and the 256x256 tile of
- *   BF16X3 applies: ~8 % less tensor time than FP16X3's 256x128 tile, and a 2x shorter truncating accumulation (smaller
- *   systematic bias).  Same window rule, repair and fallback as FP16X3. */
+ * FP16X3U: FP16X3 with the lo parts stored UNSCALED (no 2^11 factor).  All three products then carry one scale, so a whole
+ *   256-long k-chunk accumulates into ONE TMEM accumulator and the 256x256 tile of BF16X3 applies: ~8 % less tensor time than
+ *   FP16X3's 256x128 tile and a 2x shorter truncating accumulation (smaller systematic bias).  Price: lo parts below 2^-14 are
+ *   subnormal halves, so the split error per element is max(2^-22 |a'|, 2^-25) - still 2^-22 relative within 2^-17 of the row /
+ *   column maximum, 2^-19 at the edge of the (narrower) window, 2^-20 .. 2^-21 of the maximum; per product <= 2^-18 + 2^-22 =
+ *   4.1e-6 worst case, every input.  Elements outside the window: same sparse repair / gated TF32X3 fallback as FP16X3. */
 enum nb200_gemm_precision { NB200_GEMM_TF32X3 = 0, NB200_GEMM_TF32X1 = 1, NB200_GEMM_BF16X3 = 2, NB200_GEMM_AUTO = 3,
-                            NB200_GEMM_FP16X3 = 4, NB200_GEMM_H16B16X3 = 5 };
+                            NB200_GEMM_FP16X3 = 4, NB200_GEMM_FP16X3U = 5 };
 
 /* ---- context / device -------------------------------------------------------- */
 /* Replaces the process-global cudaSetDevice of NDArray::setDevice (numpower.c:615-635). */

@@ -4,4 +4,4 @@ Layout: csrc/ (hand-written CUDA kernels + the C-ABI of include/nb200.h, the leg
 the C++ host mirror), _lib.py (ctypes loader, no fallback), ndarray.py (NDArray / nd:: surface).
 """
 from ._lib import BackendError, BackendMissing, lib  # noqa: F401
-from .ndarray import NDArray, nd, GoldenBackend, TF32X1, TF32X3, BF16X3, GEMM_AUTO, FP16X3, H16B16X3, ORDER_TREE, ORDER_SEQUENTIAL  # noqa: F401
+from .ndarray import NDArray, nd, GoldenBackend, TF32X1, TF32X3, BF16X3, GEMM_AUTO, FP16X3, FP16X3U, ORDER_TREE, ORDER_SEQUENTIAL  # noqa: F401

@@ -53,9 +53,9 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
                                 int precision) {
     NB_READY();
     if (!C_host || !A_host || !B_host || M < 0 || N < 0 || K < 0) return set_error(NB200_EINVAL, "nb200_sgemm_host: bad argument");
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_H16B16X3) return set_error(NB200_EINVAL, "unknown precision %d", precision);
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3U) return set_error(NB200_EINVAL, "unknown precision %d", precision);
     precision = gemm_resolve_precision(precision, K);
-    if (precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_H16B16X3) precision = NB200_GEMM_TF32X3;   // this path is PCIe-bound; it keeps the two-kernel TF32x3 pipeline
+    if (precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_FP16X3U) precision = NB200_GEMM_TF32X3;   // this path is PCIe-bound; it keeps the two-kernel TF32x3 pipeline
     if (M == 0 || N == 0) return NB200_OK;
     Ctx &c = ctx();
     Pipe &P = g_pipes[c.device];
@@ -179,7 +179,7 @@ extern "C" int nb200_sgemm_batched_host(float *C_host, const float *A_host, cons
                                         int precision) {
     NB_READY();
     if (!C_host || !A_host || !B_host || batch < 0 || M < 0 || N < 0 || K < 0) return set_error(NB200_EINVAL, "nb200_sgemm_batched_host: bad argument");
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_H16B16X3) return set_error(NB200_EINVAL, "unknown precision %d", precision);
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3U) return set_error(NB200_EINVAL, "unknown precision %d", precision);
     if (batch == 0 || M == 0 || N == 0) return NB200_OK;
     Ctx &c = ctx();
     Pipe &P = g_pipes[c.device];

@@ -39,13 +39,16 @@ namespace nb200 {
 // ------------------------------------------------------------------ configuration
 template <int CG_, int BN_, int PASSES_, bool INK_ = false, bool BF16_ = false, bool MERGED_ = false, bool SCALED_ = false, bool MIXLO_ = false>
 struct GemmCfg {
-    // MIXLO (H16B16x3 = SCALED with bfloat16 lo parts): hi = rn_f16(a') as in FP16x3, lo = rn_bf16(a' - hi) UNSCALED - bfloat16 has
-    // fp32's exponent range, so the lo parts need no 2^11 factor and all three products of a k-block carry the same scale.  The
-    // cross products multiply an f16 operand with a bf16 one: tcgen05.mma.kind::f16 takes the A and B formats from separate fields
-    // of the instruction descriptor.  One accumulator per chunk => the MERGED 256x256 tile works exactly as for BF16x3 (K = 256
-    // chunks, no scale-input-d).  Split error per element <= 2^-11 * 2^-8 = 2^-19 (FP16x3: 2^-22; BF16x3: 2^-16).
+    // MIXLO (FP16x3U = SCALED with UNSCALED lo parts): hi = rn_f16(a') as in FP16x3, lo = rn_f16(a' - hi) without the 2^11 factor, so
+    // all three products of a k-block carry the same scale and accumulate into ONE accumulator per chunk => the MERGED 256x256 tile
+    // works exactly as for BF16x3 (K = 256 chunks, no scale-input-d).  Price: a lo part below 2^-14 is a subnormal half (absolute
+    // error 2^-25), so the split error per element is max(2^-22 |a'|, 2^-25): 2^-22 relative for elements within 2^-17 of the row /
+    // column maximum, growing to 2^-19 at |a'| = 2^-6; elements below 2^-6 (2^-20 .. 2^-21 of the maximum instead of FP16x3's 2^-28)
+    // take the sparse-repair path.
+    // [Measured on B200: tcgen05.mma.kind::f16 with DIFFERENT A and B formats (f16 x bf16) raises "illegal instruction", although the
+    //  instruction descriptor has separate format fields - a bfloat16 lo part next to a half hi part is therefore not an option.]
     static constexpr bool MIXLO = MIXLO_;
-    static_assert(!MIXLO_ || SCALED_, "bf16 lo parts belong to the scaled half-precision mode");
+    static_assert(!MIXLO_ || SCALED_, "unscaled lo parts belong to the scaled half-precision mode");
     // SCALED (FP16x3): the 16-bit operand parts are IEEE half (11-bit significands, TF32x3-class split error) of
     // A scaled per row and B scaled per column by powers of two (so that every row / column uses the top of fp16's
     // exponent range); the epilogue undoes the scaling with one exact scalbnf per output element.
@@ -742,7 +745,6 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader) {
             constexpr uint32_t FMT = Cfg::SCALED ? 0u : (Cfg::BF16 ? 1u : 2u);   // operand format: f16 / bf16 (kind::f16), tf32
-            constexpr uint32_t FMT_LO = Cfg::MIXLO ? 1u : FMT;                   // format of the lo parts (MIXLO: bf16 next to f16 hi parts)
             constexpr uint32_t BL = Cfg::BF16 ? LAYOUT_SW128 : LAYOUT_SW128_BASE32B;
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, tile_phase = 0;
@@ -777,9 +779,6 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     // flags such calls; the cross terms then use (a_lo, b_lo) — finite, ~2^-22 of the result — so the
                     // call degrades to TF32x1 accuracy but keeps IEEE inf/NaN propagation identical to the reference.
                     const int hi_part = (!Cfg::INK && *reinterpret_cast<const volatile int *>(p.nonfinite) == p.nonfinite_gen) ? 1 : 0;
-                    // per-product instruction descriptors (they differ only when the lo parts have their own format)
-                    const uint32_t idesc_lh = make_idesc(BM * CG, nn, FMT_LO, hi_part ? FMT_LO : FMT);
-                    const uint32_t idesc_hl = make_idesc(BM * CG, nn, hi_part ? FMT_LO : FMT, FMT_LO);
                     const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
                     for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
                         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.debug, 0x300u + acc);
@@ -797,13 +796,13 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, 1) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, hi_part) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc_lh, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, ((Cfg::MERGED ? kb - kb0 : kb) | k) != 0 ? 1u : 0u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
                                     const uint64_t da = make_smem_desc(a_smem(stage, hi_part) + k * 32, 16, 1024, LAYOUT_SW128);
                                     const uint64_t db = make_smem_desc(b_smem(stage, 1) + k * Cfg::B_KSTEP, Cfg::B_CHUNK_BYTES, Cfg::B_SBO, BL);
-                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc_hl, 1u);
+                                    umma_tf32<CG, Cfg::BF16>(d_x, da, db, idesc, 1u);
                                 }
 #pragma unroll
                                 for (int k = 0; k < BK / Cfg::UMMA_K; k++) {
@@ -1124,7 +1123,8 @@ struct FixList {
     unsigned int *count;                   // device counter (reset by the host before the operand is split)
     int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
 };
-// MIX: the lo part is an UNSCALED bfloat16, lo = rn_bf16(a' - hi) (GemmCfg::MIXLO): remainder <= 2^-19 |a'|, same window rule.
+// MIX (GemmCfg::MIXLO): the lo part is stored UNSCALED, lo = rn_f16(a' - hi): remainder <= max(2^-22 |a'|, 2^-25), and the window
+// closes at |a'| = 2^-6 (remainder <= 2^-19 |a'|) instead of 2^-14.
 template <bool MIX>
 __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, unsigned short &l, int *nonfinite, int gen,
                                           const FixList &fix, int64_t row, int64_t col) {
@@ -1138,9 +1138,8 @@ __device__ __forceinline__ void split_f16(float a, int e, unsigned short &h, uns
     const float x = scale_pow2(a, e);
     const __half hh = __float2half_rn(x);
     h = __half_as_ushort(hh);
-    if constexpr (MIX) l = __bfloat16_as_ushort(__float2bfloat16_rn(x - __half2float(hh)));
-    else l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * 2048.0f));
-    if (ab != 0u && fabsf(x) < 6.103515625e-05f) {  // below 2^-14: hi would be a subnormal half -> repair record
+    l = __half_as_ushort(__float2half_rn((x - __half2float(hh)) * (MIX ? 1.0f : 2048.0f)));
+    if (ab != 0u && fabsf(x) < (MIX ? 0.015625f : 6.103515625e-05f)) {  // below 2^-14 (MIX: 2^-6): hi (MIX: lo) would lose bits as a subnormal half -> repair record
         // The element leaves the GEMM entirely (hi = lo = 0) and is carried by the record in full fp32: a lo-only
         // representation would multiply it with the partner's hi part alone, i.e. with 11 bits (measured 4.7e-4).
         h = 0;
@@ -1212,10 +1211,12 @@ __device__ __noinline__ uint4 split4_careful(float4 v, int e0, int e1, int e2, i
     return make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
                       (uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
 }
-// not in [2^-14, inf) and not zero: the element needs the careful path
+// not in [2^-14, inf) (MIX: [2^-6, inf)) and not zero: the element needs the careful path
+template <bool MIX>
 __device__ __forceinline__ bool outside_window(float x) {
     const unsigned int b = __float_as_uint(x) & 0x7FFFFFFFu;
-    return (b - 0x38800000u) >= 0x47000000u && b != 0u;
+    constexpr unsigned int LOW = MIX ? 0x3C800000u : 0x38800000u;
+    return (b - LOW) >= (0x7F800000u - LOW) && b != 0u;
 }
 template <bool MIX>
 __device__ __forceinline__ bool split4_fast(const float4 &v, const Pow2Pair &s0, const Pow2Pair &s1, const Pow2Pair &s2, const Pow2Pair &s3,
@@ -1224,15 +1225,11 @@ __device__ __forceinline__ bool split4_fast(const float4 &v, const Pow2Pair &s0,
     const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
     hi = make_uint2(*reinterpret_cast<const uint32_t *>(&h01), *reinterpret_cast<const uint32_t *>(&h23));
-    if constexpr (MIX) {
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2bfloat162_rn(x2 - f23.x, x3 - f23.y);
-        lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
-    } else {
-        const __half2 l01 = __floats2half2_rn((x0 - f01.x) * 2048.0f, (x1 - f01.y) * 2048.0f);
-        const __half2 l23 = __floats2half2_rn((x2 - f23.x) * 2048.0f, (x3 - f23.y) * 2048.0f);
-        lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
-    }
-    return outside_window(x0) | outside_window(x1) | outside_window(x2) | outside_window(x3);
+    constexpr float LS = MIX ? 1.0f : 2048.0f;   // the lo parts are stored times 2^11 unless MIX
+    const __half2 l01 = __floats2half2_rn((x0 - f01.x) * LS, (x1 - f01.y) * LS);
+    const __half2 l23 = __floats2half2_rn((x2 - f23.x) * LS, (x3 - f23.y) * LS);
+    lo = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+    return outside_window<MIX>(x0) | outside_window<MIX>(x1) | outside_window<MIX>(x2) | outside_window<MIX>(x3);
 }
 
 // ---- The flat FP16x3 pre-pass (contiguous operands, cols % 8 == 0, 16-byte aligned: output index == input index): ONE persistent
@@ -1993,7 +1990,7 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
     { const int rcf = gemm_reset_nonfinite(); if (rcf != NB200_OK) return rcf; }
     const int v = gemm_variant();
     const int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
-    // H16B16x3 (mix): one accumulator per chunk, so the merged 256x256 tile is chosen exactly as for BF16x3 (wave quantisation)
+    // FP16x3U (mix): one accumulator per chunk, so the merged 256x256 tile is chosen exactly as for BF16x3 (wave quantisation)
     const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? (mix ? bf16_pair_bn(chunk, g.M, g.N) : fp16_pair_bn(chunk, g.M, g.N)) : 128);
     const bool merged = cg == 2 && bn == 256;
     // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
@@ -2121,7 +2118,7 @@ int gemm_resolve_precision(int precision, int64_t K) {
     static const char *mode = getenv("NB200_GEMM_AUTO_MODE");
     static const int fast = !mode ? NB200_GEMM_FP16X3 : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
                                   : strcmp(mode, "tf32x3") == 0 ? NB200_GEMM_TF32X3
-                                  : strcmp(mode, "h16b16x3") == 0 ? NB200_GEMM_H16B16X3 : NB200_GEMM_FP16X3;
+                                  : strcmp(mode, "fp16x3u") == 0 ? NB200_GEMM_FP16X3U : NB200_GEMM_FP16X3;
     return K >= 128 ? fast : NB200_GEMM_TF32X3;
 }
 
@@ -2139,11 +2136,11 @@ static int gemm_impl(GemmArgs g, int precision) {
     static const bool force_simt = getenv("NB200_GEMM_FORCE_SIMT") != nullptr;   // debugging switch, read once
     if (precision == NB200_GEMM_BF16X3 && bf16_ok && !force_simt) return gemm_bf16x3(g);
     if (precision == NB200_GEMM_FP16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g, false);
-    if (precision == NB200_GEMM_H16B16X3 && bf16_ok && !force_simt) return gemm_fp16x3(g, true);
+    if (precision == NB200_GEMM_FP16X3U && bf16_ok && !force_simt) return gemm_fp16x3(g, true);
     // TF32X3 asked for on operands the TF32 path cannot read (4-byte aligned views, ld % 4 != 0): the FP16x3 pre-pass
     // repacks them, same class of guaranteed bound, so they stay on the tensor pipe instead of the fp32 SIMT kernel
     if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g, false);
-    if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_H16B16X3) precision = NB200_GEMM_TF32X3;   // tiny shapes
+    if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_FP16X3U) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
         if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
@@ -2228,7 +2225,7 @@ extern "C" int nb200_sgemm_batched(float *C, const float *A, const float *B, int
     NB_READY();
     if (!C || !A || !B || batch < 0 || M < 0 || N < 0 || K < 0 || strideA < 0 || strideB < 0 || strideC < 0)
         return set_error(NB200_EINVAL, "nb200_sgemm_batched: bad argument");
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_H16B16X3)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3U)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, batch, M, N, K, K, N, N, strideA, strideB, strideC};
     return gemm_impl(g, precision);
@@ -2240,7 +2237,7 @@ extern "C" int nb200_sgemm(float *C, const float *A, const float *B, int64_t M, 
     if (!C || !A || !B || M < 0 || N < 0 || K < 0 || lda < K || ldb < N || ldc < N)
         return set_error(NB200_EINVAL, "Shape mismatch for matmul (M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
                          (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
-    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_H16B16X3)
+    if (precision < NB200_GEMM_TF32X3 || precision > NB200_GEMM_FP16X3U)
         return set_error(NB200_EINVAL, "nb200_sgemm: unknown precision %d", precision);
     GemmArgs g{C, A, B, nullptr, nullptr, 1, M, N, K, lda, ldb, ldc, 0, 0, 0};
     return gemm_impl(g, precision);
@@ -2253,7 +2250,7 @@ extern "C" int nb200_sgemm_workspace_bytes(int64_t batch, int64_t M, int64_t N, 
     if (precision == NB200_GEMM_TF32X1) { *bytes = 0; return NB200_OK; }
     precision = gemm_resolve_precision(precision, K);
     int64_t per = precision == NB200_GEMM_BF16X3 ? 4 * (M * round8(K) + K * round8(N)) + 1024
-                : (precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_H16B16X3) ? 4 * (M * round8(K) + K * round8(N)) + 4 * round4(M) + 2 * ((16 + 4 * round4(N) + 255) & ~int64_t(255)) + 4 * (round4(M * K) + round4(K * N)) + 2 * (int64_t)FIX_CAP * 16 + 1024
+                : (precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_FP16X3U) ? 4 * (M * round8(K) + K * round8(N)) + 4 * round4(M) + 2 * ((16 + 4 * round4(N) + 255) & ~int64_t(255)) + 4 * (round4(M * K) + round4(K * N)) + 2 * (int64_t)FIX_CAP * 16 + 1024
                                                  : 4 * (round4(M * K) + round4(K * N));
     int64_t total = per * batch;
     const int64_t budget = gemm_ws_budget();

@@ -23,7 +23,7 @@ UN = {
     "positive": 31, "sign": 32, "reciprocal": 33, "rsqrt": 34, "clip": 35, "round": 36, "square": 37,
 }
 RED = {"sum": 0, "prod": 1, "min": 2, "max": 3}
-TF32X3, TF32X1, BF16X3, GEMM_AUTO, FP16X3, H16B16X3 = 0, 1, 2, 3, 4, 5   # include/nb200.h nb200_gemm_precision
+TF32X3, TF32X1, BF16X3, GEMM_AUTO, FP16X3, FP16X3U = 0, 1, 2, 3, 4, 5   # include/nb200.h nb200_gemm_precision
 ORDER_TREE, ORDER_SEQUENTIAL = 0, 1
 
 

@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
-PNAME = {0: "x3", 1: "x1", 2: "bf16x3", 3: "auto", 4: "fp16x3", 5: "h16b16x3"}
+PNAME = {0: "x3", 1: "x1", 2: "bf16x3", 3: "auto", 4: "fp16x3", 5: "fp16x3u"}
 VARIANTS = {"auto": 0, "cg1_bn256": 384, "cg1_bn128": 320, "cg2_bn256": 640, "cg2_bn128": 576}
 
 

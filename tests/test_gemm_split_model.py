@@ -279,69 +279,98 @@ def test_fp16x3_merged_scale_input_d_matches_the_split_model(k):
     assert (np.abs(fp16x3_merged_model(a, b) - exact) / exact).max() <= 3 * 2.0 ** -22 + (k / 64 + 2) * 2.0 ** -24
 
 
-# ------------------------------------------------------------------ H16B16x3: half hi parts + UNSCALED bfloat16 lo parts
-def split_h16b16_scaled(x, e):
-    """split_f16<MIX = true>() in sgemm_tcgen05.cu: hi = rn_f16(x * 2^e), lo = rn_bf16(x * 2^e - hi), no 2^11 factor."""
+# ------------------------------------------------------------------ FP16x3U: half hi parts + UNSCALED half lo parts
+def split_f16u_scaled(x, e):
+    """split_f16<MIX = true>() in sgemm_tcgen05.cu: hi = rn_f16(x * 2^e), lo = rn_f16(x * 2^e - hi) with NO 2^11 factor (a lo part
+    below 2^-14 is a subnormal half); the window closes at 2^-6 instead of 2^-14."""
     xs = np.ldexp(x.astype(np.float64), e)
     hi = xs.astype(np.float32).astype(np.float16)
-    lo = rn_bf16((xs - hi.astype(np.float64)).astype(np.float32))      # xs - hi is exact in fp32
-    eligible = bool(((xs == 0) | (np.abs(xs) >= 2.0 ** -14)).all())
+    lo = (xs - hi.astype(np.float64)).astype(np.float32).astype(np.float16)      # xs - hi is exact in fp32
+    eligible = bool(((xs == 0) | (np.abs(xs) >= 2.0 ** -6)).all())
     return hi.astype(np.float64), lo.astype(np.float64), eligible
 
 
-def h16b16x3_model(a, b):
+def fp16x3u_model(a, b):
     ea = scale_exp(np.abs(a).max(axis=1))[:, None]
     eb = scale_exp(np.abs(b).max(axis=0))[None, :]
-    ah, al, ok_a = split_h16b16_scaled(a, ea)
-    bh, bl, ok_b = split_h16b16_scaled(b, eb)
+    ah, al, ok_a = split_f16u_scaled(a, ea)
+    bh, bl, ok_b = split_f16u_scaled(b, eb)
     if not (ok_a and ok_b):
         return None
     return np.ldexp(ah @ bh + ah @ bl + al @ bh, -(ea + eb))
 
 
-def test_h16b16_split_remainder_bound():
-    """11-bit hi + 8-bit lo: |lo| <= 2^-11 |x|, remainder <= 2^-19 |x| for every element inside the window."""
+def test_fp16u_split_remainder_bound():
+    """remainder <= max(2^-22 |x'|, 2^-25): 2^-22 relative down to 2^-3 (2^-17 of the maximum's binade), 2^-19 at the window edge 2^-6."""
     r = np.random.default_rng(21)
-    x = ((r.random(1 << 16, dtype=np.float32) + 0.5) * np.exp2(r.integers(-27, 1, 1 << 16)).astype(np.float32)).astype(np.float32)
+    x = ((r.random(1 << 16, dtype=np.float32) + 0.5) * np.exp2(r.integers(-19, 1, 1 << 16)).astype(np.float32)).astype(np.float32)
     x[0] = 1.4999999                                                  # the row maximum: the exponent brings it to [2^14, 2^15)
-    hi, lo, ok = split_h16b16_scaled(x[None, :], scale_exp(np.abs(x).max(keepdims=True))[:, None])
+    e = scale_exp(np.abs(x).max(keepdims=True))[:, None]
+    hi, lo, ok = split_f16u_scaled(x[None, :], e)
     assert ok
-    xs = np.ldexp(x.astype(np.float64), int(scale_exp(np.abs(x).max(keepdims=True))[0]))
-    assert (np.abs(lo[0]) <= np.abs(xs) * 2.0 ** -11).all()
-    assert (np.abs(xs - hi[0] - lo[0]) <= np.abs(xs) * 2.0 ** -19).all()
+    xs = np.ldexp(x.astype(np.float64), int(e[0, 0]))
+    rem = np.abs(xs - hi[0] - lo[0])
+    assert (rem <= np.maximum(np.abs(xs) * 2.0 ** -22, 2.0 ** -25)).all()
+    assert (rem <= np.abs(xs) * 2.0 ** -19).all()
+    big = np.abs(xs) >= 2.0 ** -3
+    assert (rem[big] <= np.abs(xs[big]) * 2.0 ** -22).all()
 
 
-def test_h16b16x3_coherent_inputs_stay_inside_1e5():
-    """One product repeated K times (what breaks BF16x3): the per-product error is bounded by 2^-18 + 2^-22 = 4.1e-6 for
-    EVERY pair of values, i.e. the 1e-5 contract holds with a factor 2.4 to spare before accumulation effects."""
+def test_fp16x3u_coherent_inputs_stay_inside_1e5():
+    """One product repeated K times (what breaks BF16x3).  Constant matrices put every element AT its row / column maximum, where the
+    split error is 2^-22: the same class as FP16x3."""
     r = np.random.default_rng(7)
     n = 100_000
     a = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
     b = ((r.random(n, dtype=np.float32) + 0.5) * np.exp2(r.integers(-3, 3, n))).astype(np.float32)
     exact = a.astype(np.float64) * b.astype(np.float64)
-    got = np.array([h16b16x3_model(a[i:i + 1, None], b[None, i:i + 1])[0, 0] for i in range(0, n, 20)])
+    got = np.array([fp16x3u_model(a[i:i + 1, None], b[None, i:i + 1])[0, 0] for i in range(0, n, 20)])
     err = np.abs(got - exact[::20]) / exact[::20]
+    assert err.max() <= 2.0 ** -20
+
+
+def test_fp16x3u_worst_case_pair_at_the_window_edge():
+    """Both factors 2^-20 below their row / column maximum: per-product error <= 2^-18 + 2^-22 = 4.1e-6 < 1e-5."""
+    r = np.random.default_rng(9)
+    k = 512
+    a = np.zeros((k, 2), np.float32)
+    b = np.zeros((2, k), np.float32)
+    a[:, 0] = 1.5; b[0, :] = 1.5                                      # the maxima (they meet only each other)
+    a[:, 1] = ((r.random(k) + 1.0) * 2.0 ** -20).astype(np.float32)  # x' in [2^-6, 2^-5): window edge
+    b[1, :] = ((r.random(k) + 1.0) * 2.0 ** -20).astype(np.float32)
+    a[:, 0] = 0.0                                                     # ... and now only the small elements contribute
+    a[0, 0] = 1.5
+    got = fp16x3u_model(a, b)
+    assert got is not None
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    sel = exact[1:, :] > 0
+    err = np.abs(got[1:, :] - exact[1:, :])[sel] / exact[1:, :][sel]
     assert err.max() <= 2.0 ** -18 + 2.0 ** -22 < 1e-5
-    assert err.max() > 2.0 ** -21                                     # (it IS coarser than FP16x3's 2^-20 class: documented trade)
 
 
 @pytest.mark.parametrize("k", [8, 256, 2048])
-def test_h16b16x3_random_dynamic_range_and_gather(k):
+def test_fp16x3u_random_dynamic_range_and_gather(k):
     r = np.random.default_rng(300 + k)
     a, b = r.random((64, k), dtype=np.float32), r.random((k, 48), dtype=np.float32)
     exact = a.astype(np.float64) @ b.astype(np.float64)
-    err = np.abs(h16b16x3_model(a, b) - exact) / exact
-    assert err.max() <= 2.0 ** -18
-    if k >= 256:
-        assert err.max() <= 5e-7                                      # zero-mean split errors average out over K
-    a2 = (a * np.exp2(r.integers(-60, 61, size=(64, 1))).astype(np.float32)).astype(np.float32)
-    b2 = (b * np.exp2(r.integers(-60, 61, size=(1, 48))).astype(np.float32)).astype(np.float32)
+    got = fp16x3u_model(a, b)
+    if got is not None:                                               # (U[0,1) data: an element below 2^-21 of its maximum is possible)
+        err = np.abs(got - exact) / exact
+        assert err.max() <= 2.0 ** -18
+        if k >= 256:
+            assert err.max() <= 5e-7
+    a2 = ((a + 0.01) * np.exp2(r.integers(-60, 61, size=(64, 1))).astype(np.float32)).astype(np.float32)
+    b2 = ((b + 0.01) * np.exp2(r.integers(-60, 61, size=(1, 48))).astype(np.float32)).astype(np.float32)
     exact2 = a2.astype(np.float64) @ b2.astype(np.float64)
-    assert (np.abs(h16b16x3_model(a2, b2) - exact2) / np.abs(exact2)).max() <= 2.0 ** -18
-    # gather: every output is ONE input element with its own split error (<= 2^-19), also 2^-26 below the row maximum
-    g = ((r.random((32, 128), dtype=np.float32) + 0.5) * np.exp2(r.integers(-26, 1, size=(32, 128))).astype(np.float32)).astype(np.float32)
+    assert (np.abs(fp16x3u_model(a2, b2) - exact2) / np.abs(exact2)).max() <= 2.0 ** -18
+    # gather: every output is ONE input element with its own split error (<= 2^-19 inside the window, here down to 2^-19 of the maximum)
+    g = ((r.random((32, 128), dtype=np.float32) + 0.5) * np.exp2(r.integers(-19, 1, size=(32, 128))).astype(np.float32)).astype(np.float32)
+    g[:, 0] = 1.4
     perm = r.permutation(128)
     pm = np.zeros((128, 128), np.float32)
     pm[perm, np.arange(128)] = 1.0
-    got = h16b16x3_model(g, pm)
+    got = fp16x3u_model(g, pm)
+    assert got is not None
     assert (np.abs(got - g[:, perm].astype(np.float64)) / g[:, perm]).max() <= 2.0 ** -19
+    g[3, 4] = g[3].max() * np.float32(2.0 ** -23)                     # outside the (narrower) window: repair / fallback path
+    assert fp16x3u_model(g, pm) is None

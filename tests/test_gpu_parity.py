@@ -428,10 +428,10 @@ def test_matmul_auto_both_fp16_tiles_all_contract_cases(nb, tile, monkeypatch):
     _matmul_contract_cases(nb, nb.FP16X3, 1000 + int(tile), 2.0 ** -19)
 
 
-def test_matmul_h16b16x3_all_contract_cases(nb):
-    """H16B16x3 (half hi parts + unscaled bfloat16 lo parts, mixed-format kind::f16 cross products, merged 256x256 tile): the same
-    contract cases.  A gathered element carries the split error of ONE element: <= 2^-19 (include/nb200.h)."""
-    _matmul_contract_cases(nb, nb.H16B16X3, 1500, 2.0 ** -18.9)
+def test_matmul_fp16x3u_all_contract_cases(nb):
+    """FP16x3U (half hi parts + UNSCALED half lo parts, one accumulator per chunk, merged 256x256 tile): the same contract cases.
+    A gathered element carries the split error of ONE element: <= 2^-19 at the edge of the window (include/nb200.h)."""
+    _matmul_contract_cases(nb, nb.FP16X3U, 1500, 2.0 ** -18.9)
 
 
 def test_matmul_auto_contract_cases(nb):
@@ -441,10 +441,10 @@ def test_matmul_auto_contract_cases(nb):
 
 @pytest.mark.parametrize("mkn", [(128, 128, 256), (384, 1024, 640), (1000, 520, 776), (333, 77, 129), (257, 1001, 67), (2048, 2048, 512),
                                  (4096, 256, 4096)])
-def test_matmul_h16b16x3_vs_cblas_sgemm(nb, mkn):
+def test_matmul_fp16x3u_vs_cblas_sgemm(nb, mkn):
     m, k, n = mkn
     r = _rng(m + k + n + 2)
-    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.H16B16X3, RTOL)
+    _matmul_check(nb, r.random((m, k), dtype=np.float32), r.random((k, n), dtype=np.float32), nb.FP16X3U, RTOL)
 
 
 def test_matmul_unaligned_operands_stay_on_the_tensor_path(nb):
