@@ -298,6 +298,23 @@ class Bench:
         return total / steps
 
 
+    def time_rotating(self, fn, n_sets, rounds, warm_rounds=1):
+        """ms per launch of fn(i), i cycling over n_sets DISTINCT operand sets whose combined size is many times the L2: every launch
+        reads data that cannot be cached (the other sets were streamed in between), launches go back to back, one event pair around
+        all of them - the kernel's steady-state rate without a per-launch event / drain gap."""
+        torch = self.torch
+        for _ in range(warm_rounds * n_sets):
+            fn(_ % n_sets)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(rounds * n_sets):
+            fn(r % n_sets)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (rounds * n_sets)
+
+
 def best_of(fn, reps, warm=1):
     for _ in range(warm):
         fn()
@@ -423,62 +440,88 @@ def run_single(args):
     torch.cuda.synchronize()
     e2e_err = float(((hc.cuda() - c).abs() / c.abs()).max())       # host pipeline (TF32x3 kernels) vs resident AUTO: both inside 1e-5
 
-    # ---- the other BASELINE configs: HBM-bound (inputs > L2, plus an explicit L2 flush between timed launches)
+    # ---- the other BASELINE configs: HBM-bound.  Two timings each: `ms` = launches back to back over NSETS distinct operand sets
+    # (>= 1 GiB streamed between two uses of a set, 8x the 126 MB L2: nothing can be cached; one event pair around all launches),
+    # `ms_isolated` = one launch between its own event pair after an explicit L2 flush (adds the ~5 us event / drain gap per launch).
     hbm = peaks["hbm_gbs"]
     per = {}
     m = 8192
-    x = torch.rand(m, m, device="cuda", generator=g)
-    y = torch.rand(m, m, device="cuda", generator=g)
-    z = torch.rand(m, m, device="cuda", generator=g)
-    out = torch.empty(m, m, device="cuda")
-    tmp = torch.empty(m, m, device="cuda")
+    NSETS = 4
+    xs = [torch.rand(m, m, device="cuda", generator=g) for _ in range(NSETS)]
+    ys = [torch.rand(m, m, device="cuda", generator=g) for _ in range(NSETS)]
+    zs = [torch.rand(m, m, device="cuda", generator=g) for _ in range(NSETS)]
+    outs = [torch.empty(m, m, device="cuda") for _ in range(NSETS)]
+    tmps = [torch.empty(m, m, device="cuda") for _ in range(NSETS)]
+    x, y, z, out, tmp = xs[0], ys[0], zs[0], outs[0], tmps[0]
     shp = (C.c_int64 * 2)(m, m)
     full = (C.c_int64 * 2)(m, 1)
     rowv = (C.c_int64 * 2)(0, 1)
     colv = (C.c_int64 * 2)(1, 0)
     reps = 10
 
-    def rec_hbm(name, ms_, bytes_, config, kernels):
+    def rec_hbm(name, ms_, bytes_, config, kernels, ms_iso=None):
         tb, src, _ = ncu_lookup(traffic, *kernels, near=bytes_) if kernels else (None, None, None)
         per[name] = {"config": config, "bound": "hbm", "ms": ms_, "achieved": bytes_ / ms_ / 1e6, "peak": hbm, "unit": "GB/s",
-                     "frac": bytes_ / ms_ / 1e6 / hbm, "algorithmic_bytes": bytes_, "traffic": tb, "traffic_source": src}
+                     "frac": bytes_ / ms_ / 1e6 / hbm, "algorithmic_bytes": bytes_, "traffic": tb, "traffic_source": src,
+                     "timing": f"back to back over {NSETS} distinct operand sets (inputs >> L2), one event pair"}
+        if ms_iso is not None:
+            per[name]["ms_isolated"] = ms_iso
+            per[name]["frac_isolated"] = bytes_ / ms_iso / 1e6 / hbm
 
-    t = B.time_steps(lambda: B.check(lib.nb200_ew_mul_add(out.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(), 2, shp, full, full, full)), reps, 3, flush=True)
-    rec_hbm("chain_fused_8192sq", t, 4 * m * m * 4, "configs[2] a*b+c 8192^2, one fused call (nb200_ew_mul_add)", [("ew_flat_vec", "MulAdd")])
+    def both(fn_i, rounds=5):
+        """(steady-state ms over the rotating sets, isolated ms after an L2 flush)"""
+        return B.time_rotating(fn_i, NSETS, rounds), B.time_steps(lambda: fn_i(0), reps, 3, flush=True)
 
-    def unfused():
-        B.check(lib.nb200_ew_binary(2, tmp.data_ptr(), x.data_ptr(), y.data_ptr(), 2, shp, full, full))
-        B.check(lib.nb200_ew_binary(0, out.data_ptr(), tmp.data_ptr(), z.data_ptr(), 2, shp, full, full))
-    t = B.time_steps(unfused, reps, 3, flush=True)
-    rec_hbm("chain_two_calls_8192sq", t, 6 * m * m * 4, "configs[2] a*b+c 8192^2 as the two nd:: calls unchanged PHP makes", None)
-    t = B.time_steps(lambda: B.check(lib.nb200_ew_mul_add(out.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(), 2, shp, full, rowv, colv)), reps, 3, flush=True)
-    rec_hbm("chain_fused_row_col_broadcast_8192sq", t, 2 * m * m * 4 + 2 * m * 4, "configs[2] broadcast variant: b row vector, c column vector", [("ew_bcast2d", "MulAdd")])
-    t = B.time_steps(lambda: B.check(lib.nb200_ew_unary(2, out.data_ptr(), x.data_ptr(), m * m, 0.0, 0.0)), reps, 3, flush=True)
-    rec_hbm("unary_exp_8192sq", t, 2 * m * m * 4, "nd::exp 8192^2 (math unary)", None)
+    t, ti = both(lambda i: B.check(lib.nb200_ew_mul_add(outs[i].data_ptr(), xs[i].data_ptr(), ys[i].data_ptr(), zs[i].data_ptr(), 2, shp, full, full, full)))
+    rec_hbm("chain_fused_8192sq", t, 4 * m * m * 4, "configs[2] a*b+c 8192^2, one fused call (nb200_ew_mul_add)", [("ew_flat_vec", "MulAdd")], ti)
+
+    def unfused(i):
+        B.check(lib.nb200_ew_binary(2, tmps[i].data_ptr(), xs[i].data_ptr(), ys[i].data_ptr(), 2, shp, full, full))
+        B.check(lib.nb200_ew_binary(0, outs[i].data_ptr(), tmps[i].data_ptr(), zs[i].data_ptr(), 2, shp, full, full))
+    t, ti = both(unfused)
+    rec_hbm("chain_two_calls_8192sq", t, 6 * m * m * 4, "configs[2] a*b+c 8192^2 as the two nd:: calls unchanged PHP makes", None, ti)
+    t, ti = both(lambda i: B.check(lib.nb200_ew_mul_add(outs[i].data_ptr(), xs[i].data_ptr(), ys[i].data_ptr(), zs[i].data_ptr(), 2, shp, full, rowv, colv)))
+    rec_hbm("chain_fused_row_col_broadcast_8192sq", t, 2 * m * m * 4 + 2 * m * 4, "configs[2] broadcast variant: b row vector, c column vector", [("ew_bcast2d", "MulAdd")], ti)
+    t, ti = both(lambda i: B.check(lib.nb200_ew_unary(2, outs[i].data_ptr(), xs[i].data_ptr(), m * m, 0.0, 0.0)))
+    rec_hbm("unary_exp_8192sq", t, 2 * m * m * 4, "nd::exp 8192^2 (math unary)", None, ti)
     res = torch.empty(16, device="cuda")
     ax = torch.empty(m, device="cuda")
-    t = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), x.data_ptr(), 1, m, m, 0)), reps, 3, flush=True)
-    rec_hbm("sum_axis0_8192sq", t, m * m * 4, "nd::sum(axis=0) 8192^2 (axis reduction, north_star)", [("reduce_cols_kernel",)])
-    t = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), x.data_ptr(), m, m, 1, 0)), reps, 3, flush=True)
-    rec_hbm("sum_axis1_8192sq", t, m * m * 4, "nd::sum(axis=1) 8192^2 (axis reduction, north_star)", [("reduce_rows_kernel",)])
+    # (the 8192^2 reductions read one 256 MiB array per launch: all four operand arrays of every set serve as inputs, 16 x 256 MiB)
+    red_in = xs + ys + zs + outs
+    for o_ in outs:
+        o_.copy_(xs[0])
+    t = B.time_rotating(lambda i: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), red_in[i].data_ptr(), 1, m, m, 0)), len(red_in), 2)
+    ti = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), x.data_ptr(), 1, m, m, 0)), reps, 3, flush=True)
+    rec_hbm("sum_axis0_8192sq", t, m * m * 4, "nd::sum(axis=0) 8192^2 (axis reduction, north_star)", [("reduce_cols_kernel",)], ti)
+    t = B.time_rotating(lambda i: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), red_in[i].data_ptr(), m, m, 1, 0)), len(red_in), 2)
+    ti = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax.data_ptr(), x.data_ptr(), m, m, 1, 0)), reps, 3, flush=True)
+    rec_hbm("sum_axis1_8192sq", t, m * m * 4, "nd::sum(axis=1) 8192^2 (axis reduction, north_star)", [("reduce_rows_kernel",)], ti)
+    for k_ in ("sum_axis0_8192sq", "sum_axis1_8192sq"):
+        per[k_]["timing"] = f"back to back over {len(red_in)} distinct 256 MiB inputs (4 GiB >> L2), one event pair"
     host["chain_x"], host["chain_y"], host["chain_z"] = x.cpu().numpy(), y.cpu().numpy(), z.cpu().numpy()
-    del y, z, out, tmp
-    big = torch.rand(1 << 28, device="cuda", generator=g)
-    t = B.time_steps(lambda: B.check(lib.nb200_reduce_full(0, res.data_ptr(), big.data_ptr(), 1 << 28)), reps, 3, flush=True)
-    rec_hbm("sum_2pow28", t, 1 << 30, "configs[3] nd::sum over 2^28", [("reduce_rows_kernel",)])
+    del y, z, out, tmp, x, xs, ys, zs, outs, tmps, red_in
+    bigs = [torch.rand(1 << 28, device="cuda", generator=g) for _ in range(NSETS)]
+    big = bigs[0]
+    t = B.time_rotating(lambda i: B.check(lib.nb200_reduce_full(0, res.data_ptr(), bigs[i].data_ptr(), 1 << 28)), NSETS, 3)
+    ti = B.time_steps(lambda: B.check(lib.nb200_reduce_full(0, res.data_ptr(), big.data_ptr(), 1 << 28)), reps, 3, flush=True)
+    rec_hbm("sum_2pow28", t, 1 << 30, "configs[3] nd::sum over 2^28", [("reduce_rows_kernel",)], ti)
     gpu_sum = float(res[0].item())
-    t = B.time_steps(lambda: B.check(lib.nb200_argminmax(1, res.data_ptr(), big.data_ptr(), 1, 1 << 28, 1)), reps, 3, flush=True)
-    rec_hbm("argmax_2pow28", t, 1 << 30, "configs[3] nd::argmax over 2^28", [("arg_rows_kernel",)])
+    t = B.time_rotating(lambda i: B.check(lib.nb200_argminmax(1, res.data_ptr(), bigs[i].data_ptr(), 1, 1 << 28, 1)), NSETS, 3)
+    B.check(lib.nb200_argminmax(1, res.data_ptr(), big.data_ptr(), 1, 1 << 28, 1))
+    ti = B.time_steps(lambda: B.check(lib.nb200_argminmax(1, res.data_ptr(), big.data_ptr(), 1, 1 << 28, 1)), reps, 3, flush=True)
+    rec_hbm("argmax_2pow28", t, 1 << 30, "configs[3] nd::argmax over 2^28", [("arg_rows_kernel",)], ti)
     per["sum_2pow28"]["result"] = gpu_sum
     per["sum_2pow28"]["fp64_truth"] = float(big.double().sum().item())
     # SURVEY §8(d) 4b: the 8192^2 axis sums are only 256 MiB (~45 us): launch + fold latency is visible, so also the 1 GiB shape
     ax2 = torch.empty(32768, device="cuda")
-    t = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), big.data_ptr(), 1, 32768, 8192, 0)), reps, 3, flush=True)
-    rec_hbm("sum_axis0_32768x8192", t, 1 << 30, "nd::sum(axis=0) 32768x8192 (1 GiB)", None)
-    t = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), big.data_ptr(), 32768, 8192, 1, 0)), reps, 3, flush=True)
-    rec_hbm("sum_axis1_32768x8192", t, 1 << 30, "nd::sum(axis=1) 32768x8192 (1 GiB)", None)
+    t = B.time_rotating(lambda i: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), bigs[i].data_ptr(), 1, 32768, 8192, 0)), NSETS, 3)
+    ti = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), big.data_ptr(), 1, 32768, 8192, 0)), reps, 3, flush=True)
+    rec_hbm("sum_axis0_32768x8192", t, 1 << 30, "nd::sum(axis=0) 32768x8192 (1 GiB)", None, ti)
+    t = B.time_rotating(lambda i: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), bigs[i].data_ptr(), 32768, 8192, 1, 0)), NSETS, 3)
+    ti = B.time_steps(lambda: B.check(lib.nb200_reduce_axis(0, ax2.data_ptr(), big.data_ptr(), 32768, 8192, 1, 0)), reps, 3, flush=True)
+    rec_hbm("sum_axis1_32768x8192", t, 1 << 30, "nd::sum(axis=1) 32768x8192 (1 GiB)", None, ti)
     host["big"] = big.cpu().numpy()
-    del big, x
+    del big, bigs
     # configs[0]: nd::add 1024x1024 (launch-latency bound on a GPU: 12 MiB of traffic, L2-resident)
     s = torch.rand(1024, 1024, device="cuda"); s2 = torch.rand(1024, 1024, device="cuda"); so = torch.empty(1024, 1024, device="cuda")
     s1 = (C.c_int64 * 1)(1 << 20); st1 = (C.c_int64 * 1)(1)
@@ -486,13 +529,20 @@ def run_single(args):
     per["add_1024sq_l2_warm"] = {"config": "configs[0] nd::add 1024x1024 on the GPU, back to back (L2-resident: launch-latency bound, reported, not a target)",
                                  "bound": "launch latency", "ms": t, "achieved": 3 * (1 << 22) / t / 1e6, "unit": "GB/s", "algorithmic_bytes": 3 << 22}
     # the launch-latency path: 50 nd::add calls recorded once (nb200_graph_begin / end) and replayed with one launch
+    # (the legacy default stream cannot be captured: record and replay on a side stream, which is also where the events are recorded)
     gexec = C.c_void_p()
-    B.check(lib.nb200_graph_begin())
-    for _ in range(50):
-        B.check(lib.nb200_ew_binary(0, so.data_ptr(), s.data_ptr(), s2.data_ptr(), 1, s1, st1, st1))
-    B.check(lib.nb200_graph_end(C.byref(gexec)))
-    tg = B.time_steps(lambda: B.check(lib.nb200_graph_launch(gexec)), 20, 3) / 50
-    B.check(lib.nb200_graph_destroy(gexec))
+    cap_stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(cap_stream):
+        B.check(lib.nb200_set_stream(C.c_void_p(cap_stream.cuda_stream)))
+        B.check(lib.nb200_graph_begin())
+        for _ in range(50):
+            B.check(lib.nb200_ew_binary(0, so.data_ptr(), s.data_ptr(), s2.data_ptr(), 1, s1, st1, st1))
+        B.check(lib.nb200_graph_end(C.byref(gexec)))
+        tg = B.time_steps(lambda: B.check(lib.nb200_graph_launch(gexec)), 20, 3) / 50
+        B.check(lib.nb200_graph_destroy(gexec))
+    torch.cuda.synchronize()
+    B.check(lib.nb200_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     per["add_1024sq_graph_replay"] = {"config": "configs[0] nd::add 1024x1024: 50 calls captured into one CUDA graph (nb200_graph_*), per-op time of a replay",
                                       "bound": "launch latency", "ms": tg, "achieved": 3 * (1 << 22) / tg / 1e6, "unit": "GB/s", "algorithmic_bytes": 3 << 22}
     host["add_a"], host["add_b"] = s.cpu().numpy(), s2.cpu().numpy()

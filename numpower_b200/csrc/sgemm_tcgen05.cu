@@ -1523,7 +1523,13 @@ __global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, c
         if (lo0 != nullptr) split_tf32_body(A, lo0, n0, B, lo1, n1, nonfinite, gen);
         return;
     }
-    for (unsigned int rec = blockIdx.x; rec < na + nb; rec += gridDim.x) {
+    // Every record is spread over `parts` CTAs (the whole grid works on the few records there are: a B-record walks a COLUMN of C and
+    // of A - one cache line per element - and is pure latency; one CTA per record took 16 dependent rounds for M = 4096).
+    const unsigned int nrec = na + nb;
+    unsigned int parts = gridDim.x / nrec;
+    if (parts < 1) parts = 1;
+    for (unsigned int w = blockIdx.x; w < nrec * parts; w += gridDim.x) {
+        const unsigned int rec = w / parts, part = w - rec * parts;
         const bool from_a = rec < na;
         const int4 q = from_a ? fa.recs[rec] : fb.recs[rec - na];
         const float d = __int_as_float(q.z);
@@ -1532,14 +1538,14 @@ __global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, c
             for (int64_t bb = sA ? bi : 0; bb < (sA ? bi + 1 : batch); bb++) {
                 const float *brow = B + (sB ? bb * sB : 0) + k * ldb;
                 float *crow = C + bb * sC + i * ldc;
-                for (int64_t j = threadIdx.x; j < N; j += 256) atomicAdd(crow + j, d * brow[j]);
+                for (int64_t j = (int64_t)part * 256 + threadIdx.x; j < N; j += (int64_t)parts * 256) atomicAdd(crow + j, d * brow[j]);
             }
         } else {
             const int64_t bk = sB ? q.x / K : 0, k = sB ? q.x - bk * K : q.x, j = q.y;
             for (int64_t bb = sB ? bk : 0; bb < (sB ? bk + 1 : batch); bb++) {
                 const float *acol = A + (sA ? bb * sA : 0) + k;
                 float *ccol = C + bb * sC + j;
-                for (int64_t i = threadIdx.x; i < M; i += 256) atomicAdd(ccol + i * ldc, acol[i * lda] * d);
+                for (int64_t i = (int64_t)part * 256 + threadIdx.x; i < M; i += (int64_t)parts * 256) atomicAdd(ccol + i * ldc, acol[i * lda] * d);
             }
         }
     }
@@ -1890,7 +1896,7 @@ static int fp16_pair_bn(int64_t batch, int64_t M, int64_t N) {
 }
 static int launch_fp16_prepass(const float *a_src, const float *b_src, const GemmArgs &g, int64_t ba, int64_t bb, bool do_a, bool do_b,
                                SplitSpanF16 &sa, SplitSpanF16 &sb, unsigned int *row_max, unsigned int *col_max, unsigned int *barrier,
-                               unsigned int *zero_ptr, int64_t zero_words, bool *zeroed_other, bool mix) {
+                               unsigned int *zero_ptr, int64_t zero_words, bool *zeroed_other, bool mix, int max_ctas_per_sm = 0) {
     *zeroed_other = false;
     const int64_t n_rows = ba * g.M;
     if (sa.s.groups + sb.s.groups == 0) return NB200_OK;
@@ -1922,7 +1928,9 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
         const int64_t rpc = n8 <= 64 ? 8 : n8 <= 128 ? 4 : n8 <= 256 ? 2 : 1;
         const int64_t a_elems = q.a_rows * g.K, b_elems = q.b_mats * g.K * g.N;
         const int64_t a_ctas = (q.a_rows + rpc - 1) / rpc, b_ctas = (b_elems + 32767) / 32768;
-        int64_t grid = (int64_t)ctx().num_sms * occ;
+        // (max_ctas_per_sm: the pipelined batched path runs this kernel BESIDE a persistent GEMM grid that leaves room for one of
+        // these CTAs per SM; the grid barrier needs every CTA resident)
+        int64_t grid = (int64_t)ctx().num_sms * (max_ctas_per_sm > 0 && max_ctas_per_sm < occ ? max_ctas_per_sm : occ);
         if (grid > a_ctas + b_ctas) grid = a_ctas + b_ctas;
         if (grid < 2) grid = 2;
         // CTAs per operand in proportion to the bytes each side moves through L2: A is read once and written once (8 B per element),
@@ -1975,6 +1983,183 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
     return NB200_OK;
 }
 
+// ---- batched FP16x3 with the pre-pass of chunk c+1 running BESIDE the GEMM of chunk c ------------------------------------------------
+// A batched call spends 20-30 % of its time in the HBM-bound pre-pass while the tensor pipe idles, and the GEMM leaves most of the
+// HBM bandwidth unused.  With enough matrices the batch is cut into chunks and software-pipelined over two streams and two
+// workspace sets:   helper stream:  prep(0) prep(1)      prep(2)      prep(3) ...
+//                   call's stream:          GEMM(0)+post GEMM(1)+post GEMM(2)+post ...
+// prep(c) waits for the kernels that last used its workspace set (chunk c-2), GEMM(c) waits for prep(c).  The persistent GEMM CTA
+// (192 threads x ~220 registers, ~200 KB shared memory) leaves room for ONE 256-thread pre-pass CTA per SM (64 registers, no shared
+// memory to speak of), so from chunk 1 on the pre-pass grid is one CTA per SM - co-resident with the GEMM, which its grid barrier
+// needs.  The helper stream has the lowest priority: when both grids are pending the GEMM's CTAs are placed first.
+struct Fp16Pipe {
+    cudaStream_t helper = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_prep[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    bool ok = false;
+};
+static Fp16Pipe g_fp16_pipe[NB200_MAX_DEVICES];
+static int fp16_pipe_get(Fp16Pipe **out) {
+    const int dev = ctx().device;
+    if (dev < 0 || dev >= NB200_MAX_DEVICES) return set_error(NB200_EINVAL, "device index out of range");
+    Fp16Pipe &P = g_fp16_pipe[dev];
+    if (!P.ok) {
+        int lo = 0, hi = 0;
+        NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority
+        NB_CUDA(cudaStreamCreateWithPriority(&P.helper, cudaStreamNonBlocking, lo));
+        NB_CUDA(cudaEventCreateWithFlags(&P.ev_start, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            NB_CUDA(cudaEventCreateWithFlags(&P.ev_prep[i], cudaEventDisableTiming));
+            NB_CUDA(cudaEventCreateWithFlags(&P.ev_free[i], cudaEventDisableTiming));
+        }
+        P.ok = true;
+    }
+    *out = &P;
+    return NB200_OK;
+}
+void gemm_pipeline_release(int device) {   // nb200_shutdown
+    if (device < 0 || device >= NB200_MAX_DEVICES) return;
+    Fp16Pipe &P = g_fp16_pipe[device];
+    if (!P.ok) return;
+    cudaStreamDestroy(P.helper);
+    cudaEventDestroy(P.ev_start);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(P.ev_prep[i]); cudaEventDestroy(P.ev_free[i]); }
+    P = Fp16Pipe();
+}
+// matrices per pipelined chunk (0 = do not pipeline): ~0.3 TFLOP of work per chunk, at least 4 chunks, both workspace sets in the budget
+static int64_t fp16_pipeline_chunk(const GemmArgs &g, int64_t per_matrix_ws_bytes) {
+    static const int on = getenv("NB200_GEMM_PIPELINE") ? atoi(getenv("NB200_GEMM_PIPELINE")) : 1;   // A/B switch
+    if (!on || g.batch < 8 || (!g.sA && !g.sB)) return 0;
+    const double flop = 2.0 * (double)g.M * (double)g.N * (double)g.K;
+    int64_t chunk = (int64_t)(2.7e11 / flop) + 1;
+    if (chunk * 4 > g.batch) chunk = g.batch / 4;
+    const int64_t budget = gemm_ws_budget();
+    if (per_matrix_ws_bytes > 0 && 2 * chunk * per_matrix_ws_bytes > budget) chunk = budget / (2 * per_matrix_ws_bytes);
+    if (chunk > 65535) chunk = 65535;
+    return chunk >= 1 ? chunk : 0;
+}
+
+template <bool MIX>
+static int launch_fp16_gemm(const GemmArgs &c, int cg, bool merged) {
+    if (MIX) {
+        if (merged) return launch_gemm<GemmCfg<2, 256, 3, false, true, true, true, true>>(c);
+        return cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true, true>>(c);
+    }
+    if (merged) return launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
+    return cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
+}
+
+static int gemm_fp16x3_pipelined(const GemmArgs &g, bool mix, int64_t chunk, bool raw_ok, int cg, bool merged) {
+    Fp16Pipe *P = nullptr;
+    { const int rc = fp16_pipe_get(&P); if (rc != NB200_OK) return rc; }
+    const int64_t lda = round8(g.K), ldb = round8(g.N);
+    const int64_t per_a = g.M * lda, per_b = g.K * ldb;
+    const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
+    const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);
+    const int64_t na32 = raw_ok ? round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)) : 0, nb32 = raw_ok ? round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N)) : 0;
+    const int64_t ctl_bytes = (16 + cols_layout * 4 + 255) & ~int64_t(255);
+    const int64_t fix_bytes = 2 * (int64_t)FIX_CAP * (int64_t)sizeof(int4);
+    const int64_t set_bytes = (ctl_bytes + (na + nbb) * 4 + rows_layout * 4 + (na32 + nb32) * 4 + fix_bytes + 255) & ~int64_t(255);
+    Ctx &cx = ctx();
+    { const int rc = ensure_gemm_ws(2 * set_bytes + 1024); if (rc != NB200_OK) return rc; }
+    cx.ctl_ready[0] = cx.ctl_ready[1] = 0;   // the single-call control blocks are overwritten
+    cudaStream_t s_main = cx.stream, s_help = P->helper;
+    struct Set { unsigned int *fix_cnt, *col_max, *row_max; __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo; float *a_lo32, *b_lo32; int4 *recs; } set[2];
+    for (int i = 0; i < 2; i++) {
+        char *base = static_cast<char *>(cx.gemm_ws) + i * set_bytes;
+        Set &S = set[i];
+        S.fix_cnt = reinterpret_cast<unsigned int *>(base);
+        S.col_max = S.fix_cnt + 4;
+        S.a_hi = reinterpret_cast<__nv_bfloat16 *>(base + ctl_bytes);
+        S.a_lo = S.a_hi + na; S.b_hi = S.a_hi + 2 * na; S.b_lo = S.b_hi + nbb;
+        S.row_max = reinterpret_cast<unsigned int *>(S.a_hi + 2 * na + 2 * nbb);
+        S.a_lo32 = reinterpret_cast<float *>(S.row_max + rows_layout);
+        S.b_lo32 = S.a_lo32 + na32;
+        S.recs = reinterpret_cast<int4 *>(S.b_lo32 + nb32);
+    }
+    // the helper stream starts after everything already enqueued on the call's stream (the operands' producers)
+    NB_CUDA(cudaEventRecord(P->ev_start, s_main));
+    NB_CUDA(cudaStreamWaitEvent(s_help, P->ev_start, 0));
+    int64_t ci = 0;
+    for (int64_t b0 = 0; b0 < g.batch; b0 += chunk, ci++) {
+        const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
+        const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;
+        const int si = (int)(ci & 1);
+        // a shared (stride-0) operand is prepared once, with chunk 0, and lives in set 0 for the whole call (parts, maxima, records)
+        Set &S = set[si];
+        Set &SA = g.sA ? S : set[0];
+        Set &SB = g.sB ? S : set[0];
+        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);
+        FixList fix_a{SA.fix_cnt, SA.recs}, fix_b{SB.fix_cnt + 1, SB.recs + FIX_CAP};
+        const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
+        // ---- helper stream: pre-pass of this chunk, once the chunk that used this workspace set two steps ago is done with it
+        if (ci >= 2) NB_CUDA(cudaStreamWaitEvent(s_help, P->ev_free[si], 0));
+        cx.stream = s_help;
+        int rc = NB200_OK;
+        cudaError_t ce = cudaSuccess;
+        // counters [0] A records, [1] B records, [2] barrier, then the column maxima (atomicMax targets)
+        if (do_a && ce == cudaSuccess) ce = cudaMemsetAsync(SA.fix_cnt, 0, 4, s_help);
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(S.fix_cnt + 2, 0, 4, s_help);
+        if (do_b && ce == cudaSuccess) ce = cudaMemsetAsync(SB.fix_cnt + 1, 0, 4, s_help);
+        if (do_b && ce == cudaSuccess) ce = cudaMemsetAsync(SB.col_max, 0, (size_t)(bb * g.N) * 4, s_help);
+        if (ce != cudaSuccess) { cx.stream = s_main; return set_error(NB200_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(ce)); }
+        SplitSpanF16 sa, sb;
+        sa.s = make_span(a_src, SA.a_hi, SA.a_lo, do_a ? ba : 0, g.M, g.K, g.lda, g.sA);
+        sa.max_bits = SA.row_max; sa.by_col = 0; sa.fix = fix_a;
+        sb.s = make_span(b_src, SB.b_hi, SB.b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
+        sb.max_bits = SB.col_max; sb.by_col = 1; sb.fix = fix_b;
+        bool zeroed_other = false;
+        rc = launch_fp16_prepass(a_src, b_src, g, ba, bb, do_a, do_b, sa, sb, SA.row_max, SB.col_max, S.fix_cnt + 2, nullptr, 0, &zeroed_other, mix,
+                                 ci == 0 ? 0 : 1);
+        cx.stream = s_main;
+        if (rc != NB200_OK) return rc;
+        NB_CUDA(cudaEventRecord(P->ev_prep[si], s_help));
+        // ---- the call's stream: product, repair / fallback preparation, gated fallback
+        NB_CUDA(cudaStreamWaitEvent(s_main, P->ev_prep[si], 0));
+        GemmArgs c = g;
+        c.batch = nb;
+        c.A = reinterpret_cast<const float *>(SA.a_hi); c.A_lo = reinterpret_cast<const float *>(SA.a_lo);
+        c.B = reinterpret_cast<const float *>(SB.b_hi); c.B_lo = reinterpret_cast<const float *>(SB.b_lo);
+        c.lda = lda; c.ldb = ldb;
+        c.sA = g.sA ? per_a : 0; c.sB = g.sB ? per_b : 0;
+        c.C = g.C + b0 * g.sC;
+        c.row_max = SA.row_max; c.col_max = SB.col_max;
+        c.gate_want = 0;
+        rc = mix ? launch_fp16_gemm<true>(c, cg, merged) : launch_fp16_gemm<false>(c, cg, merged);
+        if (rc != NB200_OK) return rc;
+        const int64_t s_a = span(ba, g.sA, g.M, g.lda, g.K), s_b = span(bb, g.sB, g.K, g.ldb, g.N);
+        {
+            cudaLaunchConfig_t pc = {};
+            pc.gridDim = dim3((unsigned)(ctx().num_sms * 4));
+            pc.blockDim = dim3(256);
+            pc.stream = s_main;
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pa[0].val.programmaticStreamSerializationAllowed = 1;
+            pc.attrs = pa;
+            pc.numAttrs = pdl_enabled() ? 1 : 0;
+            NB_CUDA(cudaLaunchKernelEx(&pc, fp16_post_kernel, g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
+                                       fix_a, fix_b, raw_ok ? S.a_lo32 : (float *)nullptr, s_a, raw_ok ? S.b_lo32 : (float *)nullptr, s_b, nonfinite_flag(),
+                                       ctx().nonfinite_gen, ctx().trace));
+            ctx().launches++;
+        }
+        if (raw_ok) {
+            GemmArgs f = g;
+            f.batch = nb;
+            f.A = a_src; f.A_lo = S.a_lo32; f.B = b_src; f.B_lo = S.b_lo32;
+            f.C = g.C + b0 * g.sC;
+            f.gate_want = 1;
+            if ((rc = dispatch_cfg<3>(f)) != NB200_OK) return rc;
+        } else {
+            dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)nb);
+            sgemm_simt_kernel<<<grid, 256, 0, s_main>>>(g.C + b0 * g.sC, a_src, b_src, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
+                                                        nonfinite_flag() + 1, ctx().nonfinite_gen);
+            NB_LAUNCH_CHECK();
+        }
+        NB_CUDA(cudaEventRecord(P->ev_free[si], s_main));
+    }
+    return NB200_OK;
+}
+
 static int gemm_fp16x3(const GemmArgs &g, bool mix) {
     const bool raw_ok = tensor_path_ok(g);                       // the TF32x3 fallback can read the raw operands
     const int64_t lda = round8(g.K), ldb = round8(g.N);
@@ -1993,6 +2178,17 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
     // FP16x3U (mix): one accumulator per chunk, so the merged 256x256 tile is chosen exactly as for BF16x3 (wave quantisation)
     const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? (mix ? bf16_pair_bn(chunk, g.M, g.N) : fp16_pair_bn(chunk, g.M, g.N)) : 128);
     const bool merged = cg == 2 && bn == 256;
+    {
+        // enough matrices: software-pipeline the pre-pass against the GEMM (not inside a stream capture: a recorded call stays on one stream)
+        cudaStreamCaptureStatus cap0 = cudaStreamCaptureStatusNone;
+        NB_CUDA(cudaStreamIsCapturing(ctx().stream, &cap0));
+        const int64_t per_ws = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0)) + (raw_ok ? 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0)) : 0);
+        const int64_t pchunk = cap0 == cudaStreamCaptureStatusNone ? fp16_pipeline_chunk(g, per_ws) : 0;
+        if (pchunk > 0) {
+            const int pbn = v ? bn : (cg == 2 ? (mix ? bf16_pair_bn(pchunk, g.M, g.N) : fp16_pair_bn(pchunk, g.M, g.N)) : 128);
+            return gemm_fp16x3_pipelined(g, mix, pchunk, raw_ok, cg, cg == 2 && pbn == 256);
+        }
+    }
     // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
     const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
     const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);   // 16-byte aligned sub-arrays
@@ -2061,11 +2257,7 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
         c.C = g.C + b0 * g.sC;
         c.row_max = row_max; c.col_max = col_max;
         c.gate_want = 0;
-        if (mix) {
-            if (merged) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true, true>>(c);
-            else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true, true>>(c);
-        } else if (merged) rc = launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
-        else rc = cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
+        rc = mix ? launch_fp16_gemm<true>(c, cg, merged) : launch_fp16_gemm<false>(c, cg, merged);
         if (rc != NB200_OK) return rc;
         // (2) eligible: sparse repair of the recorded out-of-window elements (normally none: returns at once);
         //     ineligible: TF32 lo parts of BOTH raw operands of this chunk (a shared operand is split again with every chunk:

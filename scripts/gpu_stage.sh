@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # One parameterised GPU run script (replaces the per-experiment gpu_r2*.sh files).
 #   usage: gpu_stage.sh <tag> <stage> [<stage> ...]
-#   stages: tests | tests_matmul | shard | bench | launches | ncu_matmul | ncu_hbm | probe:<precision number,...> (0 tf32x3, 2 bf16x3, 3 auto, 4 fp16x3, ...) | timeline | memcheck | multi:<N>
+#   stages: tests | tests_matmul | shard | bench | launches | ncu_matmul | ncu_hbm | probe:<precision number,...> (0 tf32x3, 2 bf16x3, 3 auto, 4 fp16x3, ...) | timeline:<precision,...> | memcheck | multi:<N>
 tag=$1; shift
 mkdir -p gpurun_out
 for stage in "$@"; do
@@ -18,7 +18,8 @@ for stage in "$@"; do
        python scripts/ncu_extract.py gpurun_out/prof_${tag}_hbm.ncu-rep gpurun_out/${tag}_ncu_hbm.csv ;;
     probe:*) for prec in $(echo ${stage#probe:} | tr , ' '); do
          timeout 300 python scripts/gemm_probe.py child auto $prec 4096x4096x4096 8192x8192x8192 2048x2048x2048 1024x1024x1024 1000x520x776 > gpurun_out/${tag}_probe_$prec.jsonl 2> gpurun_out/${tag}_probe_$prec.err; cut -c1-330 gpurun_out/${tag}_probe_$prec.jsonl; tail -2 gpurun_out/${tag}_probe_$prec.err; done ;;
-    timeline) timeout 300 python scripts/gemm_timeline.py > gpurun_out/${tag}_timeline.jsonl 2> gpurun_out/${tag}_timeline.err; cut -c1-900 gpurun_out/${tag}_timeline.jsonl ;;
+    timeline:*) for prec in $(echo ${stage#timeline:} | tr , ' '); do
+         timeout 300 python scripts/gemm_timeline.py $prec 4096x4096x4096 8192x8192x8192 2048x2048x2048 > gpurun_out/${tag}_timeline_$prec.jsonl 2> gpurun_out/${tag}_timeline_$prec.err; cut -c1-1200 gpurun_out/${tag}_timeline_$prec.jsonl; tail -2 gpurun_out/${tag}_timeline_$prec.err; done ;;
     memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitizer_targets.py > gpurun_out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/${tag}_memcheck.log ;;
     multi:*) bash scripts/gpu_multi.sh ${stage#multi:} $tag ;;
     *) echo "unknown stage $stage" ;;

@@ -784,6 +784,56 @@ def test_sgemm_batched_in_several_workspace_chunks(nb, prec, monkeypatch):
         lib.nb200_free(p)
 
 
+@pytest.mark.parametrize("prec", [4, 5, 3])
+@pytest.mark.parametrize("shared", ["none", "B", "A"])
+def test_sgemm_batched_pipelined_prepass_beside_the_gemm(nb, prec, shared):
+    """batch >= 8: the call is cut into >= 4 chunks whose pre-pass runs on a helper stream beside the previous chunk's GEMM (two
+    workspace sets).  Every matrix against cblas_sgemm; an out-of-window element in a LATE chunk (sparse repair), a shared operand
+    that carries a repaired element (its records must survive in workspace set 0 for the whole call), a late chunk with too many
+    out-of-window elements (the whole call falls back: bit-identical to TF32X3), and the same call with the pipeline switched off."""
+    lib = nb.lib()
+    r = _rng(700 + prec)
+    batch, M, N, K = 13, 256, 264, 200
+    a = r.random((batch, M, K) if shared != "A" else (M, K), dtype=np.float32) + 0.25
+    b = r.random((batch, K, N) if shared != "B" else (K, N), dtype=np.float32) + 0.25
+    A = lambda i: a[i] if shared != "A" else a
+    Bm = lambda i: b[i] if shared != "B" else b
+    # repair cases: an element 2^-40 below its row maximum, observable through a B column that selects only it
+    if shared != "A":
+        a[11, 17, 5] = a[11, 17].max() * np.float32(2.0 ** -40)
+    else:
+        a[17, 5] = a[17].max() * np.float32(2.0 ** -40)
+    if shared != "B":
+        b[11, :, 9] = 0.0; b[11, 5, 9] = 1.5
+    else:
+        b[:, 9] = 0.0; b[5, 9] = 1.5
+    da, db = _dev(nb, a), _dev(nb, b)
+    dc = _dev(nb, np.zeros((batch, M, N), np.float32))
+    sa, sb = (0 if shared == "A" else M * K), (0 if shared == "B" else K * N)
+
+    def run(p):
+        assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, sa, sb, M * N, p) == 0, lib.nb200_last_error()
+        return _fetch(nb, dc, (batch, M, N))
+    got = run(prec)
+    for i in range(batch):
+        exp = ORACLE.matmul(A(i), Bm(i))
+        assert rel_err(got[i], exp).max() <= RTOL, i
+    # many calls back to back: workspace sets / events are reused across calls
+    for _ in range(3):
+        np.testing.assert_array_equal(run(prec), got)
+    # too many out-of-window elements in a late chunk only -> TF32x3 fallback of the chunks that see the flag, 1e-5 everywhere
+    if shared != "A":
+        a2 = a.copy()
+        a2[12, :40, :128] *= np.float32(2.0 ** -40)
+        assert lib.nb200_copy_h2d(da, a2.ctypes.data, a2.nbytes) == 0
+        got2 = run(prec)
+        for i in range(batch):
+            assert rel_err(got2[i], ORACLE.matmul(a2[i], Bm(i))).max() <= RTOL, i
+        np.testing.assert_array_equal(got2[12], nb.nd.matmul(nb.NDArray.array(a2[12]).gpu(), nb.NDArray.array(Bm(12)).gpu(), nb.TF32X3).toArray())
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
 @pytest.mark.parametrize("mkn", [(1024, 512, 768), (700, 260, 132), (64, 64, 64), (1025, 128, 128), (257, 256, 256), (2049, 512, 64)])
 def test_sgemm_host_pipeline_matches_resident_call(nb, mkn):
     """nb200_sgemm_host (B once, A row blocks in, C row blocks out) within 1e-5 of cblas_sgemm and of the resident call.

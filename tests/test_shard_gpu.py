@@ -186,7 +186,8 @@ def test_resident_sharded_batched_matmul_and_device_switching(grp):
     assert lib.nb200_mem_stats(C.byref(live), C.byref(nbytes)) == 0
     before = live.value
     assert lib.nb200_free(p) == 0
-    assert lib.nb200_mem_stats(C.byref(live), C.byref(nbytes)) == 0 and live.value == before      # device 0's ledger untouched
+    # device 0's ledger untouched (a one-GPU box has a single device: the block WAS device 0's)
+    assert lib.nb200_mem_stats(C.byref(live), C.byref(nbytes)) == 0 and live.value == before - (1 if last == g.devices[0] else 0)
     assert lib.nb200_set_device(last) == 0
     q = C.c_void_p()
     assert lib.nb200_alloc(C.byref(q), 1 << 20) == 0 and q.value == p.value                        # came back from the owner's pool
