@@ -2027,7 +2027,11 @@ void gemm_pipeline_release(int device) {   // nb200_shutdown
 }
 // matrices per pipelined chunk (0 = do not pipeline): ~0.3 TFLOP of work per chunk, at least 4 chunks, both workspace sets in the budget
 static int64_t fp16_pipeline_chunk(const GemmArgs &g, int64_t per_matrix_ws_bytes) {
-    static const int on = getenv("NB200_GEMM_PIPELINE") ? atoi(getenv("NB200_GEMM_PIPELINE")) : 1;   // A/B switch
+    // Measured on B200 (profiles/r2_summary.md): NOT a win as it stands - beside the 192-thread GEMM CTA there is room for one
+    // 256-thread pre-pass CTA per SM, and at a quarter of its usual occupancy the (latency-bound) pre-pass of a chunk takes longer
+    // than the chunk's GEMM, so the pipeline becomes pre-pass bound: 128 x 2048^2 on one GPU 6.9 -> 10.2 ms.  (The merged 256x256
+    // GEMM owns the whole register file: nothing co-resides with it at all.)  Off by default; NB200_GEMM_PIPELINE=1 switches it on.
+    static const int on = getenv("NB200_GEMM_PIPELINE") ? atoi(getenv("NB200_GEMM_PIPELINE")) : 0;
     if (!on || g.batch < 8 || (!g.sA && !g.sB)) return 0;
     const double flop = 2.0 * (double)g.M * (double)g.N * (double)g.K;
     int64_t chunk = (int64_t)(2.7e11 / flop) + 1;

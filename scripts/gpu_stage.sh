@@ -14,6 +14,8 @@ for stage in "$@"; do
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${tag}_bench_under_ncu.log 2>&1; wc -l gpurun_out/${tag}_launches_bench.csv ;;
     ncu_matmul) bash scripts/gpu_ncu.sh ${tag}_matmul_auto "prep16|sgemm_tf32_kernel|fp16_post" 4 4 gemm_auto
        python scripts/ncu_extract.py gpurun_out/prof_${tag}_matmul_auto.ncu-rep gpurun_out/${tag}_ncu_matmul_auto.csv ;;
+    ncu_merged) bash scripts/gpu_ncu.sh ${tag}_merged "sgemm_tf32_kernel" 1 6 gemm_bf16 gemm_fp16u
+       python scripts/ncu_extract.py gpurun_out/prof_${tag}_merged.ncu-rep gpurun_out/${tag}_ncu_merged.csv ;;
     ncu_hbm) bash scripts/gpu_ncu.sh ${tag}_hbm "ew_flat_vec|ew_bcast2d|reduce_rows_kernel|arg_rows_kernel|reduce_cols" 0 14 ew reduce
        python scripts/ncu_extract.py gpurun_out/prof_${tag}_hbm.ncu-rep gpurun_out/${tag}_ncu_hbm.csv ;;
     probe:*) for prec in $(echo ${stage#probe:} | tr , ' '); do

@@ -36,6 +36,12 @@ if "gemm_fp16" in which:
     for _ in range(reps + 1):
         assert lib.nb200_sgemm(c.data_ptr(), a.data_ptr(), b.data_ptr(), n, n, n, n, n, n, 4) == 0
     del a, b, c
+if "gemm_fp16u" in which:
+    n = 4096
+    a = torch.rand(n, n, device="cuda", generator=g); b = torch.rand(n, n, device="cuda", generator=g); c = torch.empty(n, n, device="cuda")
+    for _ in range(reps + 1):
+        assert lib.nb200_sgemm(c.data_ptr(), a.data_ptr(), b.data_ptr(), n, n, n, n, n, n, 5) == 0
+    del a, b, c
 if "gemm_auto" in which:   # what nd::matmul runs (NB200_GEMM_AUTO)
     n = 4096
     a = torch.rand(n, n, device="cuda", generator=g); b = torch.rand(n, n, device="cuda", generator=g); c = torch.empty(n, n, device="cuda")
