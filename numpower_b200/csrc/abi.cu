@@ -126,7 +126,6 @@ int ensure_gemm_ws(int64_t bytes) {
 }
 
 void host_pipeline_release(int device);   // host_pipeline.cu: staging buffers, streams and events of that device
-void gemm_pipeline_release(int device);   // sgemm_tcgen05.cu: helper stream and events of the pipelined batched matmul
 
 static void shutdown_device(int device) {
     Ctx &c = g_ctxs[device];
@@ -134,7 +133,6 @@ static void shutdown_device(int device) {
     cudaSetDevice(device);
     cudaStreamSynchronize(c.stream);
     host_pipeline_release(device);
-    gemm_pipeline_release(device);
     if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
     if (c.scratch) cudaFree(c.scratch);
     if (c.gemm_ws) cudaFree(c.gemm_ws);

@@ -119,7 +119,10 @@ struct GemmCfg {
     static constexpr int TMA_BYTES = INK_ ? (A_BYTES + B_BYTES) : STAGE_BYTES;   // bytes the TMA lands per stage per CTA
     static_assert(!INK_ || (PASSES_ == 3 && !BF16_), "in-kernel split only exists for TF32x3");
     static_assert(!BF16_ || PASSES_ == 3, "bf16 operands are only used by the x3 error-compensated mode");
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/;
+    // SCALED + MERGED: per-tile column scale factors (two floats per column, double-buffered by tile parity) behind the barrier block
+    static constexpr int COLFAC_BYTES = (SCALED_ && MERGED_) ? 2 * 256 * 8 : 0;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/ + COLFAC_BYTES;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
@@ -460,6 +463,8 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const int quarter = warp & 3;  // TMEM lane quarter this warp may read
         int acc = 0;
         uint32_t acc_phase = 0;
+        int epi_tile = 0;   // tiles this CTA has started (parity selects the column-factor buffer, SCALED + MERGED)
+        (void)epi_tile;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -516,6 +521,27 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const int half = (warp - Cfg::EPI_WARP0) >> 2;
                 const bool idle = half_tile && half == 1;   // half tiles only have the lower 128 accumulator columns
                 float tot[128];
+                // SCALED: the 2^-(row exponent + column exponent) of every output as FOUR exact power-of-two factors,
+                // x * (c1 * r1) * (c2 * r2) with 2^-ec = c1 * c2 and 2^-er = r1 * r2 split in halves (the intermediate lies between x
+                // and the result: no spurious overflow).  The 256 epilogue threads compute the tile's 256 column pairs ONCE, into
+                // shared memory (double-buffered by tile parity, one named barrier per tile), instead of every thread redoing the
+                // exponent arithmetic for its 128 columns at the end of the tile, when the next tile's first chunks are waiting.
+                float r1 = 1.f, r2 = 1.f;
+                uint32_t colfac = 0;
+                if constexpr (Cfg::SCALED) {
+                    const int et = (int)threadIdx.x - Cfg::EPI_WARP0 * 32;   // 0 .. 255
+                    colfac = bar_base + 384u + (uint32_t)((epi_tile & 1) * 2048);
+                    const int64_t cc = col0 + et;
+                    const int ec = cc < p.N ? scale_exp(cmax[cc]) : 0;
+                    const int c1e = (-ec) / 2, c2e = -ec - c1e;
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(colfac + (uint32_t)et * 8u),
+                                 "f"(__int_as_float((c1e + 127) << 23)), "f"(__int_as_float((c2e + 127) << 23)) : "memory");
+                    const int r1e = (-e_row) / 2, r2e = -e_row - r1e;
+                    r1 = __int_as_float((r1e + 127) << 23);
+                    r2 = __int_as_float((r2e + 127) << 23);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps (barrier 0 belongs to __syncthreads)
+                    epi_tile++;
+                }
                 for (int kb0 = 0; kb0 < num_kb; kb0 += Cfg::KB_PER_CHUNK) {
                     const bool first = kb0 == 0, last = kb0 + Cfg::KB_PER_CHUNK >= num_kb;
                     mbar_wait(tfull_bar(acc), acc_phase, p.debug, 0x400u + acc);
@@ -542,20 +568,13 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     if (last && row < p.M && !idle) {
                         const int64_t colh = col0 + half * 128;
                         if constexpr (Cfg::SCALED) {
-                            if (colh + 128 <= p.N && (p.N & 3) == 0) {   // column maxima 16-byte aligned (col_max sub-arrays are)
-                                const uint4 *mb = reinterpret_cast<const uint4 *>(cmax + colh);
+                            const uint32_t cf = colfac + (uint32_t)(half * 128) * 8u;
 #pragma unroll
-                                for (int q = 0; q < 32; q++) {
-                                    const uint4 m4 = __ldg(mb + q);
-                                    tot[4 * q] = scale_pow2(tot[4 * q], -(e_row + scale_exp(m4.x)));
-                                    tot[4 * q + 1] = scale_pow2(tot[4 * q + 1], -(e_row + scale_exp(m4.y)));
-                                    tot[4 * q + 2] = scale_pow2(tot[4 * q + 2], -(e_row + scale_exp(m4.z)));
-                                    tot[4 * q + 3] = scale_pow2(tot[4 * q + 3], -(e_row + scale_exp(m4.w)));
-                                }
-                            } else {
-#pragma unroll
-                                for (int q = 0; q < 128; q++)
-                                    if (colh + q < p.N) tot[q] = scale_pow2(tot[q], -(e_row + scale_exp(cmax[colh + q])));
+                            for (int q = 0; q < 64; q++) {   // two columns (four factors) per 16-byte shared load, same address in every lane
+                                float c1a, c2a, c1b, c2b;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c1a), "=f"(c2a), "=f"(c1b), "=f"(c2b) : "r"(cf + (uint32_t)q * 16u));
+                                tot[2 * q] = tot[2 * q] * (c1a * r1) * (c2a * r2);
+                                tot[2 * q + 1] = tot[2 * q + 1] * (c1b * r1) * (c2b * r2);
                             }
                         }
                         if (vec_ok && colh + 128 <= p.N) {
@@ -1983,65 +2002,13 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
     return NB200_OK;
 }
 
-// ---- batched FP16x3 with the pre-pass of chunk c+1 running BESIDE the GEMM of chunk c ------------------------------------------------
-// A batched call spends 20-30 % of its time in the HBM-bound pre-pass while the tensor pipe idles, and the GEMM leaves most of the
-// HBM bandwidth unused.  With enough matrices the batch is cut into chunks and software-pipelined over two streams and two
-// workspace sets:   helper stream:  prep(0) prep(1)      prep(2)      prep(3) ...
-//                   call's stream:          GEMM(0)+post GEMM(1)+post GEMM(2)+post ...
-// prep(c) waits for the kernels that last used its workspace set (chunk c-2), GEMM(c) waits for prep(c).  The persistent GEMM CTA
-// (192 threads x ~220 registers, ~200 KB shared memory) leaves room for ONE 256-thread pre-pass CTA per SM (64 registers, no shared
-// memory to speak of), so from chunk 1 on the pre-pass grid is one CTA per SM - co-resident with the GEMM, which its grid barrier
-// needs.  The helper stream has the lowest priority: when both grids are pending the GEMM's CTAs are placed first.
-struct Fp16Pipe {
-    cudaStream_t helper = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_prep[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    bool ok = false;
-};
-static Fp16Pipe g_fp16_pipe[NB200_MAX_DEVICES];
-static int fp16_pipe_get(Fp16Pipe **out) {
-    const int dev = ctx().device;
-    if (dev < 0 || dev >= NB200_MAX_DEVICES) return set_error(NB200_EINVAL, "device index out of range");
-    Fp16Pipe &P = g_fp16_pipe[dev];
-    if (!P.ok) {
-        int lo = 0, hi = 0;
-        NB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority
-        NB_CUDA(cudaStreamCreateWithPriority(&P.helper, cudaStreamNonBlocking, lo));
-        NB_CUDA(cudaEventCreateWithFlags(&P.ev_start, cudaEventDisableTiming));
-        for (int i = 0; i < 2; i++) {
-            NB_CUDA(cudaEventCreateWithFlags(&P.ev_prep[i], cudaEventDisableTiming));
-            NB_CUDA(cudaEventCreateWithFlags(&P.ev_free[i], cudaEventDisableTiming));
-        }
-        P.ok = true;
-    }
-    *out = &P;
-    return NB200_OK;
-}
-void gemm_pipeline_release(int device) {   // nb200_shutdown
-    if (device < 0 || device >= NB200_MAX_DEVICES) return;
-    Fp16Pipe &P = g_fp16_pipe[device];
-    if (!P.ok) return;
-    cudaStreamDestroy(P.helper);
-    cudaEventDestroy(P.ev_start);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(P.ev_prep[i]); cudaEventDestroy(P.ev_free[i]); }
-    P = Fp16Pipe();
-}
-// matrices per pipelined chunk (0 = do not pipeline): ~0.3 TFLOP of work per chunk, at least 4 chunks, both workspace sets in the budget
-static int64_t fp16_pipeline_chunk(const GemmArgs &g, int64_t per_matrix_ws_bytes) {
-    // Measured on B200 (profiles/r2_summary.md): NOT a win as it stands - beside the 192-thread GEMM CTA there is room for one
-    // 256-thread pre-pass CTA per SM, and at a quarter of its usual occupancy the (latency-bound) pre-pass of a chunk takes longer
-    // than the chunk's GEMM, so the pipeline becomes pre-pass bound: 128 x 2048^2 on one GPU 6.9 -> 10.2 ms.  (The merged 256x256
-    // GEMM owns the whole register file: nothing co-resides with it at all.)  Off by default; NB200_GEMM_PIPELINE=1 switches it on.
-    static const int on = getenv("NB200_GEMM_PIPELINE") ? atoi(getenv("NB200_GEMM_PIPELINE")) : 0;
-    if (!on || g.batch < 8 || (!g.sA && !g.sB)) return 0;
-    const double flop = 2.0 * (double)g.M * (double)g.N * (double)g.K;
-    int64_t chunk = (int64_t)(2.7e11 / flop) + 1;
-    if (chunk * 4 > g.batch) chunk = g.batch / 4;
-    const int64_t budget = gemm_ws_budget();
-    if (per_matrix_ws_bytes > 0 && 2 * chunk * per_matrix_ws_bytes > budget) chunk = budget / (2 * per_matrix_ws_bytes);
-    if (chunk > 65535) chunk = 65535;
-    return chunk >= 1 ? chunk : 0;
-}
-
+// ---- Tried and removed (measured on B200, profiles/r2_summary.md): software-pipelining a batched call over two streams and two
+// workspace sets so that the pre-pass of chunk c+1 runs BESIDE the GEMM of chunk c.  Beside the 192-thread GEMM CTA (~220
+// registers per thread, ~200 KB shared memory) an SM has room for ONE 256-thread pre-pass CTA, and at a quarter of its usual
+// occupancy the latency-bound pre-pass of a chunk takes longer than the chunk's GEMM: the pipeline becomes pre-pass bound
+// (128 x 2048^2 on one GPU: 6.9 -> 10.2 ms).  The merged 256x256 GEMM owns the whole register file, nothing co-resides with it.
+// Hiding the pre-pass needs a pre-pass that keeps ~40 KB per SM in flight from one small CTA (TMA-staged through the ~26 KB of
+// shared memory the GEMM leaves free) - future work.
 template <bool MIX>
 static int launch_fp16_gemm(const GemmArgs &c, int cg, bool merged) {
     if (MIX) {
@@ -2050,118 +2017,6 @@ static int launch_fp16_gemm(const GemmArgs &c, int cg, bool merged) {
     }
     if (merged) return launch_gemm<GemmCfg<2, 256, 3, false, true, true, true>>(c);
     return cg == 2 ? launch_gemm<GemmCfg<2, 128, 3, false, true, false, true>>(c) : launch_gemm<GemmCfg<1, 128, 3, false, true, false, true>>(c);
-}
-
-static int gemm_fp16x3_pipelined(const GemmArgs &g, bool mix, int64_t chunk, bool raw_ok, int cg, bool merged) {
-    Fp16Pipe *P = nullptr;
-    { const int rc = fp16_pipe_get(&P); if (rc != NB200_OK) return rc; }
-    const int64_t lda = round8(g.K), ldb = round8(g.N);
-    const int64_t per_a = g.M * lda, per_b = g.K * ldb;
-    const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
-    const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);
-    const int64_t na32 = raw_ok ? round4(span(g.sA ? chunk : 1, g.sA, g.M, g.lda, g.K)) : 0, nb32 = raw_ok ? round4(span(g.sB ? chunk : 1, g.sB, g.K, g.ldb, g.N)) : 0;
-    const int64_t ctl_bytes = (16 + cols_layout * 4 + 255) & ~int64_t(255);
-    const int64_t fix_bytes = 2 * (int64_t)FIX_CAP * (int64_t)sizeof(int4);
-    const int64_t set_bytes = (ctl_bytes + (na + nbb) * 4 + rows_layout * 4 + (na32 + nb32) * 4 + fix_bytes + 255) & ~int64_t(255);
-    Ctx &cx = ctx();
-    { const int rc = ensure_gemm_ws(2 * set_bytes + 1024); if (rc != NB200_OK) return rc; }
-    cx.ctl_ready[0] = cx.ctl_ready[1] = 0;   // the single-call control blocks are overwritten
-    cudaStream_t s_main = cx.stream, s_help = P->helper;
-    struct Set { unsigned int *fix_cnt, *col_max, *row_max; __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo; float *a_lo32, *b_lo32; int4 *recs; } set[2];
-    for (int i = 0; i < 2; i++) {
-        char *base = static_cast<char *>(cx.gemm_ws) + i * set_bytes;
-        Set &S = set[i];
-        S.fix_cnt = reinterpret_cast<unsigned int *>(base);
-        S.col_max = S.fix_cnt + 4;
-        S.a_hi = reinterpret_cast<__nv_bfloat16 *>(base + ctl_bytes);
-        S.a_lo = S.a_hi + na; S.b_hi = S.a_hi + 2 * na; S.b_lo = S.b_hi + nbb;
-        S.row_max = reinterpret_cast<unsigned int *>(S.a_hi + 2 * na + 2 * nbb);
-        S.a_lo32 = reinterpret_cast<float *>(S.row_max + rows_layout);
-        S.b_lo32 = S.a_lo32 + na32;
-        S.recs = reinterpret_cast<int4 *>(S.b_lo32 + nb32);
-    }
-    // the helper stream starts after everything already enqueued on the call's stream (the operands' producers)
-    NB_CUDA(cudaEventRecord(P->ev_start, s_main));
-    NB_CUDA(cudaStreamWaitEvent(s_help, P->ev_start, 0));
-    int64_t ci = 0;
-    for (int64_t b0 = 0; b0 < g.batch; b0 += chunk, ci++) {
-        const int64_t nb = g.batch - b0 < chunk ? g.batch - b0 : chunk;
-        const int64_t ba = g.sA ? nb : 1, bb = g.sB ? nb : 1;
-        const int si = (int)(ci & 1);
-        // a shared (stride-0) operand is prepared once, with chunk 0, and lives in set 0 for the whole call (parts, maxima, records)
-        Set &S = set[si];
-        Set &SA = g.sA ? S : set[0];
-        Set &SB = g.sB ? S : set[0];
-        const bool do_a = (b0 == 0 || g.sA), do_b = (b0 == 0 || g.sB);
-        FixList fix_a{SA.fix_cnt, SA.recs}, fix_b{SB.fix_cnt + 1, SB.recs + FIX_CAP};
-        const float *a_src = g.A + (g.sA ? b0 * g.sA : 0), *b_src = g.B + (g.sB ? b0 * g.sB : 0);
-        // ---- helper stream: pre-pass of this chunk, once the chunk that used this workspace set two steps ago is done with it
-        if (ci >= 2) NB_CUDA(cudaStreamWaitEvent(s_help, P->ev_free[si], 0));
-        cx.stream = s_help;
-        int rc = NB200_OK;
-        cudaError_t ce = cudaSuccess;
-        // counters [0] A records, [1] B records, [2] barrier, then the column maxima (atomicMax targets)
-        if (do_a && ce == cudaSuccess) ce = cudaMemsetAsync(SA.fix_cnt, 0, 4, s_help);
-        if (ce == cudaSuccess) ce = cudaMemsetAsync(S.fix_cnt + 2, 0, 4, s_help);
-        if (do_b && ce == cudaSuccess) ce = cudaMemsetAsync(SB.fix_cnt + 1, 0, 4, s_help);
-        if (do_b && ce == cudaSuccess) ce = cudaMemsetAsync(SB.col_max, 0, (size_t)(bb * g.N) * 4, s_help);
-        if (ce != cudaSuccess) { cx.stream = s_main; return set_error(NB200_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(ce)); }
-        SplitSpanF16 sa, sb;
-        sa.s = make_span(a_src, SA.a_hi, SA.a_lo, do_a ? ba : 0, g.M, g.K, g.lda, g.sA);
-        sa.max_bits = SA.row_max; sa.by_col = 0; sa.fix = fix_a;
-        sb.s = make_span(b_src, SB.b_hi, SB.b_lo, do_b ? bb : 0, g.K, g.N, g.ldb, g.sB);
-        sb.max_bits = SB.col_max; sb.by_col = 1; sb.fix = fix_b;
-        bool zeroed_other = false;
-        rc = launch_fp16_prepass(a_src, b_src, g, ba, bb, do_a, do_b, sa, sb, SA.row_max, SB.col_max, S.fix_cnt + 2, nullptr, 0, &zeroed_other, mix,
-                                 ci == 0 ? 0 : 1);
-        cx.stream = s_main;
-        if (rc != NB200_OK) return rc;
-        NB_CUDA(cudaEventRecord(P->ev_prep[si], s_help));
-        // ---- the call's stream: product, repair / fallback preparation, gated fallback
-        NB_CUDA(cudaStreamWaitEvent(s_main, P->ev_prep[si], 0));
-        GemmArgs c = g;
-        c.batch = nb;
-        c.A = reinterpret_cast<const float *>(SA.a_hi); c.A_lo = reinterpret_cast<const float *>(SA.a_lo);
-        c.B = reinterpret_cast<const float *>(SB.b_hi); c.B_lo = reinterpret_cast<const float *>(SB.b_lo);
-        c.lda = lda; c.ldb = ldb;
-        c.sA = g.sA ? per_a : 0; c.sB = g.sB ? per_b : 0;
-        c.C = g.C + b0 * g.sC;
-        c.row_max = SA.row_max; c.col_max = SB.col_max;
-        c.gate_want = 0;
-        rc = mix ? launch_fp16_gemm<true>(c, cg, merged) : launch_fp16_gemm<false>(c, cg, merged);
-        if (rc != NB200_OK) return rc;
-        const int64_t s_a = span(ba, g.sA, g.M, g.lda, g.K), s_b = span(bb, g.sB, g.K, g.ldb, g.N);
-        {
-            cudaLaunchConfig_t pc = {};
-            pc.gridDim = dim3((unsigned)(ctx().num_sms * 4));
-            pc.blockDim = dim3(256);
-            pc.stream = s_main;
-            cudaLaunchAttribute pa[1];
-            pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            pa[0].val.programmaticStreamSerializationAllowed = 1;
-            pc.attrs = pa;
-            pc.numAttrs = pdl_enabled() ? 1 : 0;
-            NB_CUDA(cudaLaunchKernelEx(&pc, fp16_post_kernel, g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
-                                       fix_a, fix_b, raw_ok ? S.a_lo32 : (float *)nullptr, s_a, raw_ok ? S.b_lo32 : (float *)nullptr, s_b, nonfinite_flag(),
-                                       ctx().nonfinite_gen, ctx().trace));
-            ctx().launches++;
-        }
-        if (raw_ok) {
-            GemmArgs f = g;
-            f.batch = nb;
-            f.A = a_src; f.A_lo = S.a_lo32; f.B = b_src; f.B_lo = S.b_lo32;
-            f.C = g.C + b0 * g.sC;
-            f.gate_want = 1;
-            if ((rc = dispatch_cfg<3>(f)) != NB200_OK) return rc;
-        } else {
-            dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)nb);
-            sgemm_simt_kernel<<<grid, 256, 0, s_main>>>(g.C + b0 * g.sC, a_src, b_src, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
-                                                        nonfinite_flag() + 1, ctx().nonfinite_gen);
-            NB_LAUNCH_CHECK();
-        }
-        NB_CUDA(cudaEventRecord(P->ev_free[si], s_main));
-    }
-    return NB200_OK;
 }
 
 static int gemm_fp16x3(const GemmArgs &g, bool mix) {
@@ -2182,17 +2037,6 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
     // FP16x3U (mix): one accumulator per chunk, so the merged 256x256 tile is chosen exactly as for BF16x3 (wave quantisation)
     const int bn = v ? (v & 0xFF) * 2 : (cg == 2 ? (mix ? bf16_pair_bn(chunk, g.M, g.N) : fp16_pair_bn(chunk, g.M, g.N)) : 128);
     const bool merged = cg == 2 && bn == 256;
-    {
-        // enough matrices: software-pipeline the pre-pass against the GEMM (not inside a stream capture: a recorded call stays on one stream)
-        cudaStreamCaptureStatus cap0 = cudaStreamCaptureStatusNone;
-        NB_CUDA(cudaStreamIsCapturing(ctx().stream, &cap0));
-        const int64_t per_ws = 4 * ((g.sA ? per_a : 0) + (g.sB ? per_b : 0)) + (raw_ok ? 4 * ((g.sA ? round4(g.sA) : 0) + (g.sB ? round4(g.sB) : 0)) : 0);
-        const int64_t pchunk = cap0 == cudaStreamCaptureStatusNone ? fp16_pipeline_chunk(g, per_ws) : 0;
-        if (pchunk > 0) {
-            const int pbn = v ? bn : (cg == 2 ? (mix ? bf16_pair_bn(pchunk, g.M, g.N) : fp16_pair_bn(pchunk, g.M, g.N)) : 128);
-            return gemm_fp16x3_pipelined(g, mix, pchunk, raw_ok, cg, cg == 2 && pbn == 256);
-        }
-    }
     // workspace offsets follow the FULL chunk size (a shared operand prepared with the first chunk must not move)
     const int64_t na = (g.sA ? chunk : 1) * per_a, nbb = (g.sB ? chunk : 1) * per_b;
     const int64_t rows_layout = round4((g.sA ? chunk : 1) * g.M), cols_layout = round4((g.sB ? chunk : 1) * g.N);   // 16-byte aligned sub-arrays

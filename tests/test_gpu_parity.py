@@ -786,11 +786,12 @@ def test_sgemm_batched_in_several_workspace_chunks(nb, prec, monkeypatch):
 
 @pytest.mark.parametrize("prec", [4, 5, 3])
 @pytest.mark.parametrize("shared", ["none", "B", "A"])
-def test_sgemm_batched_pipelined_prepass_beside_the_gemm(nb, prec, shared):
-    """batch >= 8: the call is cut into >= 4 chunks whose pre-pass runs on a helper stream beside the previous chunk's GEMM (two
-    workspace sets).  Every matrix against cblas_sgemm; an out-of-window element in a LATE chunk (sparse repair), a shared operand
-    that carries a repaired element (its records must survive in workspace set 0 for the whole call), a late chunk with too many
-    out-of-window elements (the whole call falls back: bit-identical to TF32X3), and the same call with the pipeline switched off."""
+def test_sgemm_batched_many_chunks_repair_and_fallback_in_late_chunks(nb, prec, shared, monkeypatch):
+    """13 matrices processed in 13 workspace chunks (1 MiB budget).  Every matrix against cblas_sgemm; an out-of-window element in a
+    LATE chunk (sparse repair), a shared operand that carries a repaired element (prepared once with chunk 0: its records must
+    survive for the whole call), and a late chunk with too many out-of-window elements (that chunk falls back: bit-identical to
+    TF32X3; the flag is per call, so later chunks follow)."""
+    monkeypatch.setenv("NB200_GEMM_WS_BUDGET_MB", "1")
     lib = nb.lib()
     r = _rng(700 + prec)
     batch, M, N, K = 13, 256, 264, 200
