@@ -90,8 +90,8 @@ enum nb200_reduce_order { NB200_ORDER_TREE = 0, NB200_ORDER_SEQUENTIAL = 1 };
 
 /* nd::matmul precision.
  * AUTO (what nd::matmul passes): the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every
- *   input - a scaled half-precision split (FP16X3 or FP16X3U, see nb200_gemm_resolve_precision) for K >= 128,
- *   TF32X3 below (pre-pass not worth it) and for shapes too small for the tensor path.
+ *   input - FP16X3U for K >= 128 (nb200_gemm_resolve_precision; NB200_GEMM_AUTO_MODE overrides), TF32X3 below (pre-pass not
+ *   worth it) and for shapes too small for the tensor path.
  * TF32X3: error-compensated 3-pass TF32 on the tcgen05 tensor pipe; guaranteed bound ~3*2^-22 per product
  *   (+ chunked round-to-nearest accumulation).  Also what the FP16X3 / FP16X3U device-side fallback runs.
  * TF32X1: single pass, fast mode (~7e-4); not a parity mode.
@@ -252,6 +252,11 @@ int nb200_shard_synchronize(void);
  * root array itself: no copy).  Ordered after / before the work on the context streams involved. */
 int nb200_shard_scatter(float *const *shard_ptrs, const float *root_src, int64_t rows, int64_t row_elems, int root, int transport);
 int nb200_shard_gather(float *root_dst, const float *const *shard_ptrs, int64_t rows, int64_t row_elems, int root, int transport);
+/* sharded `gpu()` / `cpu()` (NDArray_ToGPU / NDArray_ToCPU, ndarray.c:1037-1093, are one blocking copy to the current device): host
+ * array <-> row shards, every shard over its own device's PCIe link, all links at once, asynchronous on the context streams for
+ * pinned host memory (nb200_host_alloc); nb200_shard_synchronize() completes them. */
+int nb200_shard_upload(float *const *shard_ptrs, const float *host_src, int64_t rows, int64_t row_elems);
+int nb200_shard_download(float *host_dst, const float *const *shard_ptrs, int64_t rows, int64_t row_elems);
 /* resident shards, same-shape operands: one launch per device, no collective (arithmetics.c:160-926 per shard) */
 int nb200_shard_ew_binary(int op, float *const *out, const float *const *a, const float *const *b, int64_t rows, int64_t row_elems);
 int nb200_shard_ew_mul_add(float *const *out, const float *const *a, const float *const *b, const float *const *c, int64_t rows,

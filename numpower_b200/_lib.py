@@ -70,6 +70,8 @@ ABI = {
     "nb200_shard_split": (C.c_int, [i64, C.c_int, C.c_int, i64p, i64p]), "nb200_shard_synchronize": (C.c_int, []),
     "nb200_shard_scatter": (C.c_int, [C.c_void_p, fp, i64, i64, C.c_int, C.c_int]),
     "nb200_shard_gather": (C.c_int, [fp, C.c_void_p, i64, i64, C.c_int, C.c_int]),
+    "nb200_shard_upload": (C.c_int, [C.c_void_p, fp, i64, i64]),
+    "nb200_shard_download": (C.c_int, [fp, C.c_void_p, i64, i64]),
     "nb200_shard_ew_binary": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, i64, i64]),
     "nb200_shard_ew_mul_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64, i64]),
     "nb200_shard_ew_unary": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, i64, i64, C.c_float, C.c_float]),

@@ -2144,21 +2144,23 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
     return NB200_OK;
 }
 
-// AUTO = the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every input: FP16x3 (per product
-// <= 3 * 2^-22 plus the chunked accumulation; measured ~3e-6),
-// whose out-of-window handling (sparse repair / gated TF32x3 fallback) is decided on the device.  TF32x3 has the same
-// class of bound at half the tensor rate and is what AUTO uses for K < 128 (pre-pass not worth it) and what the FP16x3
-// fallback runs.  BF16x3 is as fast as FP16x3 but its bound is only statistical: each product may be off by up to
-// 2^-16 + 2 * 2^-17 (dropped a2.b2 and the split remainders) - zero-mean, so it averages out over K for ordinary data
-// (measured 1.2-2.5e-6) but adds up coherently for e.g. constant matrices (tests/test_gemm_split_model.py: 4.7 % of random
-// constant pairs exceed 1e-5).  It has to be asked for: precision = NB200_GEMM_BF16X3 per call.
-// NB200_GEMM_AUTO_MODE = tf32x3 | bf16x3 | fp16x3 overrides what AUTO stands for at K >= 128.
+// AUTO = the fastest mode whose error bound GUARANTEES 1e-5 against cblas_sgemm for every input: FP16x3U - half hi parts of
+// row-scaled A / column-scaled B plus UNSCALED half lo parts, all three products of a 256-long k-chunk in one TMEM accumulator,
+// merged 256x256 tile (per product <= 2^-18 + 2^-22 at the edge of its 2^-21 window, 3 * 2^-22 near the row / column maximum;
+// measured ~2e-6), out-of-window elements repaired / gated TF32x3 fallback decided on the device.  Measured on B200 against FP16x3
+// (2^11-scaled lo parts, 256x128 tile, 2^-28 window): 4096^3 0.334 vs 0.338 ms, 8192^3 2.36 vs 2.55 ms, 2048^3 0.074 vs 0.096 ms.
+// TF32x3 has a tighter bound at half the tensor rate and is what AUTO uses for K < 128 (pre-pass not worth it) and what the
+// fallback runs.  BF16x3 is faster still but its bound is only statistical: each product may be off by up to 2^-16 + 2 * 2^-17
+// (dropped a2.b2 and the split remainders) - zero-mean, so it averages out over K for ordinary data (measured 1.2-2.5e-6) but adds
+// up coherently for e.g. constant matrices (tests/test_gemm_split_model.py: 4.7 % of random constant pairs exceed 1e-5).  It has
+// to be asked for: precision = NB200_GEMM_BF16X3 per call.
+// NB200_GEMM_AUTO_MODE = tf32x3 | bf16x3 | fp16x3 | fp16x3u overrides what AUTO stands for at K >= 128.
 int gemm_resolve_precision(int precision, int64_t K) {
     if (precision != NB200_GEMM_AUTO) return precision;
     static const char *mode = getenv("NB200_GEMM_AUTO_MODE");
-    static const int fast = !mode ? NB200_GEMM_FP16X3 : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
+    static const int fast = !mode ? NB200_GEMM_FP16X3U : strcmp(mode, "bf16x3") == 0 ? NB200_GEMM_BF16X3
                                   : strcmp(mode, "tf32x3") == 0 ? NB200_GEMM_TF32X3
-                                  : strcmp(mode, "fp16x3u") == 0 ? NB200_GEMM_FP16X3U : NB200_GEMM_FP16X3;
+                                  : strcmp(mode, "fp16x3") == 0 ? NB200_GEMM_FP16X3 : NB200_GEMM_FP16X3U;
     return K >= 128 ? fast : NB200_GEMM_TF32X3;
 }
 
@@ -2179,7 +2181,7 @@ static int gemm_impl(GemmArgs g, int precision) {
     if (precision == NB200_GEMM_FP16X3U && bf16_ok && !force_simt) return gemm_fp16x3(g, true);
     // TF32X3 asked for on operands the TF32 path cannot read (4-byte aligned views, ld % 4 != 0): the FP16x3 pre-pass
     // repacks them, same class of guaranteed bound, so they stay on the tensor pipe instead of the fp32 SIMT kernel
-    if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g, false);
+    if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g, true);
     if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_FP16X3U) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
         dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);

@@ -249,6 +249,46 @@ extern "C" int nb200_shard_scatter(float *const *shard_ptrs, const float *root_s
     return NB200_OK;
 }
 
+// ---- sharded residency: `$a->gpu()` / `->cpu()` of an array that lives as row shards on every GPU --------------------------------
+// The reference moves an array with ONE blocking cudaMemcpy to / from the current device (NDArray_ToGPU / NDArray_ToCPU,
+// src/ndarray.c:1037-1093).  Here every shard travels over its OWN device's PCIe link, all links at once: G copies are enqueued
+// on the G context streams (asynchronous for pinned host memory, nb200_host_alloc), so the aggregate host<->device rate is up to G
+// times one link's.  Ordered with the other work on each context stream; nb200_shard_synchronize() (or any blocking call) makes
+// the host buffer reusable / the downloaded data visible.
+extern "C" int nb200_shard_upload(float *const *shard_ptrs, const float *host_src, int64_t rows, int64_t row_elems) {
+    int rc = check_init("nb200_shard_upload");
+    if (rc != NB200_OK) return rc;
+    if (!shard_ptrs || !host_src || rows < 0 || row_elems < 0) return set_error(NB200_EINVAL, "nb200_shard_upload: bad argument");
+    DeviceScope scope;
+    for (int s = 0; s < g.n; s++) {
+        int64_t lo, cnt;
+        shard_range(rows, g.n, s, &lo, &cnt);
+        const int64_t bytes = cnt * row_elems * 4;
+        if (bytes == 0) continue;
+        if (!shard_ptrs[s]) return set_error(NB200_EINVAL, "nb200_shard_upload: shard %d has %lld rows but no buffer", s, (long long)cnt);
+        NB_CUDA(cudaSetDevice(g.dev[s]));
+        NB_CUDA(cudaMemcpyAsync(shard_ptrs[s], host_src + lo * row_elems, (size_t)bytes, cudaMemcpyHostToDevice, ctx_of(g.dev[s])->stream));
+    }
+    return NB200_OK;
+}
+
+extern "C" int nb200_shard_download(float *host_dst, const float *const *shard_ptrs, int64_t rows, int64_t row_elems) {
+    int rc = check_init("nb200_shard_download");
+    if (rc != NB200_OK) return rc;
+    if (!shard_ptrs || !host_dst || rows < 0 || row_elems < 0) return set_error(NB200_EINVAL, "nb200_shard_download: bad argument");
+    DeviceScope scope;
+    for (int s = 0; s < g.n; s++) {
+        int64_t lo, cnt;
+        shard_range(rows, g.n, s, &lo, &cnt);
+        const int64_t bytes = cnt * row_elems * 4;
+        if (bytes == 0) continue;
+        if (!shard_ptrs[s]) return set_error(NB200_EINVAL, "nb200_shard_download: shard %d has %lld rows but no buffer", s, (long long)cnt);
+        NB_CUDA(cudaSetDevice(g.dev[s]));
+        NB_CUDA(cudaMemcpyAsync(host_dst + lo * row_elems, shard_ptrs[s], (size_t)bytes, cudaMemcpyDeviceToHost, ctx_of(g.dev[s])->stream));
+    }
+    return NB200_OK;
+}
+
 extern "C" int nb200_shard_gather(float *root_dst, const float *const *shard_ptrs, int64_t rows, int64_t row_elems, int root, int transport) {
     int rc = check_init("nb200_shard_gather");
     if (rc != NB200_OK) return rc;

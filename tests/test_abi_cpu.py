@@ -71,8 +71,8 @@ def test_gemm_auto_resolves_to_the_guaranteed_mode_by_default(monkeypatch):
     monkeypatch.delenv("NB200_GEMM_AUTO_MODE", raising=False)
     import numpower_b200 as nb
     lib = nb.lib()
-    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 4096) == nb.FP16X3
-    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 128) == nb.FP16X3
+    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 4096) == nb.FP16X3U
+    assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 128) == nb.FP16X3U
     assert lib.nb200_gemm_resolve_precision(nb.GEMM_AUTO, 16) == nb.TF32X3
     for mode in (nb.TF32X3, nb.TF32X1, nb.BF16X3, nb.FP16X3):
         assert lib.nb200_gemm_resolve_precision(mode, 4096) == mode

@@ -60,6 +60,31 @@ def test_scatter_gather_round_trip_is_bit_exact(grp, transport):
             np.testing.assert_array_equal(back.cpu().numpy(), a)
 
 
+def test_sharded_upload_download_round_trip_and_use(grp):
+    """nb200_shard_upload / nb200_shard_download: the sharded `gpu()` / `cpu()` - host array <-> row shards over every device's own
+    PCIe link (pinned and pageable host memory), bit-exact, and the uploaded shards feed a sharded op directly (stream order)."""
+    g, nb, torch = grp
+    lib = nb.lib()
+    r = np.random.default_rng(15)
+    for rows, cols, pinned in ((1000, 37, True), (7, 4096, False), (max(g.n - 1, 1), 3, True), (2053, 1024, True)):
+        a = r.random((rows, cols), dtype=np.float32)
+        host = torch.from_numpy(a.copy())
+        if pinned:
+            host = host.pin_memory()
+        shards = g.empty_shards(rows, (cols,))
+        assert lib.nb200_shard_upload(g.ptrs(shards), host.data_ptr(), rows, cols) == 0, lib.nb200_last_error()
+        out = g.empty_shards(rows, (cols,))
+        assert lib.nb200_shard_ew_binary(2, g.ptrs(out), g.ptrs(shards), g.ptrs(shards), rows, cols) == 0, lib.nb200_last_error()   # a * a
+        back = torch.empty(rows, cols)
+        if pinned:
+            back = back.pin_memory()
+        assert lib.nb200_shard_download(back.data_ptr(), g.ptrs(out), rows, cols) == 0, lib.nb200_last_error()
+        g.synchronize()
+        for s, (lo, hi) in enumerate(g.split(rows)):
+            np.testing.assert_array_equal(shards[s].cpu().numpy(), a[lo:hi])
+        np.testing.assert_array_equal(back.numpy(), ORACLE.binary("mul", a, a))
+
+
 def test_sharded_elementwise_matches_oracle(grp):
     g, nb, torch = grp
     lib = nb.lib()
