@@ -40,9 +40,30 @@ nd.matmul(A(r.random((5, 7), dtype=np.float32)).gpu(), A(r.random((7, 3), dtype=
 if os.environ.get("SANITIZE_16BIT", "1") == "1":
     # 16-bit operand modes: odd K / N (repacking split), merged 256-column tile incl. the split tail, scaled half mode
     m3, m4 = A(r.random((300, 137), dtype=np.float32)).gpu(), A(r.random((137, 201), dtype=np.float32)).gpu()
-    for prec in (nb.BF16X3, nb.FP16X3):
+    for prec in (nb.BF16X3, nb.FP16X3, nb.FP16X3U):
         nd.matmul(m1, m2, prec).toArray(); nd.matmul(m3, m4, prec).toArray()
         nd.matmul(A(r.random((512, 160), dtype=np.float32)).gpu(), A(r.random((160, 512), dtype=np.float32)).gpu(), prec).toArray()
         nd.matmul(A(r.random((3, 260, 72), dtype=np.float32)).gpu(), A(r.random((3, 72, 264), dtype=np.float32)).gpu(), prec).toArray()
+    # out-of-window elements: sparse repair (records spread over the grid) and the gated TF32x3 fallback, both 16-bit scaled modes
+    m5 = r.random((300, 256), dtype=np.float32) + 0.25
+    m6 = r.random((256, 264), dtype=np.float32) + 0.25
+    m5[17, 5] = 2.0 ** -40; m6[30, 21] = 2.0 ** -40
+    m7 = m5.copy(); m7[:40, :128] *= np.float32(2.0 ** -40)
+    for prec in (nb.FP16X3, nb.FP16X3U):
+        nd.matmul(A(m5).gpu(), A(m6).gpu(), prec).toArray(); nd.matmul(A(m7).gpu(), A(m6).gpu(), prec).toArray()
 nd.dot(m1, A(r.random(136, dtype=np.float32)).gpu()).toArray()
+# boolean reductions, transpose, in-place elementwise (out == in), CUDA-graph capture / replay
+nd.all(big); nd.allclose(big, big); nd.all(a[1]); nd.allclose(a[1], a[2])
+import ctypes as C
+lib = nb.lib()
+t_in, t_out = A(r.random((33, 65), dtype=np.float32)).gpu(), A(np.zeros((65, 33), np.float32)).gpu()
+assert lib.nb200_transpose2d(t_out.data_ptr, t_in.data_ptr, 33, 65) == 0
+assert lib.nb200_ew_unary(1, big.data_ptr, big.data_ptr, big.size, 0.0, 0.0) == 0
+shp, st = (C.c_int64 * 1)(big.size), (C.c_int64 * 1)(1)
+assert lib.nb200_ew_binary(0, big.data_ptr, big.data_ptr, big.data_ptr, 1, shp, st, st) == 0
+assert lib.nb200_graph_begin() == 0
+assert lib.nb200_ew_binary(2, big.data_ptr, big.data_ptr, big.data_ptr, 1, shp, st, st) == 0
+g = C.c_void_p()
+assert lib.nb200_graph_end(C.byref(g)) == 0
+assert lib.nb200_graph_launch(g) == 0 and lib.nb200_synchronize() == 0 and lib.nb200_graph_destroy(g) == 0
 print("sanitizer targets done;", nb.lib().nb200_launch_count(), "launches")
