@@ -1294,23 +1294,35 @@ __device__ __forceinline__ void store_group_a(const float4 &a, const float4 &b, 
     st_l2(lo, make_uint4(l0.x, l0.y, l1.x, l1.y), pol);
 }
 // Rows of A held in registers: TPR threads per row, 256 / TPR rows per CTA pass, up to two groups per thread (row length <= 16 * TPR).
+// Software-pipelined over the passes: the loads of pass i+1 are issued before pass i is reduced, split and stored, so a CTA always
+// has a row batch in flight (without it every pass was load -> wait -> compute -> store with nothing outstanding during the last
+// three: ncu showed the pre-pass at 50 % of the DRAM rate, latency-bound).
 template <int TPR, bool MIX>
 __device__ __forceinline__ void prep_a_rows(const PrepCoop &q, int rank, int n_ctas, int *nonfinite, int gen, unsigned int (*red)[8], uint64_t pol) {
     constexpr int RPC = 256 / TPR;                         // rows per CTA pass
     const int t = threadIdx.x % TPR, rg = threadIdx.x / TPR, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n8 = q.a.s.cols >> 3;
-    int it = 0;
-    for (int64_t base = (int64_t)rank * RPC; base < q.a_rows; base += (int64_t)n_ctas * RPC, it++) {   // uniform trip count over the CTA
+    const int64_t stride = (int64_t)n_ctas * RPC;
+    const float4 *in4 = reinterpret_cast<const float4 *>(q.a.s.in);
+    auto load = [&](int64_t base, float4 (&dst)[2][2]) {
         const int64_t r = base + rg;
-        const bool live = r < q.a_rows;
-        const float4 *s4 = reinterpret_cast<const float4 *>(q.a.s.in) + r * (2 * n8);
-        float4 v[2][2];
-        unsigned int m = 0;
+        if (r >= q.a_rows) return;
+        const float4 *s4 = in4 + r * (2 * n8);
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int64_t g = t + u * TPR;
-            if (live && g < n8) { v[u][0] = ldg_stream_l2(s4 + 2 * g, pol); v[u][1] = ldg_stream_l2(s4 + 2 * g + 1, pol); }
+            if (g < n8) { dst[u][0] = ldg_stream_l2(s4 + 2 * g, pol); dst[u][1] = ldg_stream_l2(s4 + 2 * g + 1, pol); }
         }
+    };
+    float4 v[2][2], nv[2][2];
+    int64_t base = (int64_t)rank * RPC;
+    if (base < q.a_rows) load(base, v);
+    int it = 0;
+    for (; base < q.a_rows; base += stride, it++) {   // uniform trip count over the CTA
+        if (base + stride < q.a_rows) load(base + stride, nv);
+        const int64_t r = base + rg;
+        const bool live = r < q.a_rows;
+        unsigned int m = 0;
 #pragma unroll
         for (int u = 0; u < 2; u++)
             if (live && t + u * TPR < n8) m = max(m, abs8_bits(v[u][0], v[u][1]));
@@ -1322,16 +1334,19 @@ __device__ __forceinline__ void prep_a_rows(const PrepCoop &q, int rank, int n_c
 #pragma unroll
             for (int w = 0; w < TPR / 32; w++) m = max(m, red[it & 1][rg * (TPR / 32) + w]);
         }
-        if (!live) continue;
-        if (t == 0) q.row_max_out[r] = m;
-        const int e = scale_exp(m);
-        const Pow2Pair sc = scale_factors(e);
-        uint4 *hi = reinterpret_cast<uint4 *>(q.a.s.hi) + r * n8, *lo = reinterpret_cast<uint4 *>(q.a.s.lo) + r * n8;
+        if (live) {
+            if (t == 0) q.row_max_out[r] = m;
+            const int e = scale_exp(m);
+            const Pow2Pair sc = scale_factors(e);
+            uint4 *hi = reinterpret_cast<uint4 *>(q.a.s.hi) + r * n8, *lo = reinterpret_cast<uint4 *>(q.a.s.lo) + r * n8;
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int64_t g = t + u * TPR;
-            if (g < n8) store_group_a<MIX>(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
+            for (int u = 0; u < 2; u++) {
+                const int64_t g = t + u * TPR;
+                if (g < n8) store_group_a<MIX>(v[u][0], v[u][1], e, sc, hi + g, lo + g, nonfinite, gen, q.a.fix, r, g << 3, pol);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 2; u++) { v[u][0] = nv[u][0]; v[u][1] = nv[u][1]; }
     }
 }
 // rows longer than 4096: one CTA per row, pass 1 reduces the |max|, pass 2 re-reads the row (L1 / L2: this CTA just read it) and splits
@@ -1380,7 +1395,7 @@ __device__ __forceinline__ void prep_a_rows_long(const PrepCoop &q, int rank, in
     }
 }
 template <bool MIX>
-__global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, int *__restrict__ nonfinite, int gen) {
+__global__ void __launch_bounds__(256, 3) prep16_coop_kernel(const PrepCoop q, int *__restrict__ nonfinite, int gen) {
     __shared__ unsigned int red[2][8];
     const int t = threadIdx.x;
     pdl_wait();   // launched with programmatic stream serialization: the operands / control blocks belong to earlier work until here
@@ -1482,14 +1497,14 @@ __global__ void __launch_bounds__(256, 4) prep16_coop_kernel(const PrepCoop q, i
         const float4 *src = reinterpret_cast<const float4 *>(q.b.s.in) + mat * K * n4 + c4;
         uint2 *hi = reinterpret_cast<uint2 *>(q.b.s.hi) + mat * K * n4 + c4, *lo = reinterpret_cast<uint2 *>(q.b.s.lo) + mat * K * n4 + c4;
         const int64_t r0 = seg * per, r1 = r0 + per < K ? r0 + per : K;
-        // rows r1-1-ty, r1-1-ty-TY, ... >= r0, four in flight
+        // rows r1-1-ty, r1-1-ty-TY, ... >= r0, eight in flight
         int64_t r = r1 - 1 - ty;
-        for (; r - 3 * TY >= r0; r -= 4 * TY) {
-            float4 v[4];
+        for (; r - 7 * TY >= r0; r -= 8 * TY) {
+            float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = ldg_stream_l2(src + (r - u * TY) * n4, pol);   // last use of the raw tile
+            for (int u = 0; u < 8; u++) v[u] = ldg_stream_l2(src + (r - u * TY) * n4, pol);   // last use of the raw tile
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int64_t rr = r - u * TY;
                 uint2 h, l;
                 if (split4_fast<MIX>(v[u], s0, s1, s2, s3, h, l)) {

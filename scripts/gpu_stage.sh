@@ -23,6 +23,15 @@ for stage in "$@"; do
     timeline:*) for prec in $(echo ${stage#timeline:} | tr , ' '); do
          timeout 300 python scripts/gemm_timeline.py $prec 4096x4096x4096 8192x8192x8192 2048x2048x2048 > gpurun_out/${tag}_timeline_$prec.jsonl 2> gpurun_out/${tag}_timeline_$prec.err; cut -c1-1200 gpurun_out/${tag}_timeline_$prec.jsonl; tail -2 gpurun_out/${tag}_timeline_$prec.err; done ;;
     memcheck) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitizer_targets.py > gpurun_out/${tag}_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/${tag}_memcheck.log ;;
+    prepbw) for bw in 100 150 200 250; do
+         NB200_PREP_BW=$bw timeout 200 python scripts/gemm_timeline.py 5 4096x4096x4096 2048x2048x2048 > gpurun_out/${tag}_timeline_bw$bw.jsonl 2> gpurun_out/${tag}_timeline_bw$bw.err
+         python - <<PY
+import json
+for ln in open("gpurun_out/${tag}_timeline_bw$bw.jsonl"):
+    d = json.loads(ln); t = d["timeline_us"]
+    print("bw $bw", d["M"], "period", round(d["ms_per_call_back_to_back"], 4), "A done", t["prep_phaseA_done"], "B1", t["prep_phaseB1_done"], "prep done", t["prep_last_cta_done"], "gemm", t["gemm_first_cta_past_wait"], "->", t["gemm_last_cta_done"])
+PY
+       done ;;
     synccheck) timeout 1500 compute-sanitizer --tool synccheck --error-exitcode 9 python scripts/sanitizer_targets.py > gpurun_out/${tag}_synccheck.log 2>&1; echo "synccheck rc=$?"; tail -4 gpurun_out/${tag}_synccheck.log ;;
     multi:*) bash scripts/gpu_multi.sh ${stage#multi:} $tag ;;
     *) echo "unknown stage $stage" ;;
