@@ -1968,8 +1968,9 @@ static int launch_fp16_prepass(const float *a_src, const float *b_src, const Gem
         if (grid > a_ctas + b_ctas) grid = a_ctas + b_ctas;
         if (grid < 2) grid = 2;
         // CTAs per operand in proportion to the bytes each side moves through L2: A is read once and written once (8 B per element),
-        // B is read twice and written once (12 B per element; NB200_PREP_BW overrides the B weight in percent of A's, default 150)
-        static const int64_t bw = getenv("NB200_PREP_BW") ? atoll(getenv("NB200_PREP_BW")) : 150;
+        // B is read twice and written once (12 B per element; NB200_PREP_BW overrides the B weight in percent of A's).  Measured with
+        // the software-pipelined A rows (4096^2, pre-pass end): 100 -> 63.8 us, 150 -> 57.3, 200 -> 50.3, 250 -> 55.6.
+        static const int64_t bw = getenv("NB200_PREP_BW") ? atoll(getenv("NB200_PREP_BW")) : 200;
         const int64_t wa = a_elems * 100, wb = b_elems * bw;
         int64_t n_b = a_elems == 0 ? grid : b_elems == 0 ? 0 : (int64_t)(((double)grid * (double)wb) / ((double)wa + (double)wb) + 0.5);
         if (a_elems > 0 && b_elems > 0) { if (n_b < 1) n_b = 1; if (n_b > grid - 1) n_b = grid - 1; }
