@@ -627,6 +627,8 @@ def run_single(args):
                 "mode": "NB200_GEMM_AUTO (" + ("the host pipeline keeps the TF32x3 kernels: PCIe-bound, per-row-block splits" if auto_name in ("fp16x3", "fp16x3u") else auto_name) + ")",
                 "pcie_bound_ms": 2 * nbytes / pcie["h2d_GBps"] / 1e6,
                 "pcie_bound_duplex_ms": nbytes / pcie["h2d_GBps"] / 1e6 + nbytes / pcie["duplex_each_GBps"] / 1e6,
+                "frac_of_pcie_bound": (2 * nbytes / pcie["h2d_GBps"] / 1e6) / ms_e2e,
+                "frac_of_pcie_bound_duplex": (nbytes / pcie["h2d_GBps"] / 1e6 + nbytes / pcie["duplex_each_GBps"] / 1e6) / ms_e2e,
                 "note": "H2D of A and B (128 MiB) is the floor; the D2H of C overlaps the second half of it, where the link runs at its measured "
                         "duplex rate (pcie_bound_duplex_ms)"},
         "gpu_launches": int(launches_timed),
@@ -744,13 +746,32 @@ def run_multi(args):
     t_h2d = B.time_steps(lambda: dbuf.copy_(pin, non_blocking=True), 3, 1)
     device_barrier()
     h2d_gbps = pin.numel() * 4 / t_h2d / 1e6
-    del dbuf
+    # ... and with the D2H of C running against it (the pipeline's steady state: both directions of the link busy)
+    dbuf2 = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    pin2 = hc.view(-1)[: 64 << 20]
+    side = torch.cuda.Stream()
+
+    def duplex():
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pin2.copy_(dbuf2, non_blocking=True)
+        dbuf.copy_(pin, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
+    device_barrier()
+    t_dup = B.time_steps(duplex, 3, 1)
+    device_barrier()
+    dup_gbps = pin.numel() * 4 / t_dup / 1e6
+    # floor of one step: the D2H bytes overlap as many H2D bytes at the duplex rate, the remaining H2D bytes run at the one-way rate
+    floor_duplex_ms = nbytes / dup_gbps / 1e6 + nbytes / h2d_gbps / 1e6
+    del dbuf, dbuf2
     t2 = torch.tensor([my_e2e], device="cuda")
     dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = float(t2.item())
     e2e_rank = [None] * world
     dist.all_gather_object(e2e_rank, {"rank": rank, "ms_per_step": my_e2e, "h2d_GBps_under_contention": h2d_gbps,
-                                      "pcie_bound_ms": 2 * nbytes / h2d_gbps / 1e6, "frac_of_pcie_bound": (2 * nbytes / h2d_gbps / 1e6) / my_e2e}, group=cpu_pg)
+                                      "duplex_each_GBps_under_contention": dup_gbps,
+                                      "pcie_bound_ms": 2 * nbytes / h2d_gbps / 1e6, "frac_of_pcie_bound": (2 * nbytes / h2d_gbps / 1e6) / my_e2e,
+                                      "pcie_bound_duplex_ms": floor_duplex_ms, "frac_of_pcie_bound_duplex": floor_duplex_ms / my_e2e}, group=cpu_pg)
     del a, b, ha, hb, hc
     torch.cuda.empty_cache()
 

@@ -13,6 +13,6 @@ except Exception as e:
 print("N", d["n_gpus"], "value", round(d["value"], 1), "ms", round(d["ms_per_step"], 3), "base", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in d["scaling_base"].items() if k != "workload"})
 for r in d["per_rank"]: print("  rank", r["rank"], round(r["ms_per_step"], 3), {k: r["clocks"].get(k) for k in ("sm_mhz", "sm_min_mhz", "power_w_max", "power_w_median", "reasons")})
 for k, v in d["roofline"]["per_config"].items(): print("  sharded", k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items()})
-print("  e2e", round(d["e2e"]["value"], 1), round(d["e2e"]["ms_per_step"], 2), [(r["rank"], round(r["ms_per_step"], 2), round(r["h2d_GBps_under_contention"], 1), round(r["frac_of_pcie_bound"], 2)) for r in d["e2e"]["per_rank"]])
+print("  e2e", round(d["e2e"]["value"], 1), round(d["e2e"]["ms_per_step"], 2), [(r["rank"], round(r["ms_per_step"], 2), round(r["h2d_GBps_under_contention"], 1), round(r.get("duplex_each_GBps_under_contention", 0), 1), round(r["frac_of_pcie_bound"], 2), round(r.get("frac_of_pcie_bound_duplex", 0), 2)) for r in d["e2e"]["per_rank"]])
 print("  scatter_gather", json.dumps(d["scatter_gather"])[:1500])
 PY
