@@ -684,6 +684,10 @@ def test_config3_chain_full_size_properties(nb):
     s_rows = nb.nd.sum(nb.nd.sum(P, 1))
     s_cols = nb.nd.sum(nb.nd.sum(P, 0))
     assert s_full == s_rows == s_cols == float(p.astype(np.float64).sum())
+    # ... and the axis sums themselves against the oracle (exact set: every summation order gives the same bits)
+    np.testing.assert_array_equal(nb.nd.sum(P, 0).toArray(), oracle.port.reduce_axis("sum", p, 0))
+    np.testing.assert_array_equal(nb.nd.sum(P, 1).toArray(), oracle.port.reduce_axis("sum", p, 1))
+    assert s_full == float(ORACLE.reduce_full("sum", p))
 
 
 def test_config4_sum_argmax_2pow28(nb):
@@ -691,11 +695,14 @@ def test_config4_sum_argmax_2pow28(nb):
     x = _set_p(n, 8)
     A = nb.NDArray.array(x).gpu()
     assert nb.nd.sum(A) == float(x.astype(np.float64).sum())   # exact set: any order gives the same integer
+    assert nb.nd.sum(A) == float(ORACLE.reduce_full("sum", x))  # the reference's own sequential fp32 loop on the full 2^28 input
     x[123456789] = 7.0
     x[200000001] = 7.0
     A = nb.NDArray.array(x).gpu()
     assert nb.nd.argmax(A) == float(np.float32(123456789))
     assert nb.nd.argmin(A) == float(np.argmin(x))
+    assert nb.nd.argmax(A) == float(ORACLE.argminmax(True, x)) and nb.nd.argmin(A) == float(ORACLE.argminmax(False, x))
+    assert nb.nd.max(A) == float(ORACLE.reduce_full("max", x)) and nb.nd.min(A) == float(ORACLE.reduce_full("min", x))
 
 
 def test_config2_matmul_4096_checksum(nb):
