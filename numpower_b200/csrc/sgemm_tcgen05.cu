@@ -127,6 +127,13 @@ struct GemmCfg {
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
 
+// Out-of-window elements of the scaled half modes (see split_f16): records the split pre-pass appends, one list per operand.
+constexpr int FIX_CAP = 4096;              // records per operand and chunk
+struct FixList {
+    unsigned int *count;                   // device counter (reset by the host before the operand is split)
+    int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
+};
+
 struct GemmParams {
     float *C;
     int64_t M, N, K, ldc, strideC;
@@ -146,6 +153,12 @@ struct GemmParams {
     int nonfinite_gen;         // this call's tag (a fresh value per call instead of a memset per call)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
     unsigned long long *trace; // optional timeline stamps (common.cuh), nullptr normally
+    // SCALED + MERGED: the sparse repair of out-of-window elements happens IN THE EPILOGUE (C += d * partner row / column of the
+    // other RAW fp32 operand, after the scaling, before the store) instead of in the post kernel behind the GEMM: epi_repair != 0
+    int epi_repair;
+    FixList fix_a, fix_b;
+    const float *rawA, *rawB;  // the call's original operands (this chunk), with their leading dimensions / batch strides
+    int64_t raw_lda, raw_ldb, raw_sA, raw_sB;
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -465,6 +478,12 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         uint32_t acc_phase = 0;
         int epi_tile = 0;   // tiles this CTA has started (parity selects the column-factor buffer, SCALED + MERGED)
         (void)epi_tile;
+        // in-epilogue repair: the record lists were written by the pre-pass, complete since griddepcontrol.wait returned
+        unsigned int fix_na = 0, fix_nb = 0;
+        if (Cfg::SCALED && Cfg::MERGED && p.epi_repair) {
+            fix_na = min(*reinterpret_cast<volatile unsigned int *>(p.fix_a.count), (unsigned int)FIX_CAP);
+            fix_nb = min(*reinterpret_cast<volatile unsigned int *>(p.fix_b.count), (unsigned int)FIX_CAP);
+        }
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -585,6 +604,32 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                             for (int q = 0; q < 128; q++)
                                 if (colh + q < p.N) crow[colh + q] = tot[q];
+                        }
+                        // Sparse repair of the recorded out-of-window elements (normally there are none: one uniform branch), on the row
+                        // segment this thread has just stored - it owns these elements, so plain read-modify-writes do (the running
+                        // totals stay in registers: indexing tot[] at run time would move the whole array to local memory).
+                        // A-record (i, k, d): C[i, :] += d * B[k, :]; B-record (k, j, d): C[:, j] += A[:, k] * d, raw fp32 partners.
+                        if constexpr (Cfg::SCALED) {
+                            if ((fix_na | fix_nb) != 0u) {
+                                const int64_t arow = (p.a_batched ? b * p.M : 0) + row;
+                                const int64_t ncol = p.N - colh < 128 ? p.N - colh : 128;
+                                for (unsigned int rr = 0; rr < fix_na; rr++) {
+                                    const int4 rec = p.fix_a.recs[rr];
+                                    if ((int64_t)rec.x != arow) continue;
+                                    const float d = __int_as_float(rec.z);
+                                    const float *brow = p.rawB + (p.b_batched ? b * p.raw_sB : 0) + (int64_t)rec.y * p.raw_ldb + colh;
+                                    for (int64_t q = 0; q < ncol; q++) crow[colh + q] = fmaf(d, brow[q], crow[colh + q]);
+                                }
+                                for (unsigned int rr = 0; rr < fix_nb; rr++) {
+                                    const int4 rec = p.fix_b.recs[rr];
+                                    const int64_t bk = p.b_batched ? (int64_t)rec.x / p.K : 0;
+                                    if (p.b_batched && bk != b) continue;
+                                    const int64_t jj = (int64_t)rec.y - colh;
+                                    if (jj < 0 || jj >= ncol) continue;
+                                    const int64_t k = (int64_t)rec.x - bk * p.K;
+                                    crow[colh + jj] += p.rawA[(p.a_batched ? b * p.raw_sA : 0) + row * p.raw_lda + k] * __int_as_float(rec.z);
+                                }
+                            }
                         }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -1137,11 +1182,6 @@ __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restri
 // zeroes the element's half parts, and the post kernel adds a times the partner row / column of the other (raw fp32)
 // operand to C after the GEMM (a sparse rank-1 repair in full fp32 precision).  Only when a record list overflows is
 // the call marked ineligible (nonfinite[1] = gen) and left to the gated fallback (see gemm_fp16x3).
-constexpr int FIX_CAP = 4096;              // records per operand and chunk
-struct FixList {
-    unsigned int *count;                   // device counter (reset by the host before the operand is split)
-    int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
-};
 // MIX (GemmCfg::MIXLO): the lo part is stored UNSCALED, lo = rn_f16(a' - hi): remainder <= max(2^-22 |a'|, 2^-25), and the window
 // closes at |a'| = 2^-6 (remainder <= 2^-19 |a'|) instead of 2^-14.
 template <bool MIX>
@@ -1540,15 +1580,18 @@ __global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, c
                                                         int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                                         int64_t ldc, int64_t sA, int64_t sB, int64_t sC, FixList fa, FixList fb,
                                                         float *lo0, int64_t n0, float *lo1, int64_t n1,
-                                                        int *nonfinite, int gen, unsigned long long *trace) {
+                                                        int *nonfinite, int gen, unsigned long long *trace, int repair_done_by_gemm) {
     if (threadIdx.x == 0) trace_min(trace, 8);
+    // the gated fallback behind this kernel may become resident as soon as the GEMM's CTAs leave (it waits for this kernel's
+    // completion itself before it reads the gate or the lo parts)
+    pdl_launch_dependents();
     // Launched with programmatic stream serialization: these reads only touch what the PRE-PASS wrote (complete before any CTA of
     // the GEMM passed its own griddepcontrol.wait, which precedes its launch_dependents).  In the normal case - eligible, no
     // records - the grid leaves at once, while the GEMM is still running; one thread stays to keep completion ordered.
     const bool fallback = *reinterpret_cast<const volatile int *>(nonfinite + 1) == gen;
     const unsigned int na = min(*reinterpret_cast<volatile unsigned int *>(fa.count), (unsigned int)FIX_CAP),
                        nb = min(*reinterpret_cast<volatile unsigned int *>(fb.count), (unsigned int)FIX_CAP);
-    if (!fallback && na + nb == 0) {
+    if (!fallback && (na + nb == 0 || repair_done_by_gemm)) {   // (the merged scaled GEMM repairs in its own epilogue)
         if (blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); trace_max(trace, 9); }
         return;
     }
@@ -1669,6 +1712,10 @@ struct GemmArgs {
     int64_t batch, M, N, K, lda, ldb, ldc, sA, sB, sC;
     const unsigned int *row_max = nullptr, *col_max = nullptr;   // FP16x3 scaling inputs (GemmCfg::SCALED)
     int gate_want = -1;   // -1: ungated; 0: run unless the call was marked ineligible for FP16x3; 1: run only if it was
+    // in-epilogue repair (GemmCfg SCALED + MERGED only): record lists and the raw fp32 operands of this chunk
+    FixList fix_a{nullptr, nullptr}, fix_b{nullptr, nullptr};
+    const float *rawA = nullptr, *rawB = nullptr;
+    int64_t raw_lda = 0, raw_ldb = 0, raw_sA = 0, raw_sB = 0;
 };
 
 static bool pdl_enabled() {
@@ -1725,6 +1772,10 @@ static int launch_gemm(const GemmArgs &g) {
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
     p.debug = reinterpret_cast<unsigned int *>(ctx().host_result) + 4;
     p.trace = ctx().trace;
+    p.epi_repair = (Cfg::SCALED && Cfg::MERGED && g.fix_a.count != nullptr && g.rawA != nullptr) ? 1 : 0;
+    p.fix_a = g.fix_a; p.fix_b = g.fix_b;
+    p.rawA = g.rawA; p.rawB = g.rawB;
+    p.raw_lda = g.raw_lda; p.raw_ldb = g.raw_ldb; p.raw_sA = g.raw_sA; p.raw_sB = g.raw_sB;
     auto kern = sgemm_tf32_kernel<Cfg>;
     // the opt-in shared-memory size is a per-device function attribute (nb200_set_device may move the context)
     static bool attr_set[64] = {};
@@ -2121,6 +2172,13 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
         c.C = g.C + b0 * g.sC;
         c.row_max = row_max; c.col_max = col_max;
         c.gate_want = 0;
+        // the merged tile repairs out-of-window elements in its epilogue (the FP16X3 merged experiment folds per k-block: post kernel)
+        const bool epi_repair = merged && mix;
+        if (epi_repair) {
+            c.fix_a = fix_a; c.fix_b = fix_b;
+            c.rawA = a_src; c.rawB = b_src;
+            c.raw_lda = g.lda; c.raw_ldb = g.ldb; c.raw_sA = g.sA; c.raw_sB = g.sB;
+        }
         rc = mix ? launch_fp16_gemm<true>(c, cg, merged) : launch_fp16_gemm<false>(c, cg, merged);
         if (rc != NB200_OK) return rc;
         // (2) eligible: sparse repair of the recorded out-of-window elements (normally none: returns at once);
@@ -2139,7 +2197,7 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
             pc.numAttrs = pdl_enabled() ? 1 : 0;
             NB_CUDA(cudaLaunchKernelEx(&pc, fp16_post_kernel, g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
                                        fix_a, fix_b, raw_ok ? a_lo32 : (float *)nullptr, s_a, raw_ok ? b_lo32 : (float *)nullptr, s_b, nonfinite_flag(),
-                                       ctx().nonfinite_gen, ctx().trace));
+                                       ctx().nonfinite_gen, ctx().trace, epi_repair ? 1 : 0));
             ctx().launches++;
         }
         // (3) the gated fallback, runs only if the call was marked: TF32x3 on the raw operands, bit-identical to a TF32X3 call
