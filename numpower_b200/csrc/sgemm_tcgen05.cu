@@ -121,7 +121,10 @@ struct GemmCfg {
     static_assert(!BF16_ || PASSES_ == 3, "bf16 operands are only used by the x3 error-compensated mode");
     // SCALED + MERGED: per-tile column scale factors (two floats per column, double-buffered by tile parity) behind the barrier block
     static constexpr int COLFAC_BYTES = (SCALED_ && MERGED_) ? 2 * 256 * 8 : 0;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/ + COLFAC_BYTES;
+    // ... and behind them a copy of the (few) repair records of the call: EPI_FIX_MAX per operand, 16 bytes each
+    static constexpr int EPI_FIX_MAX = 32;
+    static constexpr int FIXREC_BYTES = (SCALED_ && MERGED_) ? 2 * EPI_FIX_MAX * 16 : 0;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/ + COLFAC_BYTES + FIXREC_BYTES;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -478,12 +481,34 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         uint32_t acc_phase = 0;
         int epi_tile = 0;   // tiles this CTA has started (parity selects the column-factor buffer, SCALED + MERGED)
         (void)epi_tile;
-        // in-epilogue repair: the record lists were written by the pre-pass, complete since griddepcontrol.wait returned
+        // In-epilogue repair: the record lists were written by the pre-pass, complete since griddepcontrol.wait returned.  With at
+        // most EPI_FIX_MAX records per operand (the normal case: a handful) the epilogue warps copy them into shared memory once and
+        // every tile checks them there; longer lists are left to the post kernel, which applies the same test to the same counters.
         unsigned int fix_na = 0, fix_nb = 0;
-        if (Cfg::SCALED && Cfg::MERGED && p.epi_repair) {
-            fix_na = min(*reinterpret_cast<volatile unsigned int *>(p.fix_a.count), (unsigned int)FIX_CAP);
-            fix_nb = min(*reinterpret_cast<volatile unsigned int *>(p.fix_b.count), (unsigned int)FIX_CAP);
+        const uint32_t fixrec = bar_base + 384u + (uint32_t)Cfg::COLFAC_BYTES;
+        if constexpr (Cfg::SCALED && Cfg::MERGED) {
+            if (p.epi_repair) {
+                fix_na = *reinterpret_cast<volatile unsigned int *>(p.fix_a.count);
+                fix_nb = *reinterpret_cast<volatile unsigned int *>(p.fix_b.count);
+                if (fix_na > (unsigned int)Cfg::EPI_FIX_MAX || fix_nb > (unsigned int)Cfg::EPI_FIX_MAX) fix_na = fix_nb = 0u;
+                if ((fix_na | fix_nb) != 0u) {   // uniform over the grid
+                    const int et = (int)threadIdx.x - Cfg::EPI_WARP0 * 32;
+                    if (et < Cfg::EPI_FIX_MAX && (unsigned int)et < fix_na) {
+                        const int4 rec = p.fix_a.recs[et];
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fixrec + (uint32_t)et * 16u), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w) : "memory");
+                    } else if (et >= Cfg::EPI_FIX_MAX && et < 2 * Cfg::EPI_FIX_MAX && (unsigned int)(et - Cfg::EPI_FIX_MAX) < fix_nb) {
+                        const int4 rec = p.fix_b.recs[et - Cfg::EPI_FIX_MAX];
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fixrec + (uint32_t)et * 16u), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w) : "memory");
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            }
         }
+        auto fix_rec = [&](unsigned int idx) {   // idx < EPI_FIX_MAX: A-records, then the B-records
+            int4 rec;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(fixrec + idx * 16u));
+            return rec;
+        };
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -614,14 +639,14 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                                 const int64_t arow = (p.a_batched ? b * p.M : 0) + row;
                                 const int64_t ncol = p.N - colh < 128 ? p.N - colh : 128;
                                 for (unsigned int rr = 0; rr < fix_na; rr++) {
-                                    const int4 rec = p.fix_a.recs[rr];
+                                    const int4 rec = fix_rec(rr);
                                     if ((int64_t)rec.x != arow) continue;
                                     const float d = __int_as_float(rec.z);
                                     const float *brow = p.rawB + (p.b_batched ? b * p.raw_sB : 0) + (int64_t)rec.y * p.raw_ldb + colh;
                                     for (int64_t q = 0; q < ncol; q++) crow[colh + q] = fmaf(d, brow[q], crow[colh + q]);
                                 }
                                 for (unsigned int rr = 0; rr < fix_nb; rr++) {
-                                    const int4 rec = p.fix_b.recs[rr];
+                                    const int4 rec = fix_rec((unsigned int)Cfg::EPI_FIX_MAX + rr);
                                     const int64_t bk = p.b_batched ? (int64_t)rec.x / p.K : 0;
                                     if (p.b_batched && bk != b) continue;
                                     const int64_t jj = (int64_t)rec.y - colh;
@@ -1591,7 +1616,10 @@ __global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, c
     const bool fallback = *reinterpret_cast<const volatile int *>(nonfinite + 1) == gen;
     const unsigned int na = min(*reinterpret_cast<volatile unsigned int *>(fa.count), (unsigned int)FIX_CAP),
                        nb = min(*reinterpret_cast<volatile unsigned int *>(fb.count), (unsigned int)FIX_CAP);
-    if (!fallback && (na + nb == 0 || repair_done_by_gemm)) {   // (the merged scaled GEMM repairs in its own epilogue)
+    // (the merged scaled GEMM repairs in its own epilogue when neither list has more than GemmCfg::EPI_FIX_MAX = 32 records)
+    const bool gemm_repaired = repair_done_by_gemm && *reinterpret_cast<volatile unsigned int *>(fa.count) <= 32u &&
+                               *reinterpret_cast<volatile unsigned int *>(fb.count) <= 32u;
+    if (!fallback && (na + nb == 0 || gemm_repaired)) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); trace_max(trace, 9); }
         return;
     }
