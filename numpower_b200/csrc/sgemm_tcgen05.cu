@@ -630,30 +630,40 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                             for (int q = 0; q < 128; q++)
                                 if (colh + q < p.N) crow[colh + q] = tot[q];
                         }
-                        // Sparse repair of the recorded out-of-window elements (normally there are none: one uniform branch), on the row
-                        // segment this thread has just stored - it owns these elements, so plain read-modify-writes do (the running
-                        // totals stay in registers: indexing tot[] at run time would move the whole array to local memory).
-                        // A-record (i, k, d): C[i, :] += d * B[k, :]; B-record (k, j, d): C[:, j] += A[:, k] * d, raw fp32 partners.
-                        if constexpr (Cfg::SCALED) {
-                            if ((fix_na | fix_nb) != 0u) {
-                                const int64_t arow = (p.a_batched ? b * p.M : 0) + row;
-                                const int64_t ncol = p.N - colh < 128 ? p.N - colh : 128;
-                                for (unsigned int rr = 0; rr < fix_na; rr++) {
-                                    const int4 rec = fix_rec(rr);
-                                    if ((int64_t)rec.x != arow) continue;
+                    }
+                    // Sparse repair of the recorded out-of-window elements (normally there are none: one uniform branch) on the tile
+                    // segment this WARP has just stored (32 rows x 128 columns: it owns these elements, plain read-modify-writes do).
+                    // A-record (i, k, d): C[i, :] += d * B[k, :] - the whole warp walks the matching lane's row segment (coalesced; one
+                    // lane alone would pay 128 dependent L2 round trips and hold up the tile).  B-record (k, j, d): C[:, j] += A[:, k] * d,
+                    // one element per lane.  Raw fp32 partners.  The running totals stay in registers (indexing tot[] at run time would
+                    // move the whole array to local memory).
+                    if constexpr (Cfg::SCALED) {
+                        if (last && !idle && (fix_na | fix_nb) != 0u) {   // warp-uniform
+                            __syncwarp();                                 // this warp's stores of the tile are ordered before the repairs
+                            const int64_t colh = col0 + half * 128;
+                            const int64_t arow = (p.a_batched ? b * p.M : 0) + row;
+                            const int64_t ncol = p.N - colh < 128 ? p.N - colh : 128;
+                            for (unsigned int rr = 0; rr < fix_na; rr++) {
+                                const int4 rec = fix_rec(rr);
+                                unsigned int hit = __ballot_sync(0xFFFFFFFFu, row < p.M && (int64_t)rec.x == arow);
+                                while (hit) {
+                                    const int src = __ffs(hit) - 1;
+                                    hit &= hit - 1;
+                                    float *rrow = crow + (int64_t)(src - lane) * p.ldc + colh;   // the matching lane's row segment
                                     const float d = __int_as_float(rec.z);
                                     const float *brow = p.rawB + (p.b_batched ? b * p.raw_sB : 0) + (int64_t)rec.y * p.raw_ldb + colh;
-                                    for (int64_t q = 0; q < ncol; q++) crow[colh + q] = fmaf(d, brow[q], crow[colh + q]);
+                                    for (int64_t q = lane; q < ncol; q += 32) rrow[q] = fmaf(d, brow[q], rrow[q]);
                                 }
-                                for (unsigned int rr = 0; rr < fix_nb; rr++) {
-                                    const int4 rec = fix_rec((unsigned int)Cfg::EPI_FIX_MAX + rr);
-                                    const int64_t bk = p.b_batched ? (int64_t)rec.x / p.K : 0;
-                                    if (p.b_batched && bk != b) continue;
-                                    const int64_t jj = (int64_t)rec.y - colh;
-                                    if (jj < 0 || jj >= ncol) continue;
-                                    const int64_t k = (int64_t)rec.x - bk * p.K;
-                                    crow[colh + jj] += p.rawA[(p.a_batched ? b * p.raw_sA : 0) + row * p.raw_lda + k] * __int_as_float(rec.z);
-                                }
+                            }
+                            __syncwarp();
+                            for (unsigned int rr = 0; rr < fix_nb; rr++) {
+                                const int4 rec = fix_rec((unsigned int)Cfg::EPI_FIX_MAX + rr);
+                                const int64_t bk = p.b_batched ? (int64_t)rec.x / p.K : 0;
+                                if (p.b_batched && bk != b) continue;
+                                const int64_t jj = (int64_t)rec.y - colh;
+                                if (jj < 0 || jj >= ncol || row >= p.M) continue;
+                                const int64_t k = (int64_t)rec.x - bk * p.K;
+                                crow[colh + jj] += p.rawA[(p.a_batched ? b * p.raw_sA : 0) + row * p.raw_lda + k] * __int_as_float(rec.z);
                             }
                         }
                     }
