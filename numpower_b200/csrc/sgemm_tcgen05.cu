@@ -121,20 +121,10 @@ struct GemmCfg {
     static_assert(!BF16_ || PASSES_ == 3, "bf16 operands are only used by the x3 error-compensated mode");
     // SCALED + MERGED: per-tile column scale factors (two floats per column, double-buffered by tile parity) behind the barrier block
     static constexpr int COLFAC_BYTES = (SCALED_ && MERGED_) ? 2 * 256 * 8 : 0;
-    // ... and behind them a copy of the (few) repair records of the call: EPI_FIX_MAX per operand, 16 bytes each
-    static constexpr int EPI_FIX_MAX = 32;
-    static constexpr int FIXREC_BYTES = (SCALED_ && MERGED_) ? 2 * EPI_FIX_MAX * 16 : 0;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/ + COLFAC_BYTES + FIXREC_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 384 /*barriers*/ + COLFAC_BYTES;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
-};
-
-// Out-of-window elements of the scaled half modes (see split_f16): records the split pre-pass appends, one list per operand.
-constexpr int FIX_CAP = 4096;              // records per operand and chunk
-struct FixList {
-    unsigned int *count;                   // device counter (reset by the host before the operand is split)
-    int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
 };
 
 struct GemmParams {
@@ -156,12 +146,6 @@ struct GemmParams {
     int nonfinite_gen;         // this call's tag (a fresh value per call instead of a memset per call)
     unsigned int *debug;       // [0] = timeout flag, [1..] = info
     unsigned long long *trace; // optional timeline stamps (common.cuh), nullptr normally
-    // SCALED + MERGED: the sparse repair of out-of-window elements happens IN THE EPILOGUE (C += d * partner row / column of the
-    // other RAW fp32 operand, after the scaling, before the store) instead of in the post kernel behind the GEMM: epi_repair != 0
-    int epi_repair;
-    FixList fix_a, fix_b;
-    const float *rawA, *rawB;  // the call's original operands (this chunk), with their leading dimensions / batch strides
-    int64_t raw_lda, raw_ldb, raw_sA, raw_sB;
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -481,34 +465,6 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         uint32_t acc_phase = 0;
         int epi_tile = 0;   // tiles this CTA has started (parity selects the column-factor buffer, SCALED + MERGED)
         (void)epi_tile;
-        // In-epilogue repair: the record lists were written by the pre-pass, complete since griddepcontrol.wait returned.  With at
-        // most EPI_FIX_MAX records per operand (the normal case: a handful) the epilogue warps copy them into shared memory once and
-        // every tile checks them there; longer lists are left to the post kernel, which applies the same test to the same counters.
-        unsigned int fix_na = 0, fix_nb = 0;
-        const uint32_t fixrec = bar_base + 384u + (uint32_t)Cfg::COLFAC_BYTES;
-        if constexpr (Cfg::SCALED && Cfg::MERGED) {
-            if (p.epi_repair) {
-                fix_na = *reinterpret_cast<volatile unsigned int *>(p.fix_a.count);
-                fix_nb = *reinterpret_cast<volatile unsigned int *>(p.fix_b.count);
-                if (fix_na > (unsigned int)Cfg::EPI_FIX_MAX || fix_nb > (unsigned int)Cfg::EPI_FIX_MAX) fix_na = fix_nb = 0u;
-                if ((fix_na | fix_nb) != 0u) {   // uniform over the grid
-                    const int et = (int)threadIdx.x - Cfg::EPI_WARP0 * 32;
-                    if (et < Cfg::EPI_FIX_MAX && (unsigned int)et < fix_na) {
-                        const int4 rec = p.fix_a.recs[et];
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fixrec + (uint32_t)et * 16u), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w) : "memory");
-                    } else if (et >= Cfg::EPI_FIX_MAX && et < 2 * Cfg::EPI_FIX_MAX && (unsigned int)(et - Cfg::EPI_FIX_MAX) < fix_nb) {
-                        const int4 rec = p.fix_b.recs[et - Cfg::EPI_FIX_MAX];
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(fixrec + (uint32_t)et * 16u), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w) : "memory");
-                    }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
-            }
-        }
-        auto fix_rec = [&](unsigned int idx) {   // idx < EPI_FIX_MAX: A-records, then the B-records
-            int4 rec;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(fixrec + idx * 16u));
-            return rec;
-        };
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.strideC & 3) == 0);
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         for (int64_t t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -629,42 +585,6 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
                             for (int q = 0; q < 128; q++)
                                 if (colh + q < p.N) crow[colh + q] = tot[q];
-                        }
-                    }
-                    // Sparse repair of the recorded out-of-window elements (normally there are none: one uniform branch) on the tile
-                    // segment this WARP has just stored (32 rows x 128 columns: it owns these elements, plain read-modify-writes do).
-                    // A-record (i, k, d): C[i, :] += d * B[k, :] - the whole warp walks the matching lane's row segment (coalesced; one
-                    // lane alone would pay 128 dependent L2 round trips and hold up the tile).  B-record (k, j, d): C[:, j] += A[:, k] * d,
-                    // one element per lane.  Raw fp32 partners.  The running totals stay in registers (indexing tot[] at run time would
-                    // move the whole array to local memory).
-                    if constexpr (Cfg::SCALED) {
-                        if (last && !idle && (fix_na | fix_nb) != 0u) {   // warp-uniform
-                            __syncwarp();                                 // this warp's stores of the tile are ordered before the repairs
-                            const int64_t colh = col0 + half * 128;
-                            const int64_t arow = (p.a_batched ? b * p.M : 0) + row;
-                            const int64_t ncol = p.N - colh < 128 ? p.N - colh : 128;
-                            for (unsigned int rr = 0; rr < fix_na; rr++) {
-                                const int4 rec = fix_rec(rr);
-                                unsigned int hit = __ballot_sync(0xFFFFFFFFu, row < p.M && (int64_t)rec.x == arow);
-                                while (hit) {
-                                    const int src = __ffs(hit) - 1;
-                                    hit &= hit - 1;
-                                    float *rrow = crow + (int64_t)(src - lane) * p.ldc + colh;   // the matching lane's row segment
-                                    const float d = __int_as_float(rec.z);
-                                    const float *brow = p.rawB + (p.b_batched ? b * p.raw_sB : 0) + (int64_t)rec.y * p.raw_ldb + colh;
-                                    for (int64_t q = lane; q < ncol; q += 32) rrow[q] = fmaf(d, brow[q], rrow[q]);
-                                }
-                            }
-                            __syncwarp();
-                            for (unsigned int rr = 0; rr < fix_nb; rr++) {
-                                const int4 rec = fix_rec((unsigned int)Cfg::EPI_FIX_MAX + rr);
-                                const int64_t bk = p.b_batched ? (int64_t)rec.x / p.K : 0;
-                                if (p.b_batched && bk != b) continue;
-                                const int64_t jj = (int64_t)rec.y - colh;
-                                if (jj < 0 || jj >= ncol || row >= p.M) continue;
-                                const int64_t k = (int64_t)rec.x - bk * p.K;
-                                crow[colh + jj] += p.rawA[(p.a_batched ? b * p.raw_sA : 0) + row * p.raw_lda + k] * __int_as_float(rec.z);
-                            }
                         }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -1217,6 +1137,11 @@ __global__ void __launch_bounds__(256) absmax_cols4_kernel(const float *__restri
 // zeroes the element's half parts, and the post kernel adds a times the partner row / column of the other (raw fp32)
 // operand to C after the GEMM (a sparse rank-1 repair in full fp32 precision).  Only when a record list overflows is
 // the call marked ineligible (nonfinite[1] = gen) and left to the gated fallback (see gemm_fp16x3).
+constexpr int FIX_CAP = 4096;              // records per operand and chunk
+struct FixList {
+    unsigned int *count;                   // device counter (reset by the host before the operand is split)
+    int4 *recs;                            // {row (over batch * rows), column, float bits of d, 0}
+};
 // MIX (GemmCfg::MIXLO): the lo part is stored UNSCALED, lo = rn_f16(a' - hi): remainder <= max(2^-22 |a'|, 2^-25), and the window
 // closes at |a'| = 2^-6 (remainder <= 2^-19 |a'|) instead of 2^-14.
 template <bool MIX>
@@ -1604,6 +1529,11 @@ __global__ void __launch_bounds__(256, 3) prep16_coop_kernel(const PrepCoop q, i
     if (t == 0) trace_max(q.trace, 4);
 }
 
+// (Tried and removed, measured on one box, profiles/r2_summary.md: doing the repair in the merged GEMM's own epilogue - records in
+//  shared memory, the warp walking a matching row segment together - so that this kernel always leaves at once.  The tail after the
+//  GEMM shrank from 12 to 2.5 us, but the read-modify-writes at the end of the affected tiles (a record touches 16 tiles) sit on the
+//  epilogue's critical path: 4096^3 0.336 -> 0.340 ms, 2048^3 / 8192^3 unchanged.  Releasing the dependents of this kernel early
+//  changed nothing either.)
 // After the FP16x3 GEMM, one launch, exactly one of two jobs:
 //  * the call stayed eligible: sparse repair of the recorded out-of-window elements (see split_f16), one block per
 //    record.  A-record (i, k, d): C[i, :] += d * B[k, :]; B-record (k, j, d): C[:, j] += A[:, k] * d.  A record of an operand
@@ -1615,21 +1545,15 @@ __global__ void __launch_bounds__(256) fp16_post_kernel(float *__restrict__ C, c
                                                         int64_t batch, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                                         int64_t ldc, int64_t sA, int64_t sB, int64_t sC, FixList fa, FixList fb,
                                                         float *lo0, int64_t n0, float *lo1, int64_t n1,
-                                                        int *nonfinite, int gen, unsigned long long *trace, int repair_done_by_gemm) {
+                                                        int *nonfinite, int gen, unsigned long long *trace) {
     if (threadIdx.x == 0) trace_min(trace, 8);
-    // the gated fallback behind this kernel may become resident as soon as the GEMM's CTAs leave (it waits for this kernel's
-    // completion itself before it reads the gate or the lo parts)
-    pdl_launch_dependents();
     // Launched with programmatic stream serialization: these reads only touch what the PRE-PASS wrote (complete before any CTA of
     // the GEMM passed its own griddepcontrol.wait, which precedes its launch_dependents).  In the normal case - eligible, no
     // records - the grid leaves at once, while the GEMM is still running; one thread stays to keep completion ordered.
     const bool fallback = *reinterpret_cast<const volatile int *>(nonfinite + 1) == gen;
     const unsigned int na = min(*reinterpret_cast<volatile unsigned int *>(fa.count), (unsigned int)FIX_CAP),
                        nb = min(*reinterpret_cast<volatile unsigned int *>(fb.count), (unsigned int)FIX_CAP);
-    // (the merged scaled GEMM repairs in its own epilogue when neither list has more than GemmCfg::EPI_FIX_MAX = 32 records)
-    const bool gemm_repaired = repair_done_by_gemm && *reinterpret_cast<volatile unsigned int *>(fa.count) <= 32u &&
-                               *reinterpret_cast<volatile unsigned int *>(fb.count) <= 32u;
-    if (!fallback && (na + nb == 0 || gemm_repaired)) {
+    if (!fallback && na + nb == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { pdl_wait(); trace_max(trace, 9); }
         return;
     }
@@ -1750,10 +1674,6 @@ struct GemmArgs {
     int64_t batch, M, N, K, lda, ldb, ldc, sA, sB, sC;
     const unsigned int *row_max = nullptr, *col_max = nullptr;   // FP16x3 scaling inputs (GemmCfg::SCALED)
     int gate_want = -1;   // -1: ungated; 0: run unless the call was marked ineligible for FP16x3; 1: run only if it was
-    // in-epilogue repair (GemmCfg SCALED + MERGED only): record lists and the raw fp32 operands of this chunk
-    FixList fix_a{nullptr, nullptr}, fix_b{nullptr, nullptr};
-    const float *rawA = nullptr, *rawB = nullptr;
-    int64_t raw_lda = 0, raw_ldb = 0, raw_sA = 0, raw_sB = 0;
 };
 
 static bool pdl_enabled() {
@@ -1810,10 +1730,6 @@ static int launch_gemm(const GemmArgs &g) {
     // pinned host memory (device-visible under UVA): survives a trap so the host can report which wait timed out
     p.debug = reinterpret_cast<unsigned int *>(ctx().host_result) + 4;
     p.trace = ctx().trace;
-    p.epi_repair = (Cfg::SCALED && Cfg::MERGED && g.fix_a.count != nullptr && g.rawA != nullptr) ? 1 : 0;
-    p.fix_a = g.fix_a; p.fix_b = g.fix_b;
-    p.rawA = g.rawA; p.rawB = g.rawB;
-    p.raw_lda = g.raw_lda; p.raw_ldb = g.raw_ldb; p.raw_sA = g.raw_sA; p.raw_sB = g.raw_sB;
     auto kern = sgemm_tf32_kernel<Cfg>;
     // the opt-in shared-memory size is a per-device function attribute (nb200_set_device may move the context)
     static bool attr_set[64] = {};
@@ -2210,13 +2126,6 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
         c.C = g.C + b0 * g.sC;
         c.row_max = row_max; c.col_max = col_max;
         c.gate_want = 0;
-        // the merged tile repairs out-of-window elements in its epilogue (the FP16X3 merged experiment folds per k-block: post kernel)
-        const bool epi_repair = merged && mix;
-        if (epi_repair) {
-            c.fix_a = fix_a; c.fix_b = fix_b;
-            c.rawA = a_src; c.rawB = b_src;
-            c.raw_lda = g.lda; c.raw_ldb = g.ldb; c.raw_sA = g.sA; c.raw_sB = g.sB;
-        }
         rc = mix ? launch_fp16_gemm<true>(c, cg, merged) : launch_fp16_gemm<false>(c, cg, merged);
         if (rc != NB200_OK) return rc;
         // (2) eligible: sparse repair of the recorded out-of-window elements (normally none: returns at once);
@@ -2235,7 +2144,7 @@ static int gemm_fp16x3(const GemmArgs &g, bool mix) {
             pc.numAttrs = pdl_enabled() ? 1 : 0;
             NB_CUDA(cudaLaunchKernelEx(&pc, fp16_post_kernel, g.C + b0 * g.sC, a_src, b_src, nb, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA, g.sB, g.sC,
                                        fix_a, fix_b, raw_ok ? a_lo32 : (float *)nullptr, s_a, raw_ok ? b_lo32 : (float *)nullptr, s_b, nonfinite_flag(),
-                                       ctx().nonfinite_gen, ctx().trace, epi_repair ? 1 : 0));
+                                       ctx().nonfinite_gen, ctx().trace));
             ctx().launches++;
         }
         // (3) the gated fallback, runs only if the call was marked: TF32x3 on the raw operands, bit-identical to a TF32X3 call
