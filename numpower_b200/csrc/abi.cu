@@ -6,6 +6,11 @@
 #include <unordered_map>
 #include <map>
 #include <cstdlib>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 namespace nb200 {
 
@@ -126,6 +131,7 @@ int ensure_gemm_ws(int64_t bytes) {
 }
 
 void host_pipeline_release(int device);   // host_pipeline.cu: staging buffers, streams and events of that device
+void staging_release(int device);         // below: pinned staging slots of the pageable-copy path
 
 static void shutdown_device(int device) {
     Ctx &c = g_ctxs[device];
@@ -133,6 +139,7 @@ static void shutdown_device(int device) {
     cudaSetDevice(device);
     cudaStreamSynchronize(c.stream);
     host_pipeline_release(device);
+    staging_release(device);
     if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
     if (c.scratch) cudaFree(c.scratch);
     if (c.gemm_ws) cudaFree(c.gemm_ws);
@@ -343,9 +350,158 @@ extern "C" int nb200_free(void *dev_ptr) {
     return NB200_OK;
 }
 
+// ---- `$a->gpu()` / `->cpu()` from PAGEABLE host memory (SURVEY.md section 8 f, N3) ---------------------------------------------
+// PHP's arrays are emalloc'd, i.e. pageable.  A plain cudaMemcpy from pageable memory goes through the driver's single-threaded
+// staging copy: measured on the B200 boxes 10.3 GB/s host-to-device and 21.2 GB/s device-to-host against 55.5 / 57.1 GB/s for
+// pinned memory (scripts/pageable_probe.py).  Large pageable copies are therefore staged HERE: chunks move through a ring of pinned
+// slots, a small pool of worker threads does the pageable <-> pinned memcpy of a chunk in parallel slices, and the DMA of chunk i
+// runs while chunk i+1 is being staged.  Pinned / registered / managed pointers and small copies take the direct path.
+// NB200_STAGE_THREADS (default 8, 0 = always the direct path), NB200_STAGE_CHUNK_MB (default 8).
+namespace nb200 {
+class CopyPool {
+  public:
+    explicit CopyPool(int workers) {
+        for (int i = 0; i < workers; i++) threads_.emplace_back([this, i] { run(i); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    // memcpy(dst, src, n) cut into workers + 1 slices (the caller copies the first one)
+    void copy(char *dst, const char *src, size_t n) {
+        const size_t parts = threads_.size() + 1;
+        if (parts == 1 || n < ((size_t)1 << 20)) { memcpy(dst, src, n); return; }
+        const size_t per = ((n / parts) + 4095) & ~size_t(4095);
+        { std::lock_guard<std::mutex> lk(m_); dst_ = dst; src_ = src; n_ = n; per_ = per; pending_ = (int)threads_.size(); gen_++; }
+        cv_.notify_all();
+        memcpy(dst, src, per < n ? per : n);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+  private:
+    void run(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            char *dst; const char *src; size_t n, per;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                dst = dst_; src = src_; n = n_; per = per_;
+            }
+            const size_t off = (size_t)(idx + 1) * per;
+            if (off < n) memcpy(dst + off, src + off, n - off < per ? n - off : per);
+            { std::lock_guard<std::mutex> lk(m_); if (--pending_ == 0) done_.notify_one(); }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    char *dst_ = nullptr; const char *src_ = nullptr;
+    size_t n_ = 0, per_ = 0;
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+struct Staging {
+    static constexpr int SLOTS = 3;
+    char *slot[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr};
+    size_t chunk = 0;
+    bool ok = false;
+};
+static Staging g_stage[NB200_MAX_DEVICES];
+static CopyPool *g_copy_pool = nullptr;
+static int stage_threads() {
+    static const int n = getenv("NB200_STAGE_THREADS") ? atoi(getenv("NB200_STAGE_THREADS")) : 8;
+    return n < 0 ? 0 : (n > 32 ? 32 : n);
+}
+// host pointer the DMA engines cannot read directly (plain malloc / emalloc memory)?
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static int staging_get(Staging **out) {
+    const int dev = ctx().device;
+    if (dev < 0 || dev >= NB200_MAX_DEVICES) return set_error(NB200_EINVAL, "device index out of range");
+    Staging &S = g_stage[dev];
+    if (!S.ok) {
+        static const size_t mb = getenv("NB200_STAGE_CHUNK_MB") ? (size_t)atoll(getenv("NB200_STAGE_CHUNK_MB")) : 8;
+        S.chunk = (mb < 1 ? 1 : mb) << 20;
+        for (int i = 0; i < Staging::SLOTS; i++) {
+            if (cudaMallocHost(reinterpret_cast<void **>(&S.slot[i]), S.chunk) != cudaSuccess) {
+                cudaGetLastError();
+                return set_error(NB200_ENOMEM, "pinned staging allocation failed");
+            }
+            NB_CUDA(cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming));
+        }
+        S.ok = true;
+    }
+    if (!g_copy_pool) g_copy_pool = new CopyPool(stage_threads() - 1);
+    *out = &S;
+    return NB200_OK;
+}
+void staging_release(int device) {   // nb200_shutdown
+    if (device < 0 || device >= NB200_MAX_DEVICES) return;
+    Staging &S = g_stage[device];
+    for (int i = 0; i < Staging::SLOTS; i++) {
+        if (S.slot[i]) cudaFreeHost(S.slot[i]);
+        if (S.ev[i]) cudaEventDestroy(S.ev[i]);
+    }
+    S = Staging();
+}
+static int staged_copy(char *dev, char *host, size_t bytes, bool to_device) {
+    Staging *S = nullptr;
+    int rc = staging_get(&S);
+    if (rc != NB200_OK) return rc;
+    cudaStream_t st = ctx().stream;
+    const size_t C = S->chunk;
+    const size_t nchunks = (bytes + C - 1) / C;
+    if (to_device) {
+        for (size_t i = 0; i < nchunks; i++) {
+            const int sl = (int)(i % Staging::SLOTS);
+            const size_t off = i * C, n = bytes - off < C ? bytes - off : C;
+            if (i >= (size_t)Staging::SLOTS) NB_CUDA(cudaEventSynchronize(S->ev[sl]));   // the DMA that last read this slot is done
+            g_copy_pool->copy(S->slot[sl], host + off, n);
+            NB_CUDA(cudaMemcpyAsync(dev + off, S->slot[sl], n, cudaMemcpyHostToDevice, st));
+            NB_CUDA(cudaEventRecord(S->ev[sl], st));
+        }
+        NB_CUDA(cudaStreamSynchronize(st));
+    } else {
+        // DMA of chunk i + 1 and i + 2 in flight while chunk i is copied out of its slot
+        size_t issued = 0;
+        auto issue = [&](size_t i) -> int {
+            const int sl = (int)(i % Staging::SLOTS);
+            const size_t off = i * C, n = bytes - off < C ? bytes - off : C;
+            NB_CUDA(cudaMemcpyAsync(S->slot[sl], dev + off, n, cudaMemcpyDeviceToHost, st));
+            NB_CUDA(cudaEventRecord(S->ev[sl], st));
+            return NB200_OK;
+        };
+        for (; issued < nchunks && issued < (size_t)Staging::SLOTS - 1; issued++)
+            if ((rc = issue(issued)) != NB200_OK) return rc;
+        for (size_t i = 0; i < nchunks; i++) {
+            if (issued < nchunks) { if ((rc = issue(issued)) != NB200_OK) return rc; issued++; }
+            const int sl = (int)(i % Staging::SLOTS);
+            const size_t off = i * C, n = bytes - off < C ? bytes - off : C;
+            NB_CUDA(cudaEventSynchronize(S->ev[sl]));
+            g_copy_pool->copy(host + off, S->slot[sl], n);
+        }
+    }
+    return NB200_OK;
+}
+static bool use_staging(const void *host, int64_t bytes) {
+    return stage_threads() > 0 && bytes >= ((int64_t)16 << 20) && is_pageable(host);
+}
+}  // namespace nb200
+
 extern "C" int nb200_copy_h2d(void *dev_dst, const void *host_src, int64_t bytes) {
     NB_READY();
     if (bytes < 0 || (bytes > 0 && (!dev_dst || !host_src))) return set_error(NB200_EINVAL, "nb200_copy_h2d: bad argument");
+    if (use_staging(host_src, bytes))
+        return staged_copy(static_cast<char *>(dev_dst), const_cast<char *>(static_cast<const char *>(host_src)), (size_t)bytes, true);
     NB_CUDA(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, ctx().stream));
     NB_CUDA(cudaStreamSynchronize(ctx().stream));
     return NB200_OK;
@@ -354,6 +510,8 @@ extern "C" int nb200_copy_h2d(void *dev_dst, const void *host_src, int64_t bytes
 extern "C" int nb200_copy_d2h(void *host_dst, const void *dev_src, int64_t bytes) {
     NB_READY();
     if (bytes < 0 || (bytes > 0 && (!host_dst || !dev_src))) return set_error(NB200_EINVAL, "nb200_copy_d2h: bad argument");
+    if (use_staging(host_dst, bytes))
+        return staged_copy(const_cast<char *>(static_cast<const char *>(dev_src)), static_cast<char *>(host_dst), (size_t)bytes, false);
     NB_CUDA(cudaMemcpyAsync(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx().stream));
     NB_CUDA(cudaStreamSynchronize(ctx().stream));
     return NB200_OK;

@@ -1102,3 +1102,27 @@ def test_transpose2d_and_the_legacy_in_place_call(nb, rc):
     np.testing.assert_array_equal(_fetch(nb, dx, (cols, rows)), x.T)
     for p in (dx, do):
         lib.nb200_free(p)
+
+
+# --------------------------------------------------------------------- residency: `$a->gpu()` / `->cpu()` from pageable memory (N3)
+@pytest.mark.parametrize("nbytes", [(16 << 20) - 4, (16 << 20), (16 << 20) + 12, (40 << 20) + 4, (100 << 20) + 4092])
+def test_pageable_copies_staged_through_pinned_slots_are_bit_exact(nb, nbytes):
+    """nb200_copy_h2d / nb200_copy_d2h from pageable host memory: >= 16 MiB goes through the pinned staging ring with the
+    multi-threaded slice copy (abi.cu), smaller copies and pinned pointers take the direct path; chunk tails, slot reuse."""
+    import ctypes as C
+    lib = nb.lib()
+    n = nbytes // 4
+    src = _rng(nbytes % 1000).integers(0, 1 << 31, size=n, dtype=np.int64).astype(np.uint32).view(np.float32)   # arbitrary bit patterns
+    back = np.zeros(n, np.float32)
+    p = C.c_void_p()
+    assert lib.nb200_alloc(C.byref(p), n * 4) == 0
+    assert lib.nb200_copy_h2d(p, src.ctypes.data, n * 4) == 0, lib.nb200_last_error()
+    assert lib.nb200_copy_d2h(back.ctypes.data, p, n * 4) == 0, lib.nb200_last_error()
+    np.testing.assert_array_equal(back.view(np.uint32), src.view(np.uint32))
+    # through a pinned buffer (direct path) the device holds the same bits
+    hp = C.c_void_p()
+    assert lib.nb200_host_alloc(C.byref(hp), n * 4) == 0
+    assert lib.nb200_copy_d2h(hp, p, n * 4) == 0
+    pinned = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n,))
+    np.testing.assert_array_equal(pinned, src.view(np.uint32))
+    assert lib.nb200_host_free(hp) == 0 and lib.nb200_free(p) == 0
