@@ -13,6 +13,10 @@
  *   NDArray_Maximum / NDArray_Minimum                     -> nb200_glue_binary   (the reference throws "not implemented for GPU")
  *   NDArray_MaxAxis                                       -> nb200_glue_max_axis (the reference throws "GPU NDArray_MaxAxis not implemented")
  *   NDArray_Dot (N-D . 1-D)                               -> nb200_glue_dot      (every leading row, not only the last matrix)
+ *   NDArray_ToGPU / NDArray_ToCPU                         -> nb200_glue_to_gpu / _to_cpu (the reference calls cudaMemcpy on emalloc'd,
+ *                                                            i.e. pageable, memory: 10 / 21 GB/s; nb200_copy_h2d / d2h stage large
+ *                                                            copies through pinned slots with worker threads: 37-40 GB/s; and no
+ *                                                            zero-filled host copy is allocated first, ndarray.c:1051)
  *
  * Unary methods need no host patch: the legacy NDArrayMathGPU_ElementWise* drivers in libnb200.so recognise the
  * cuda_float_<op> pointer the PHP method passes (numpower.c:1648-3348) and run the op out of place.
@@ -182,6 +186,32 @@ NDArray *nb200_glue_dot(NDArray *nda, NDArray *ndb) {
     NDArray *r = gpu_result(oshape, nd - 1);
     if (nb200_gemv(NDArray_FDATA(r), NDArray_FDATA(nda), NDArray_FDATA(ndb), rows, cols) != NB200_OK || nb200_synchronize() != NB200_OK) {
         glue_throw("nb200_gemv"); NDArray_FREE(r); return NULL;
+    }
+    return r;
+}
+
+/* NDArray_ToGPU ndarray.c:1037-1068 / NDArray_ToCPU :1075-1093 for host <-> device moves (device -> device and host -> host copies
+ * stay with the reference's NDArray_Copy).  nb200_copy_h2d / d2h are blocking, like the cudaMemcpy + cudaDeviceSynchronize they replace. */
+NDArray *nb200_glue_to_gpu(NDArray *target) {
+    if (NDArray_DEVICE(target) != NDARRAY_DEVICE_CPU || NDArray_NDIM(target) > NB200_MAX_DIMS) return NULL;
+    int64_t shape[NB200_MAX_DIMS];
+    for (int i = 0; i < NDArray_NDIM(target); i++) shape[i] = NDArray_SHAPE(target)[i];
+    NDArray *r = gpu_result(shape, NDArray_NDIM(target));
+    if (r == NULL) return NULL;
+    if (nb200_copy_h2d(NDArray_FDATA(r), NDArray_FDATA(target), (int64_t) NDArray_NUMELEMENTS(target) * (int64_t) sizeof(float)) != NB200_OK) {
+        glue_throw("nb200_copy_h2d"); NDArray_FREE(r); return NULL;
+    }
+    return r;
+}
+
+NDArray *nb200_glue_to_cpu(NDArray *target) {
+    if (NDArray_DEVICE(target) != NDARRAY_DEVICE_GPU) return NULL;
+    int *sh = emalloc(sizeof(int) * (NDArray_NDIM(target) > 0 ? NDArray_NDIM(target) : 1));
+    memcpy(sh, NDArray_SHAPE(target), sizeof(int) * NDArray_NDIM(target));
+    NDArray *r = NDArray_Empty(sh, NDArray_NDIM(target), NDARRAY_TYPE_FLOAT32, NDARRAY_DEVICE_CPU);
+    if (r == NULL) return NULL;
+    if (nb200_copy_d2h(NDArray_FDATA(r), NDArray_FDATA(target), (int64_t) NDArray_NUMELEMENTS(target) * (int64_t) sizeof(float)) != NB200_OK) {
+        glue_throw("nb200_copy_d2h"); NDArray_FREE(r); return NULL;
     }
     return r;
 }

@@ -14,7 +14,9 @@ DECL = ('\n#include <nb200.h>\n'
         'NDArray *nb200_glue_argminmax(NDArray *op, int axis, bool keepdims, bool is_argmax);\n'
         'NDArray *nb200_glue_matmul(NDArray *a, NDArray *b);\n'
         'NDArray *nb200_glue_max_axis(NDArray *target, int axis);\n'
-        'NDArray *nb200_glue_dot(NDArray *nda, NDArray *ndb);\n')
+        'NDArray *nb200_glue_dot(NDArray *nda, NDArray *ndb);\n'
+        'NDArray *nb200_glue_to_gpu(NDArray *target);\n'
+        'NDArray *nb200_glue_to_cpu(NDArray *target);\n')
 
 # file -> [(regex matching the function's definition line incl. "{", code inserted after it)]
 PATCHES = {
@@ -29,7 +31,9 @@ PATCHES = {
     "src/ndarray.c": [(r"^reduce\(NDArray \*array, int \*axis, NDArray \*\(\*operation\)\(NDArray \*, NDArray \*\)\) \{", "REDUCE"),
                       (r"^NDArray_MaxAxis\(NDArray \*target, int axis\) \{", "MAXAXIS"),
                       (r"^NDArray_Maximum\(NDArray \*a, NDArray \*b\) \{", "NB200_MAXIMUM"),
-                      (r"^NDArray_Minimum\(NDArray \*a, NDArray \*b\) \{", "NB200_MINIMUM")],
+                      (r"^NDArray_Minimum\(NDArray \*a, NDArray \*b\) \{", "NB200_MINIMUM"),
+                      (r"^NDArray_ToGPU\(NDArray \*target\) \{", "TOGPU"),
+                      (r"^NDArray_ToCPU\(NDArray \*target\) \{", "TOCPU")],
     "src/ndmath/calculation.c": [(r"^NDArray_ArgMinMaxCommon\(NDArray \*op, int axis, bool keepdims, bool is_argmax\) \{", "ARG")],
     "src/ndmath/linalg.c": [(r"^NDArray_Matmul\(NDArray \*a, NDArray \*b\) \{", "MATMUL"),
                             (r"^NDArray_Dot\(NDArray \*nda, NDArray \*ndb\) \{", "DOT")],
@@ -43,6 +47,10 @@ def snippet(kind):
         return "    { NDArray *nb200_r = nb200_glue_reduce(array, axis, operation); if (nb200_r != NULL) return nb200_r; }\n"
     if kind == "ARG":
         return ("    if (NDArray_DEVICE(op) == NDARRAY_DEVICE_GPU) return nb200_glue_argminmax(op, axis, keepdims, is_argmax);\n")
+    if kind == "TOGPU":
+        return "    { NDArray *nb200_r = nb200_glue_to_gpu(target); if (nb200_r != NULL) return nb200_r; }\n"
+    if kind == "TOCPU":
+        return "    { NDArray *nb200_r = nb200_glue_to_cpu(target); if (nb200_r != NULL) return nb200_r; }\n"
     if kind == "MAXAXIS":
         return "    if (NDArray_DEVICE(target) == NDARRAY_DEVICE_GPU) return nb200_glue_max_axis(target, axis);\n"
     if kind == "DOT":

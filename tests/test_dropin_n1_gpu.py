@@ -123,3 +123,14 @@ def test_unary_methods_run_out_of_place_in_one_kernel():
     got, n = _count(lambda: oracle.dropin_n1.unary("clip", x, 1.0, 5.0))
     eq(got, oracle.ref.unary("clip", x, 1.0, 5.0))
     assert n == 1
+
+
+def test_gpu_and_cpu_moves_go_through_the_staged_copies():
+    """ndarray.c:1037-1093: NDArray_ToGPU / NDArray_ToCPU (every test of this file moves its operands through them).  A 24 MiB
+    operand is above the staging threshold: pageable -> pinned slots -> device and back, bit-exact; the sum is checked too."""
+    r = _rng(9)
+    a = (r.integers(-64, 65, size=(3, 1 << 21)).astype(np.float32) / 64)      # 24 MiB, exactly summable
+    b = (r.integers(-64, 65, size=(3, 1 << 21)).astype(np.float32) / 64)
+    got = oracle.dropin_n1.binary("add", a, b)
+    np.testing.assert_array_equal(got, oracle.ref.binary("add", a, b))
+    assert oracle.dropin_n1.reduce_full("sum", a) == oracle.ref.reduce_full("sum", a)
