@@ -1793,6 +1793,9 @@ static int dispatch_cfg(const GemmArgs &g) {
     int v = gemm_variant();
     int cg = v ? (v >> 8) : (g.M > 128 ? 2 : 1);
     int bn = v ? (v & 0xFF) * 2 : (PASSES == 3 ? 128 : (g.N > 128 ? 256 : 128));   // encoded as BN/2
+    // (Measured and rejected: single-CTA 128-row tiles when a call has fewer pair tiles than half the CTA pairs, e.g. the 256-row
+    // blocks of nb200_sgemm_host - 32 pair tiles for 74 pairs.  Twice the busy SMs, but without the pair's operand multicast every
+    // CTA reads its own B panel: a block's product took 110-125 us instead of 90 and the whole call 3.02 instead of 2.78 ms.)
     if constexpr (PASSES == 3) {
         if (g.A_lo == nullptr) {   // in-kernel split (default): no lo arrays exist
             if (cg == 2) return launch_gemm<GemmCfg<2, 128, 3, true>>(g);

@@ -1,0 +1,117 @@
+"""Why does the H2D leg of nb200_sgemm_host slow down to ~30-36 GB/s once C row blocks go out?
+Part 1 (pure copies, torch streams): 64 MiB in / 64 MiB out in chunks, out chunk i gated on in chunk i; 1 or 2 streams per direction.
+Part 2: nb200_sgemm_host 4096^2 under the experiment switches of host_pipeline.cu (children, one env each).
+Output: JSON lines on stdout."""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def child():
+    import torch
+    import numpower_b200 as nb
+    lib = nb.lib()
+    assert lib.nb200_init(0) == 0
+    n = int(os.environ.get("PROBE_N", "4096"))
+    if os.environ.get("PROBE_BATCHED"):
+        nb_, m = int(os.environ["PROBE_BATCHED"]), 2048
+        hA, hB, hC = (torch.rand(nb_, m, m).pin_memory() for _ in range(3))
+        for _ in range(3):
+            assert lib.nb200_sgemm_batched_host(hC.data_ptr(), hA.data_ptr(), hB.data_ptr(), nb_, m, m, m, 3) == 0
+        ts = []
+        for _ in range(8):
+            t0 = time.perf_counter()
+            lib.nb200_sgemm_batched_host(hC.data_ptr(), hA.data_ptr(), hB.data_ptr(), nb_, m, m, m, 3)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ref = (hA[nb_ - 1].double()[:64] @ hB[nb_ - 1].double()).float()
+        err = float(((hC[nb_ - 1][:64] - ref).abs() / ref.abs()).max())
+        ts.sort()
+        print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("NB200_HOST") or k.startswith("PROBE")}, "batched": nb_, "ms_min": ts[0],
+                          "ms_median": ts[len(ts) // 2], "h2d_floor_ms_at_55GBps": nb_ * m * m * 8 / 55e6, "max_rel_err": err}))
+        return
+    ha, hb, hc = (torch.rand(n, n).pin_memory() for _ in range(3))
+    for _ in range(4):
+        assert lib.nb200_sgemm_host(hc.data_ptr(), ha.data_ptr(), hb.data_ptr(), n, n, n, 3) == 0
+    ts = []
+    for _ in range(12):
+        t0 = time.perf_counter()
+        lib.nb200_sgemm_host(hc.data_ptr(), ha.data_ptr(), hb.data_ptr(), n, n, n, 3)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ref = (ha.double()[:64] @ hb.double()).float()
+    err = float(((hc[:64] - ref).abs() / ref.abs()).max())
+    ts.sort()
+    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("NB200_HOST") or k == "PROBE_N"}, "n": n, "ms_min": ts[0], "ms_median": ts[len(ts) // 2], "max_rel_err_rows0_63": err}))
+
+
+def pure_copies():
+    import torch
+    tot = 16 << 20   # floats = 64 MiB
+    pin_in = torch.empty(tot, dtype=torch.float32).pin_memory(); pin_in.fill_(1.0)
+    pin_out = torch.empty(tot, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(tot, dtype=torch.float32, device="cuda")
+    d_out = torch.ones(tot, dtype=torch.float32, device="cuda")
+    for nstreams in (1, 2):
+        s_in = [torch.cuda.Stream() for _ in range(nstreams)]
+        s_out = [torch.cuda.Stream() for _ in range(nstreams)]
+        for chunk_mb in (2, 4, 8, 16, 64):
+            c = (chunk_mb << 20) // 4
+            nchunk = tot // c
+
+            def go(gated=True, do_in=True, do_out=True):
+                evs = []
+                if do_in:
+                    for i in range(nchunk):
+                        s = s_in[i % nstreams]
+                        with torch.cuda.stream(s):
+                            d_in[i * c:(i + 1) * c].copy_(pin_in[i * c:(i + 1) * c], non_blocking=True)
+                            e = torch.cuda.Event(); e.record(s); evs.append(e)
+                if do_out:
+                    for i in range(nchunk):
+                        s = s_out[i % nstreams]
+                        if gated and do_in:
+                            s.wait_event(evs[i])
+                        with torch.cuda.stream(s):
+                            pin_out[i * c:(i + 1) * c].copy_(d_out[i * c:(i + 1) * c], non_blocking=True)
+
+            res = {"part": "pure_copies", "streams_per_direction": nstreams, "chunk_MiB": chunk_mb}
+            for name, kw in (("in_only", dict(do_out=False)), ("out_only", dict(do_in=False)), ("both_gated", dict()), ("both_free", dict(gated=False))):
+                go(**kw); torch.cuda.synchronize()
+                best = 1e9
+                for _ in range(4):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    go(**kw)
+                    torch.cuda.synchronize()
+                    best = min(best, time.perf_counter() - t0)
+                res[name + "_ms"] = round(best * 1e3, 3)
+                res[name + "_GBps_each"] = round(tot * 4 / best / 1e9, 1)
+            print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "child":
+        child()
+        sys.exit(0)
+    if "--pure" in sys.argv:
+        pure_copies()
+    variants = [{}, {"NB200_HOST_WORKERS": "0", "NB200_HOST_BLOCKS": "8"}, {"NB200_GEMM_VARIANT": "576"},
+                {"PROBE_BATCHED": "16"}, {"PROBE_BATCHED": "16", "NB200_HOST_WORKERS": "0"}, {"PROBE_BATCHED": "16", "NB200_HOST_BLOCKS": "8"},
+                {"PROBE_BATCHED": "16", "NB200_HOST_BLOCKS": "32"}, {"PROBE_BATCHED": "16", "NB200_HOST_BLOCKS": "32", "NB200_HOST_WORKERS": "0"}]
+    for v in variants:
+        env = dict(os.environ); env.update(v)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
+        sys.stdout.write(r.stdout)
+        if r.returncode != 0:
+            print(json.dumps({"env": v, "rc": r.returncode, "stderr": r.stderr[-600:]}))
+        sys.stdout.flush()
+    # one traced call of the two most interesting variants
+    for v in ({}, {"NB200_GEMM_VARIANT": "576"}):
+        env = dict(os.environ); env.update(v); env["NB200_HOST_TRACE"] = "1"
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
+        lines = [ln for ln in r.stderr.splitlines() if ln.startswith("[nb200_sgemm_host]")]
+        print(json.dumps({"trace_env": v, "last": lines[-1] if lines else r.stderr[-300:]}), flush=True)
