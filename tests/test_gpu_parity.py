@@ -842,10 +842,11 @@ def test_sgemm_batched_many_chunks_repair_and_fallback_in_late_chunks(nb, prec, 
         lib.nb200_free(p)
 
 
-@pytest.mark.parametrize("mkn", [(1024, 512, 768), (700, 260, 132), (64, 64, 64), (1025, 128, 128), (257, 256, 256), (2049, 512, 64)])
+@pytest.mark.parametrize("mkn", [(1024, 512, 768), (700, 260, 132), (64, 64, 64), (1025, 128, 128), (257, 256, 256), (2049, 512, 64), (4097, 256, 128)])
 def test_sgemm_host_pipeline_matches_resident_call(nb, mkn):
-    """nb200_sgemm_host (B once, A row blocks in, C row blocks out) within 1e-5 of cblas_sgemm and of the resident call.
-    M % 256 == 1: the one-row tail joins the previous row block instead of being refused by the tensor path."""
+    """nb200_sgemm_host (B once, A row blocks in; every block's split + GEMM + download on one of two worker streams) within 1e-5 of
+    cblas_sgemm and of the resident call.  M % 256 == 1: the one-row tail joins the previous row block instead of being
+    refused by the tensor path; 4097 rows = 16 blocks alternating between the worker streams."""
     lib = nb.lib()
     M, K, N = mkn
     r = _rng(M)
@@ -857,6 +858,9 @@ def test_sgemm_host_pipeline_matches_resident_call(nb, mkn):
         assert rel_err(c, ORACLE.matmul(a, b)).max() <= RTOL
         resident = nb.nd.matmul(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu(), prec).toArray()
         assert rel_err(c, resident).max() <= RTOL
+        c2 = np.full((M, N), -1.0, np.float32)     # a second call reuses streams, events and staging buffers: same bits
+        assert lib.nb200_sgemm_host(c2.ctypes.data, a.ctypes.data, b.ctypes.data, M, N, K, prec) == 0, lib.nb200_last_error()
+        np.testing.assert_array_equal(c2, c)
 
 
 def test_sgemm_batched_host_pipeline(nb):
