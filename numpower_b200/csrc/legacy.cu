@@ -278,13 +278,21 @@ int nb200_shim_cublasSgemm(void *, int transa, int transb, int m, int n, int k, 
     return rc == NB200_OK ? 0 : 1;
 }
 
+// ---- NDArray_Outer's device branch (linalg.c:745-748; calculateOuterProductFloat, cuda_math.cu:70-77: r[i*n+j] = a[i]*b[j], one
+// thread per element on 16x16 blocks).  Here: the broadcast multiply of a column (stride 1, 0) by a row (stride 0, 1) - one
+// HBM-bound launch of ew_bcast2d that reads m + n floats and writes m*n.
+void cuda_calculate_outer_product(int m, int n, float *a_array, float *b_array, float *r_array) {
+    enter();
+    const int64_t shape[2] = {m, n}, sa[2] = {1, 0}, sb[2] = {0, 1};
+    leave(nb200_ew_binary(NB200_MUL, r_array, a_array, b_array, 2, shape, sa, sb), "cuda_calculate_outer_product");
+}
+
 // ---- out-of-scope exports: link, then raise
 int cuda_svd_float(float *, float *, float *, float *, int, int) { not_implemented("cuda_svd_float"); return -1; }
 int cuda_det_float(float *, float *, int) { not_implemented("cuda_det_float"); return -1; }
 void cuda_matrix_float_inverse(float *, int) { not_implemented("cuda_matrix_float_inverse"); }
 void cuda_float_lu(float *, float *, float *, float *, int) { not_implemented("cuda_float_lu"); }
 void cuda_lstsq_float(float *, int, int, float *, int, float *) { not_implemented("cuda_lstsq_float"); }
-void cuda_calculate_outer_product(int, int, float *, float *, float *) { not_implemented("cuda_calculate_outer_product"); }
 void cuda_convolve2d_same_float(const float *, const float *, const int *, const int *, const int *, const int *, char,
                                 float *, float) { not_implemented("cuda_convolve2d_same_float"); }
 void cuda_matrix_float_l1norm(float *, float *, int, int) { not_implemented("cuda_matrix_float_l1norm"); }

@@ -296,6 +296,23 @@ class nd:
         a, b = nd._a(a), nd._a(b)
         return NDArray(L.check_ptr(L.lib().NB_NDArray_Dot(a._h, b._h)))
 
+    @staticmethod
+    def outer(a, b) -> NDArray:
+        """NDArray_Outer (linalg.c:724-751: two 1-D vectors): the broadcast multiply (m, 1) * (1, n), one launch."""
+        a, b = nd._a(a), nd._a(b)
+        if a.ndim != 1 or b.ndim != 1:
+            raise ValueError("Invalid operation: NDArray::outer() requires both arrays to be 1-dimensional vectors.")
+        return nd.multiply(a.reshape(a.size, 1), b.reshape(1, b.size))
+
+    @staticmethod
+    def norm(a, order: int = 1) -> float:
+        """NDArray_Norm(a, 1) = NDArray_L1Norm (linalg.c:423-447): max over columns of the sum of absolute values.  The reference
+        transposes and sums every column with its own call; here abs + one axis-0 reduction + max.  Other orders need the SVD."""
+        if order != 1:
+            raise NotImplementedError("norm: only order 1 is on the elementwise / reduction path")
+        a = nd._a(a)
+        return float(nd.max(nd.sum(nd.unary("abs", a), 0)))
+
 
 def _make_unary(name):
     def f(a):

@@ -116,6 +116,11 @@ class _Ref:
             lib.ref_dot.argtypes = [_fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
             lib.ref_matmul_nd.restype = C.c_long
             lib.ref_matmul_nd.argtypes = [_fp, _ip, C.c_int, _fp, _ip, C.c_int, _fp, C.c_long, _dp]
+            if hasattr(lib, "ref_outer"):
+                lib.ref_outer.restype = C.c_long
+                lib.ref_outer.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp]
+                lib.ref_norm1.restype = C.c_long
+                lib.ref_norm1.argtypes = [_fp, _ip, C.c_int, _fp]
             if hasattr(lib, "ref_all"):
                 lib.ref_all.argtypes = [_fp, _ip, C.c_int]
                 lib.ref_allclose.argtypes = [_fp, _fp, _ip, C.c_int, C.c_float, C.c_float]
@@ -258,6 +263,22 @@ class _Ref:
         r = self.lib.ref_allclose(_f(a), _f(b), _shape(a), a.ndim, rtol, atol)
         self._check(0, "allclose")
         return int(r)
+
+    def outer(self, a, b) -> np.ndarray:
+        """NDArray_Outer (linalg.c:724-751)."""
+        a, b = _c32(a).ravel(), _c32(b).ravel()
+        out = np.empty((a.size, b.size), dtype=np.float32)
+        n = self.lib.ref_outer(_f(a), a.size, _f(b), b.size, _f(out))
+        self._check(n, "outer")
+        return out
+
+    def norm1(self, a) -> np.float32:
+        """NDArray_Norm(a, 1) = NDArray_L1Norm (linalg.c:423-447): max over columns of the sum of absolute values."""
+        a = _c32(a)
+        out = np.empty(1, dtype=np.float32)
+        n = self.lib.ref_norm1(_f(a), _shape(a), a.ndim, _f(out))
+        self._check(n, "norm1")
+        return out[0]
 
     def dot(self, a, b) -> np.ndarray:
         a, b = _c32(a), _c32(b)

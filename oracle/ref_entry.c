@@ -337,6 +337,24 @@ long ref_dot(const float *a, const int *ashape, int andim, const float *b, const
     return n;
 }
 
+/* ---- linalg compositions next to the path: NDArray_Outer (linalg.c:724-751: cblas_sger on zeros / cuda_calculate_outer_product)
+ * and NDArray_Norm(type 1) = NDArray_L1Norm (linalg.c:423-447: Transpose, Abs, one NDArray_Sum_Float per column, max). */
+long ref_outer(const float *a, int m, const float *b, int n, float *out) {
+    int as[1] = {m}, bs[1] = {n};
+    NDArray *na = wrap(a, as, 1), *nb = wrap(b, bs, 1);
+    NDArray *r = NDArray_Outer(na, nb);
+    long k = take(r, out, (long) m * n);
+    unwrap(na); unwrap(nb);
+    return k;
+}
+long ref_norm1(const float *a, const int *shape, int ndim, float *out) {
+    NDArray *na = wrap(a, shape, ndim);
+    NDArray *r = NDArray_Norm(na, 1);
+    long k = take(r, out, 1);
+    unwrap(na);
+    return k;
+}
+
 /* ---- logic: NDArray_All (logic.c:25-58) / NDArray_AllClose (logic.c:748-771) -------------------------
  * Only meaningful on the shapes the reference's own tests use (n < 8 for all; allclose reads out of bounds for larger
  * inputs, see oracle/port.c): these entries exist to replay tests/logic/00{1,2}-*.phpt against the real object code. */

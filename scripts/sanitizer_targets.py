@@ -66,4 +66,14 @@ assert lib.nb200_ew_binary(2, big.data_ptr, big.data_ptr, big.data_ptr, 1, shp, 
 g = C.c_void_p()
 assert lib.nb200_graph_end(C.byref(g)) == 0
 assert lib.nb200_graph_launch(g) == 0 and lib.nb200_synchronize() == 0 and lib.nb200_graph_destroy(g) == 0
+# host-operand pipelines (worker streams, ragged last block), outer product / L1 norm compositions
+hm, hk, hn = 1025, 136, 264
+ha, hb = r.random((hm, hk), dtype=np.float32), r.random((hk, hn), dtype=np.float32)
+hc = np.empty((hm, hn), np.float32)
+for prec in (0, 2, 3):
+    assert lib.nb200_sgemm_host(hc.ctypes.data, ha.ctypes.data, hb.ctypes.data, hm, hn, hk, prec) == 0
+hA, hB = r.random((5, 130, 72), dtype=np.float32), r.random((5, 72, 264), dtype=np.float32)
+hC = np.empty((5, 130, 264), np.float32)
+assert lib.nb200_sgemm_batched_host(hC.ctypes.data, hA.ctypes.data, hB.ctypes.data, 5, 130, 264, 72, 3) == 0
+nd.outer(row, A(r.random(41, dtype=np.float32)).gpu()).toArray(); nd.norm(a, 1)
 print("sanitizer targets done;", nb.lib().nb200_launch_count(), "launches")

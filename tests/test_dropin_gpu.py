@@ -78,3 +78,18 @@ def test_reference_gpu_argmax_still_unsupported_in_host():
     """calculation.c:75-78 throws for GPU arrays; reaching nb200_argminmax needs host patch N1."""
     with pytest.raises(RuntimeError, match="GPU not supported"):
         oracle.dropin.argminmax(True, np.arange(10, dtype=np.float32))
+
+
+def test_reference_host_outer_and_l1_norm_on_b200():
+    """NDArray_Outer (linalg.c:724-751) -> cuda_calculate_outer_product = one broadcast multiply; NDArray_Norm(a, 1)
+    (linalg.c:423-447) = Transpose + Abs + one Sum per column + max, every step through the legacy symbols.  Dyadic inputs:
+    products and sums are exact, so the GPU branch must give the CPU branch's bits."""
+    r = _rng(21)
+    a = (r.integers(-64, 65, size=300).astype(np.float32) / 64)
+    b = (r.integers(-64, 65, size=517).astype(np.float32) / 64)
+    g, e = oracle.dropin.outer(a, b), oracle.ref.outer(a, b)
+    assert g.shape == (300, 517)
+    eq(g, e)
+    eq(g, np.outer(a, b).astype(np.float32))
+    m = (r.integers(-64, 65, size=(37, 29)).astype(np.float32) / 64)
+    assert oracle.dropin.norm1(m) == oracle.ref.norm1(m) == np.abs(m).sum(axis=0).max()

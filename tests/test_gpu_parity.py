@@ -1012,6 +1012,23 @@ def test_statistics_compositions(nb):
     assert nb.nd.average(A) == float(mean)
 
 
+def test_outer_and_l1_norm_compositions(nb):
+    """nd.outer (NDArray_Outer, linalg.c:724-751) and nd.norm(a, 1) (NDArray_L1Norm, linalg.c:423-447) as compositions of path
+    kernels, against the reference's own functions; dyadic inputs make every product and sum exact."""
+    r = _rng(77)
+    a = (r.integers(-64, 65, size=1000).astype(np.float32) / 64)
+    b = (r.integers(-64, 65, size=777).astype(np.float32) / 64)
+    got = nb.nd.outer(nb.NDArray.array(a).gpu(), nb.NDArray.array(b).gpu()).toArray()
+    assert got.shape == (1000, 777)
+    exp = ORACLE.outer(a, b) if hasattr(ORACLE, "outer") else np.outer(a, b).astype(np.float32)
+    assert (got == exp).all()
+    m = (r.integers(-64, 65, size=(300, 41)).astype(np.float32) / 64)
+    exp_n = ORACLE.norm1(m) if hasattr(ORACLE, "norm1") else np.abs(m).sum(axis=0).max()
+    assert nb.nd.norm(nb.NDArray.array(m).gpu(), 1) == float(exp_n)
+    with pytest.raises(ValueError):
+        nb.nd.outer(nb.NDArray.array(m).gpu(), nb.NDArray.array(b).gpu())
+
+
 def test_matmul_inf_nan_propagation_and_dynamic_range(nb):
     """IEEE special values must propagate like cblas_sgemm (inf stays inf, inf*0 and NaN give NaN), and rows with a wide
     dynamic range keep fp32-class accuracy (TF32 has the full 8-bit exponent)."""
