@@ -201,7 +201,8 @@ int nb200_sgemm_batched(float *C, const float *A, const float *B, int64_t batch,
                         int64_t strideA, int64_t strideB, int64_t strideC, int precision);
 /* nd::matmul on HOST operands (what `$a->gpu(); nd::matmul; ->cpu()` does in three steps, NDArray_ToGPU/ToCPU
  * ndarray.c:1037-1093): B is uploaded once, then row blocks of A stream in, are multiplied and stream out, so the
- * H2D and D2H copies overlap each other (full-duplex PCIe) and the compute.  Blocking; C_host complete on return.
+ * H2D and D2H copies overlap each other (full-duplex PCIe) and the compute (copy-in stream + two worker streams that
+ * run split, GEMM and download of a block in stream order).  Blocking; C_host complete on return.
  * Host buffers should be pinned (nb200_host_alloc) for full PCIe speed; pageable memory works but is staged. */
 int nb200_sgemm_host(float *C_host, const float *A_host, const float *B_host, int64_t M, int64_t N, int64_t K, int precision);
 /* Batch of independent products with HOST operands (contiguous [batch][M][K], [batch][K][N] -> [batch][M][N]): chunks of matrices
