@@ -412,7 +412,8 @@ __device__ __forceinline__ unsigned long long arg_run(const float *__restrict__ 
 
 __device__ __forceinline__ float unpack_index(unsigned long long best) {
     unsigned int idx = 0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull);
-    return (float)(int)idx;  // the reference stores (float)i with int i (calculation.c:25)
+    return (float)idx;  // the reference stores (float)i with int i (calculation.c:25): the same rounding below 2^31; above, where the
+                        // reference's int shapes cannot go, the 32-bit index stays unsigned (was (float)(int)idx: negative results)
 }
 
 // rows x len (inner == 1).  grid = (S, rows); S > 1 uses u64 partials + ticket like reduce_rows_kernel.

@@ -486,7 +486,7 @@ extern "C" int nb200_shard_argminmax(int is_max, float *host_out, const float *c
         if (best_idx < 0 || key > best_key) { best_key = key; best_idx = lo[s] + (int64_t)idx; }
     }
     if (first_elem != first_elem) best_idx = 0;   // calculation.c:14-17, :41-44: a leading NaN wins outright
-    *host_out = (float)(int)best_idx;             // the reference stores (float)i with int i
+    *host_out = (float)best_idx;                  // the reference stores (float)i with int i: same rounding below 2^31, no wrap above
     return NB200_OK;
 }
 

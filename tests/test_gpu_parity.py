@@ -1012,6 +1012,71 @@ def test_statistics_compositions(nb):
     assert nb.nd.average(A) == float(mean)
 
 
+def test_arrays_beyond_2_pow_31_elements(nb):
+    """Maximum sizes: 64-bit extents end to end.  The reference stops at 2^31 elements / 4 GiB (`int` shapes ndarray.h:61-74,
+    `vmalloc(void **, unsigned int)` gpu_alloc.c:11), so there is no oracle run at this size: the expected values follow from the
+    few elements planted at known positions of an otherwise constant 8.6 GB array (every sum below is exact in any order)."""
+    import ctypes as C
+    import torch
+    lib = nb.lib()
+    n = (1 << 31) + (1 << 20) + 3
+    if torch.cuda.mem_get_info()[0] < 3 * n * 4:
+        pytest.skip("needs 26 GB of free device memory")
+    pa, po = C.c_void_p(), C.c_void_p()
+    assert lib.nb200_alloc(C.byref(pa), n * 4) == 0, lib.nb200_last_error()
+    assert lib.nb200_alloc(C.byref(po), n * 4) == 0, lib.nb200_last_error()
+
+    def poke(p, i, v):
+        x = np.array([v], np.float32)
+        assert lib.nb200_copy_h2d(C.c_void_p(p.value + 4 * i), x.ctypes.data, 4) == 0
+
+    def peek(p, i):
+        x = np.empty(1, np.float32)
+        assert lib.nb200_copy_d2h(x.ctypes.data, C.c_void_p(p.value + 4 * i), 4) == 0
+        return float(x[0])
+
+    def full(op, is_arg=False):
+        v = C.c_float()
+        fn = lib.nb200_argminmax_host if is_arg else lib.nb200_reduce_full_host
+        assert fn(op, C.byref(v), pa, n) == 0, lib.nb200_last_error()
+        return v.value
+
+    try:
+        assert lib.nb200_fill(pa, 0.0, n) == 0
+        far = (1 << 31) + 5
+        for i in (0, far, n - 1):
+            poke(pa, i, 1.0)
+        assert full(oracle.RED_OPS["sum"]) == 3.0
+        poke(pa, n - 2, 5.0)
+        poke(pa, n - 3, -2.0)
+        assert full(oracle.RED_OPS["max"]) == 5.0 and full(oracle.RED_OPS["min"]) == -2.0
+        assert full(1, True) == float(np.float32(n - 2)) and full(0, True) == float(np.float32(n - 3))   # (float) idx, calculation.c:160-190
+        # elementwise over all n elements: out = a + 1, then exp in place
+        assert lib.nb200_ew_binary_scalar(oracle.BIN_OPS["add"], po, pa, 1.0, 0, n) == 0, lib.nb200_last_error()
+        assert [peek(po, i) for i in (7, far, n - 1, n - 2, n - 3)] == [1.0, 2.0, 2.0, 6.0, -1.0]
+        assert lib.nb200_ew_unary(oracle.UN_OPS["negative"], po, po, n, 0.0, 0.0) == 0, lib.nb200_last_error()
+        assert [peek(po, i) for i in (7, far, n - 2)] == [-1.0, -2.0, -6.0]
+        # axis reductions of the (65537, 32768) view = 2^31 + 2^15 elements: ones at [0, 0] and [65536, 5]
+        rows, cols = 65537, 32768
+        assert rows * cols <= n - 3
+        out0, out1 = np.empty(cols, np.float32), np.empty(rows, np.float32)
+        pr = C.c_void_p()
+        assert lib.nb200_alloc(C.byref(pr), rows * 4) == 0
+        assert lib.nb200_reduce_axis(oracle.RED_OPS["sum"], pr, pa, 1, rows, cols, nb.ORDER_TREE) == 0, lib.nb200_last_error()
+        assert lib.nb200_copy_d2h(out0.ctypes.data, pr, cols * 4) == 0
+        e0 = np.zeros(cols, np.float32); e0[0] = 1; e0[5] = 1
+        np.testing.assert_array_equal(out0, e0)
+        assert lib.nb200_reduce_axis(oracle.RED_OPS["sum"], pr, pa, rows, cols, 1, nb.ORDER_TREE) == 0, lib.nb200_last_error()
+        assert lib.nb200_copy_d2h(out1.ctypes.data, pr, rows * 4) == 0
+        e1 = np.zeros(rows, np.float32); e1[0] = 1; e1[65536] = 1
+        np.testing.assert_array_equal(out1, e1)
+        lib.nb200_free(pr)
+    finally:
+        lib.nb200_free(pa); lib.nb200_free(po)
+        if hasattr(lib, "nb200_trim"):
+            lib.nb200_trim()
+
+
 def test_outer_and_l1_norm_compositions(nb):
     """nd.outer (NDArray_Outer, linalg.c:724-751) and nd.norm(a, 1) (NDArray_L1Norm, linalg.c:423-447) as compositions of path
     kernels, against the reference's own functions; dyadic inputs make every product and sum exact."""
