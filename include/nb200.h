@@ -187,7 +187,8 @@ int nb200_reduce_axis(int op, float *out, const float *in, int64_t outer, int64_
 /* argmax/argmin along the middle dim of (outer, len, inner); out (outer, inner) holds the
  * index as float32.  Semantics of float_argmax/float_argmin (calculation.c:9-59): first
  * occurrence; argmax skips NaN unless it is element 0, argmin returns the first NaN.
- * The reference has no GPU path ("GPU not supported.", calculation.c:75-78). */
+ * The reference has no GPU path ("GPU not supported.", calculation.c:75-78).  len < 2^32 - 1; the index is rounded to
+ * float32 like the reference's (float)i (exact below 2^24). */
 int nb200_argminmax(int is_max, float *out, const float *in, int64_t outer, int64_t len, int64_t inner);
 int nb200_argminmax_host(int is_max, float *host_out, const float *in, int64_t n);
 
