@@ -2208,11 +2208,13 @@ static int gemm_impl(GemmArgs g, int precision) {
     if (precision == NB200_GEMM_TF32X3 && bf16_ok && !tensor_path_ok(g) && g.K >= 128 && !force_simt) return gemm_fp16x3(g, true);
     if (precision == NB200_GEMM_BF16X3 || precision == NB200_GEMM_FP16X3 || precision == NB200_GEMM_FP16X3U) precision = NB200_GEMM_TF32X3;   // tiny shapes
     if (!tensor_path_ok(g) || force_simt) {
-        dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)g.batch);
-        if (g.batch > 65535) return set_error(NB200_EINVAL, "sgemm (SIMT path): batch %lld > 65535", (long long)g.batch);
-        sgemm_simt_kernel<<<grid, 256, 0, ctx().stream>>>(g.C, g.A, g.B, g.M, g.N, g.K, g.lda, g.ldb, g.ldc, g.sA,
-                                                          g.sB, g.sC);
-        NB_LAUNCH_CHECK();
+        for (int64_t b0 = 0; b0 < g.batch; b0 += 65535) {   // the batch rides on gridDim.z
+            const int64_t nb = g.batch - b0 < 65535 ? g.batch - b0 : 65535;
+            dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64), (unsigned)nb);
+            sgemm_simt_kernel<<<grid, 256, 0, ctx().stream>>>(g.C + b0 * g.sC, g.A + b0 * g.sA, g.B + b0 * g.sB, g.M, g.N, g.K, g.lda, g.ldb, g.ldc,
+                                                              g.sA, g.sB, g.sC);
+            NB_LAUNCH_CHECK();
+        }
         return NB200_OK;
     }
     if (precision == NB200_GEMM_TF32X1) return dispatch_cfg<1>(g);

@@ -772,6 +772,21 @@ def test_sgemm_batched_shared_operand_and_many_batches(nb):
         lib.nb200_free(p)
 
 
+def test_sgemm_batched_more_matrices_than_grid_z(nb):
+    """70 000 tiny matrices (3x5 . 5x4: the fp32 SIMT path puts the batch on gridDim.z, limit 65 535): processed in two launches,
+    every matrix equal to numpy's fp32 product of the same dyadic operands (exact)."""
+    lib = nb.lib()
+    r = _rng(65)
+    batch, M, K, N = 70000, 3, 5, 4
+    a = (r.integers(-8, 9, size=(batch, M, K)).astype(np.float32) / 8)
+    b = (r.integers(-8, 9, size=(batch, K, N)).astype(np.float32) / 8)
+    da, db, dc = _dev(nb, a), _dev(nb, b), _dev(nb, np.full((batch, M, N), -1.0, np.float32))
+    assert lib.nb200_sgemm_batched(dc, da, db, batch, M, N, K, M * K, K * N, M * N, nb.GEMM_AUTO) == 0, lib.nb200_last_error()
+    np.testing.assert_array_equal(_fetch(nb, dc, (batch, M, N)), np.matmul(a, b))
+    for p in (da, db, dc):
+        lib.nb200_free(p)
+
+
 @pytest.mark.parametrize("prec", [0, 2, 4])
 def test_sgemm_batched_in_several_workspace_chunks(nb, prec, monkeypatch):
     """A workspace budget of 1 MiB forces chunks of 2 + 2 + 1 matrices; B is shared (stride 0), i.e. split once with the
@@ -1073,8 +1088,72 @@ def test_arrays_beyond_2_pow_31_elements(nb):
         lib.nb200_free(pr)
     finally:
         lib.nb200_free(pa); lib.nb200_free(po)
-        if hasattr(lib, "nb200_trim"):
-            lib.nb200_trim()
+
+
+def test_matmul_gemv_broadcast_beyond_2_pow_31_elements(nb):
+    """An operand of (2^20 + 1) x 2048 = 2^31 + 2048 elements through nd::matmul (AUTO and TF32X3), nd::dot (gemv), a row / column
+    broadcast chain and the boolean reductions.  Dyadic values (k/64): every product and every sum is exact in fp32 whatever the
+    order, so the expected result follows from numpy on the few distinct rows."""
+    import ctypes as C
+    import torch
+    lib = nb.lib()
+    M, K, N = (1 << 20) + 1, 2048, 128
+    if torch.cuda.mem_get_info()[0] < 6 * M * K * 4:
+        pytest.skip("needs ~52 GB of free device memory")
+    r = _rng(2031)
+    b = (r.integers(-64, 65, size=(K, N)).astype(np.float32) / 64)
+    x = (r.integers(-64, 65, size=K).astype(np.float32) / 64)
+    planted = {0: None, (1 << 19) + 7: None, M - 1: None}
+    for i in planted:
+        planted[i] = (r.integers(-64, 65, size=K).astype(np.float32) / 64)
+    pa, pb, pc, px, py, pe = (C.c_void_p() for _ in range(6))
+    for p, nbytes in ((pa, M * K * 4), (pb, K * N * 4), (pc, M * N * 4), (px, K * 4), (py, M * 4), (pe, M * K * 4)):
+        assert lib.nb200_alloc(C.byref(p), nbytes) == 0, lib.nb200_last_error()
+    try:
+        assert lib.nb200_fill(pa, 0.5, M * K) == 0
+        for i, row in planted.items():
+            assert lib.nb200_copy_h2d(C.c_void_p(pa.value + 4 * i * K), row.ctypes.data, K * 4) == 0
+        assert lib.nb200_copy_h2d(pb, b.ctypes.data, b.nbytes) == 0 and lib.nb200_copy_h2d(px, x.ctypes.data, x.nbytes) == 0
+        exp_c = np.tile((0.5 * b.astype(np.float64).sum(axis=0)).astype(np.float32), (M, 1))
+        exp_y = np.full(M, np.float32(0.5 * x.astype(np.float64).sum()), np.float32)
+        for i, row in planted.items():
+            exp_c[i] = (row.astype(np.float64) @ b.astype(np.float64)).astype(np.float32)
+            exp_y[i] = np.float32(row.astype(np.float64) @ x.astype(np.float64))
+        got = np.empty((M, N), np.float32)
+        for prec in (nb.GEMM_AUTO, nb.TF32X3):
+            assert lib.nb200_fill(pc, -1.0, M * N) == 0
+            assert lib.nb200_sgemm(pc, pa, pb, M, N, K, K, N, N, prec) == 0, lib.nb200_last_error()
+            assert lib.nb200_copy_d2h(got.ctypes.data, pc, got.nbytes) == 0
+            np.testing.assert_array_equal(got, exp_c)
+        goty = np.empty(M, np.float32)
+        assert lib.nb200_gemv(py, pa, px, M, K) == 0, lib.nb200_last_error()
+        assert lib.nb200_copy_d2h(goty.ctypes.data, py, goty.nbytes) == 0
+        np.testing.assert_array_equal(goty, exp_y)
+        # e = a * x (row vector) + y (column vector): fused broadcast chain over 2^31 + 2048 output elements
+        shp = (C.c_int64 * 2)(M, K)
+        s_full, s_row, s_col = (C.c_int64 * 2)(K, 1), (C.c_int64 * 2)(0, 1), (C.c_int64 * 2)(1, 0)
+        assert lib.nb200_ew_mul_add(pe, pa, px, py, 2, shp, s_full, s_row, s_col) == 0, lib.nb200_last_error()
+        rowbuf = np.empty(K, np.float32)
+        for i in (0, 1, (1 << 19) + 7, (1 << 20) - 1, M - 1):
+            assert lib.nb200_copy_d2h(rowbuf.ctypes.data, C.c_void_p(pe.value + 4 * i * K), K * 4) == 0
+            arow = planted.get(i, np.full(K, 0.5, np.float32))
+            np.testing.assert_array_equal(rowbuf, arow * x + exp_y[i])
+        # boolean reductions over the whole operand: no zero in a (0.5 everywhere, planted rows may hold zeros -> overwrite them)
+        flag = C.c_int(-1)
+        for i in planted:
+            assert lib.nb200_fill(C.c_void_p(pa.value + 4 * i * K), 0.25, K) == 0
+        assert lib.nb200_all(C.byref(flag), pa, M * K) == 0 and flag.value == 1
+        zero = np.zeros(1, np.float32)
+        assert lib.nb200_copy_h2d(C.c_void_p(pa.value + 4 * (M * K - 1)), zero.ctypes.data, 4) == 0
+        assert lib.nb200_all(C.byref(flag), pa, M * K) == 0 and flag.value == 0
+        assert lib.nb200_copy_d2d(pe, pa, M * K * 4) == 0
+        assert lib.nb200_allclose(C.byref(flag), pa, pe, M * K, 1e-5, 1e-8) == 0 and flag.value == 1
+        one = np.ones(1, np.float32)
+        assert lib.nb200_copy_h2d(C.c_void_p(pe.value + 4 * (M * K - 2)), one.ctypes.data, 4) == 0
+        assert lib.nb200_allclose(C.byref(flag), pa, pe, M * K, 1e-5, 1e-8) == 0 and flag.value == 0
+    finally:
+        for p in (pa, pb, pc, px, py, pe):
+            lib.nb200_free(p)
 
 
 def test_outer_and_l1_norm_compositions(nb):
