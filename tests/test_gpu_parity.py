@@ -228,7 +228,9 @@ def test_min_max_nan_rules(nb):
 
 
 AXIS_SHAPES = [((37, 53), 0), ((37, 53), 1), ((4, 5, 6), 1), ((3, 1000, 8), 1), ((2048, 96), 0), ((96, 2048), 1),
-               ((5, 7, 2048), 2), ((3000, 5), 0), ((1, 70000), 1), ((70000, 3), 0)]
+               ((5, 7, 2048), 2), ((3000, 5), 0), ((1, 70000), 1), ((70000, 3), 0),
+               # more slices than a grid dimension holds (outer > 65535), long middle axes with a tiny / odd inner extent
+               ((70000, 40, 3), 1), ((66000, 5), 1), ((3, 70001, 2), 1), ((2, 3, 70001), 1), ((70001, 2, 4), 1)]
 
 
 @pytest.mark.parametrize("shape,axis", AXIS_SHAPES)
@@ -254,6 +256,16 @@ def test_axis_sum_sequential_order_bit_exact_on_random_data(nb, shape, axis):
 
 
 # --------------------------------------------------------------------- argmax / argmin
+@pytest.mark.parametrize("shape,axis", AXIS_SHAPES[8:])
+def test_argminmax_many_slices_and_long_axes(nb, shape, axis):
+    """argmax / argmin on the shapes with more slices than a grid dimension holds and on long middle axes; ties everywhere
+    (values 0..49): first occurrence, as float_argmax / float_argmin (calculation.c:9-59)."""
+    x = _rng(sum(shape)).integers(0, 50, size=shape).astype(np.float32)
+    A = nb.NDArray.array(x).gpu()
+    np.testing.assert_array_equal(nb.nd.argmax(A, axis).toArray(), oracle.port.argminmax(True, x, axis))
+    np.testing.assert_array_equal(nb.nd.argmin(A, axis).toArray(), oracle.port.argminmax(False, x, axis))
+
+
 def test_argminmax_axes_and_ties(nb):
     x = _rng(9).integers(0, 50, size=(6, 70, 5)).astype(np.float32)
     A = nb.NDArray.array(x).gpu()
@@ -654,6 +666,11 @@ def test_dot_variants(nb):
     a, x = r.random((300, 1000), dtype=np.float32), r.random(1000, dtype=np.float32)
     got = nb.nd.dot(nb.NDArray.array(a).gpu(), nb.NDArray.array(x).gpu()).toArray()
     assert rel_err(got, ORACLE.dot(a, x) if oracle.ref.available else oracle.port.gemv(a, x)).max() <= RTOL
+    # more rows than a grid dimension holds, odd row length (no 16-byte alignment past row 0), 4-row x long vectors; dyadic: exact
+    for rows, cols in ((70001, 37), (4, 100003), (1, 8)):
+        a2, x2 = _set_p2((rows, cols), rows), _set_p2(cols, cols)
+        got2 = nb.nd.dot(nb.NDArray.array(a2).gpu(), nb.NDArray.array(x2).gpu()).toArray()
+        np.testing.assert_array_equal(got2, (a2.astype(np.float64) @ x2.astype(np.float64)).astype(np.float32))
     v = _set_p2(5000, 3)
     w = _set_p2(5000, 4)
     got = float(nb.nd.dot(nb.NDArray.array(v).gpu(), nb.NDArray.array(w).gpu()).toArray())
@@ -1248,7 +1265,7 @@ def test_all_allclose_golden_and_errors(nb):
     assert nb.nd.all(np.zeros((0,), np.float32)) == 1
 
 
-@pytest.mark.parametrize("rc", [(1, 1), (3, 5), (32, 32), (33, 65), (257, 1031), (1000, 1), (1, 777), (2048, 4100)])
+@pytest.mark.parametrize("rc", [(1, 1), (3, 5), (32, 32), (33, 65), (257, 1031), (1000, 1), (1, 777), (2048, 4100), (70001, 3), (3, 2100001)])
 def test_transpose2d_and_the_legacy_in_place_call(nb, rc):
     """nb200_transpose2d and cuda_float_transpose (cuda_math.h:77) as the host calls it: d_in == d_out (manipulation.c:124),
     (width, height) = (cols, rows).  Bit-exact (index work)."""
