@@ -307,7 +307,8 @@ class nd:
     @staticmethod
     def norm(a, order: int = 1) -> float:
         """NDArray_Norm(a, 1) = NDArray_L1Norm (linalg.c:423-447): max over columns of the sum of absolute values.  The reference
-        transposes and sums every column with its own call; here abs + one axis-0 reduction + max.  Other orders need the SVD."""
+        transposes and sums every column with its own call (and is only safe on square inputs: it sizes its per-column results by the
+        row count); here abs + one axis-0 reduction + max, any 2-D shape.  Other orders need the SVD."""
         if order != 1:
             raise NotImplementedError("norm: only order 1 is on the elementwise / reduction path")
         a = nd._a(a)
