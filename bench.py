@@ -165,6 +165,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.1)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)      # gone before anything else is timed (its NVML queries hold driver locks)
+        except Exception:
+            self.proc.kill()
 
         def summarise(lines):
             sm, mx, reasons, power = [], None, set(), []
@@ -402,6 +406,12 @@ def run_single(args):
         mm(prec)
         mode_err[name] = float(((c[rows].double() - truth) / truth).abs().max())
     del truth
+    # The sampler stops HERE: the window covers the timed matmul loop and the other-mode loops (the headline loop alone is shorter
+    # than one nvidia-smi period).  It must not run beside the e2e loop: every NVML query holds driver locks for tens of ms on some
+    # boxes, the host thread's ~100 enqueue calls per nb200_sgemm_host step stall behind it and the PCIe pipeline starves (same build:
+    # 2.81 ms on one box, 3.25 ms on a box whose queries took 36 ms each; scripts/duplex_probe.py without a sampler: 2.77-2.80 on both).
+    sampler.mark_end()
+    clocks = sampler.stop()
 
     # ---- e2e: pinned host buffers, H2D(A,B) + matmul + D2H(C) per step, through the C-ABI
     ha, hb, hc = (torch.empty(n, n, dtype=torch.float32).pin_memory() for _ in range(3))
@@ -415,8 +425,6 @@ def run_single(args):
 
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = B.time_steps(e2e_step, e2e_steps, 3)
-    sampler.mark_end()
-    clocks = sampler.stop()   # sampled across the timed matmul / other-mode / e2e regions (the headline loop alone is shorter than one nvidia-smi period)
     # raw PCIe ceilings for the e2e number: 256 MiB pinned copies, each direction alone and both at once
     pin = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
     pin2 = torch.empty(64 << 20, dtype=torch.float32).pin_memory()

@@ -18,6 +18,11 @@ def child():
     lib = nb.lib()
     assert lib.nb200_init(0) == 0
     n = int(os.environ.get("PROBE_N", "4096"))
+    extra = [torch.cuda.Stream() for _ in range(int(os.environ.get("PROBE_EXTRA_STREAMS", "0")))]   # other streams of the process (hardware queue aliasing?)
+    for st in extra:
+        with torch.cuda.stream(st):
+            torch.zeros(16, device="cuda").add_(1.0)
+    torch.cuda.synchronize()
     if os.environ.get("PROBE_BATCHED"):
         nb_, m = int(os.environ["PROBE_BATCHED"]), 2048
         hA, hB, hC = (torch.rand(nb_, m, m).pin_memory() for _ in range(3))
@@ -45,7 +50,7 @@ def child():
     ref = (ha.double()[:64] @ hb.double()).float()
     err = float(((hc[:64] - ref).abs() / ref.abs()).max())
     ts.sort()
-    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("NB200_HOST") or k == "PROBE_N"}, "n": n, "ms_min": ts[0], "ms_median": ts[len(ts) // 2], "max_rel_err_rows0_63": err}))
+    print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("NB200_HOST") or k.startswith("PROBE") or k == "CUDA_DEVICE_MAX_CONNECTIONS"}, "n": n, "ms_min": ts[0], "ms_median": ts[len(ts) // 2], "max_rel_err_rows0_63": err}))
 
 
 def pure_copies():
@@ -99,9 +104,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--pure" in sys.argv:
         pure_copies()
-    variants = [{}, {"NB200_HOST_WORKERS": "0", "NB200_HOST_BLOCKS": "8"}, {"NB200_GEMM_VARIANT": "576"},
-                {"PROBE_BATCHED": "16"}, {"PROBE_BATCHED": "16", "NB200_HOST_WORKERS": "0"}, {"PROBE_BATCHED": "16", "NB200_HOST_BLOCKS": "8"},
-                {"PROBE_BATCHED": "16", "NB200_HOST_BLOCKS": "32"}, {"PROBE_BATCHED": "16", "NB200_HOST_BLOCKS": "32", "NB200_HOST_WORKERS": "0"}]
+    variants = [{"PROBE_EXTRA_STREAMS": str(k)} for k in (0, 1, 2, 3, 4, 5, 6, 8, 12)]
+    variants += [{"PROBE_EXTRA_STREAMS": str(k), "CUDA_DEVICE_MAX_CONNECTIONS": "32"} for k in (0, 2, 4, 6, 8, 12)]
+    variants += [{"PROBE_EXTRA_STREAMS": str(k), "NB200_HOST_WORKERS": "0", "NB200_HOST_BLOCKS": "8"} for k in (0, 4)]
     for v in variants:
         env = dict(os.environ); env.update(v)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
@@ -110,7 +115,7 @@ if __name__ == "__main__":
             print(json.dumps({"env": v, "rc": r.returncode, "stderr": r.stderr[-600:]}))
         sys.stdout.flush()
     # one traced call of the two most interesting variants
-    for v in ({}, {"NB200_GEMM_VARIANT": "576"}):
+    for v in ():
         env = dict(os.environ); env.update(v); env["NB200_HOST_TRACE"] = "1"
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
         lines = [ln for ln in r.stderr.splitlines() if ln.startswith("[nb200_sgemm_host]")]
