@@ -372,6 +372,8 @@ def run_single(args):
     B = Bench(0)
     torch, lib = B.torch, B.lib
     n = MATMUL_N
+    # pinned host buffers of the e2e arm, allocated first (see the note on the e2e spread before the e2e loop)
+    ha, hb, hc = (torch.empty(n, n, dtype=torch.float32, pin_memory=True) for _ in range(3))
     g = torch.Generator(device="cuda").manual_seed(3)
     a = torch.rand(n, n, device="cuda", generator=g)
     b = torch.rand(n, n, device="cuda", generator=g)
@@ -406,16 +408,18 @@ def run_single(args):
         mm(prec)
         mode_err[name] = float(((c[rows].double() - truth) / truth).abs().max())
     del truth
-    # The sampler stops HERE: the window covers the timed matmul loop and the other-mode loops (the headline loop alone is shorter
-    # than one nvidia-smi period).  It must not run beside the e2e loop: every NVML query holds driver locks for tens of ms on some
-    # boxes, the host thread's ~100 enqueue calls per nb200_sgemm_host step stall behind it and the PCIe pipeline starves (same build:
-    # 2.81 ms on one box, 3.25 ms on a box whose queries took 36 ms each; scripts/duplex_probe.py without a sampler: 2.77-2.80 on both).
+    # The sampler stops HERE: its window covers the timed matmul loop and the other-mode loops (the headline loop alone is shorter
+    # than one nvidia-smi period); the e2e loop below is PCIe-bound and is not the timed region of `value`.
+    # (The e2e figure varies from PROCESS to process for the same build: 2.81 / 3.25 / 3.04 / 3.29 / 2.95 / 2.87 ms in six bench.py runs
+    # on six boxes, while scripts/duplex_probe.py - the same call in a process of its own - measured 2.77-2.80 ms in every one of ~30
+    # processes on the same kind of box, including right before and after a 2.95 ms bench run.  A process is fast or slow for all of
+    # its calls.  Ruled out in isolation: the nvidia-smi sampler, the legacy default stream, other streams of the process, the order
+    # of the measurements, NUMA placement (one node).  Open: profiles/r2_summary.md section 5e.)
     sampler.mark_end()
     clocks = sampler.stop()
 
     # ---- e2e: pinned host buffers, H2D(A,B) + matmul + D2H(C) per step, through the C-ABI
-    ha, hb, hc = (torch.empty(n, n, dtype=torch.float32).pin_memory() for _ in range(3))
-    ha.copy_(a.cpu()); hb.copy_(b.cpu())
+    ha.copy_(a, non_blocking=False); hb.copy_(b, non_blocking=False)
     host["mm_a"], host["mm_b"] = ha.numpy(), hb.numpy()
     nbytes = n * n * 4
 
