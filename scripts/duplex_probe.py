@@ -1,7 +1,8 @@
-"""Why does the H2D leg of nb200_sgemm_host slow down to ~30-36 GB/s once C row blocks go out?
-Part 1 (pure copies, torch streams): 64 MiB in / 64 MiB out in chunks, out chunk i gated on in chunk i; 1 or 2 streams per direction.
-Part 2: nb200_sgemm_host 4096^2 under the experiment switches of host_pipeline.cu (children, one env each).
-Output: JSON lines on stdout."""
+"""nb200_sgemm_host 4096^2 from pinned host buffers, one child process per environment (profiles/r2_summary.md sections 5d, 5e).
+Switches of the child (env): NB200_HOST_* (host_pipeline.cu), PROBE_N, PROBE_BATCHED=<n> (nb200_sgemm_batched_host, n x 2048^2),
+PROBE_EXTRA_STREAMS=<n>, PROBE_NULL_STREAM=1 (enqueue on torch's current = legacy default stream, as bench.py does), PROBE_SMI=<ms>
+(an nvidia-smi poller beside the calls), PROBE_BENCHLIKE=1 (150 resident products in every mode first, then CUDA-event timing of
+10 calls), PROBE_AFFINITY=<numa node>.  `--pure`: chunked duplex copies on torch streams first.  Output: JSON lines on stdout."""
 import json
 import os
 import subprocess
@@ -150,8 +151,10 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--pure" in sys.argv:
         pure_copies()
-    variants = [{"PROBE_AFFINITY": "0"}, {"PROBE_AFFINITY": "1"}, {}, {"PROBE_AFFINITY": "1"}, {"PROBE_AFFINITY": "0"},
-                {"PROBE_AFFINITY": "1", "NB200_HOST_WORKERS": "0", "NB200_HOST_BLOCKS": "8"}]
+    bl = {"PROBE_BENCHLIKE": "1", "PROBE_NULL_STREAM": "1"}
+    variants = [{}, {"NB200_HOST_WORKERS": "0", "NB200_HOST_BLOCKS": "8"}, {"NB200_HOST_BLOCKS": "8"}, {"NB200_HOST_BLOCKS": "32"}, {"NB200_HOST_WORKERS": "3"},
+                {"PROBE_NULL_STREAM": "1"}, {"PROBE_SMI": "20"}, {"PROBE_EXTRA_STREAMS": "8"}, dict(bl), dict(bl), {"PROBE_N": "8192"}, {"PROBE_N": "2048"},
+                {"PROBE_BATCHED": "16"}]
     for v in variants:
         env = dict(os.environ); env.update(v)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
@@ -160,7 +163,7 @@ if __name__ == "__main__":
             print(json.dumps({"env": v, "rc": r.returncode, "stderr": r.stderr[-600:]}))
         sys.stdout.flush()
     # one traced call of the two most interesting variants
-    for v in ({"PROBE_AFFINITY": "1"},):
+    for v in ({}, {"NB200_HOST_WORKERS": "0", "NB200_HOST_BLOCKS": "8"}):
         env = dict(os.environ); env.update(v); env["NB200_HOST_TRACE"] = "1"
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=300)
         lines = [ln for ln in r.stderr.splitlines() if ln.startswith("[nb200_sgemm_host]")]
