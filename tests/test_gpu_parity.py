@@ -963,6 +963,30 @@ def test_comparisons_vs_oracle(nb, op):
     assert (got[::7] == 0).all()
 
 
+def test_comparison_and_transpose_phpt_golden_vectors(nb):
+    """tests/logic/003..008-*.phpt and tests/manipulation/001-ndarray-transpose.phpt (tests/golden/compare_vectors.json): the
+    comparison kernels give the printed 0 / 1 masks; the 2-D transposes go through nb200_transpose2d (the 1-D case is the identity
+    and the (1, 1, 4) case only permutes unit dimensions: no data movement, not kernel work)."""
+    import ctypes as C
+    import json
+    import os
+    lib = nb.lib()
+    for rec in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "compare_vectors.json")))["vectors"]:
+        exp = np.asarray(rec["expect"], np.float32)
+        if rec["op"] != "transpose":
+            a, b = (nb.NDArray.array(np.asarray(v, np.float32)).gpu() for v in rec["args"])
+            np.testing.assert_array_equal(nb.nd.binary(rec["op"], a, b).toArray(), exp, err_msg=str(rec))
+            continue
+        x = np.asarray(rec["args"][0], np.float32)
+        if x.ndim != 2:
+            assert exp.size == x.size and exp.ravel().tolist() == x.ravel().tolist()
+            continue
+        dx, do = _dev(nb, x), _dev(nb, np.zeros(exp.shape, np.float32))
+        assert lib.nb200_transpose2d(do, dx, x.shape[0], x.shape[1]) == 0, lib.nb200_last_error()
+        np.testing.assert_array_equal(_fetch(nb, do, exp.shape), exp, err_msg=str(rec))
+        lib.nb200_free(dx); lib.nb200_free(do)
+
+
 def test_array_equal(nb):
     a = _rng(1).random((100, 37), dtype=np.float32)
     A = nb.NDArray.array(a).gpu()

@@ -176,6 +176,27 @@ def test_all_allclose_golden_vectors(rec):
         assert getattr(oracle.ref, rec["op"])(*args) == rec["expect"]
 
 
+def _compare_vectors():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "compare_vectors.json")))["vectors"]
+
+
+@pytest.mark.parametrize("rec", _compare_vectors(), ids=lambda r: f"{r['op']}-{np.asarray(r['args'][0]).ndim}d")
+def test_comparison_and_transpose_golden_vectors(rec):
+    """tests/logic/003..008-*.phpt: the port and the reference's object code print the same 0 / 1 masks; the transpose vectors of
+    tests/manipulation/001-ndarray-transpose.phpt pin the layout the GPU test checks nb200_transpose2d against (numpy's .T)."""
+    exp = np.asarray(rec["expect"], np.float32)
+    if rec["op"] == "transpose":
+        x = np.asarray(rec["args"][0], np.float32)
+        np.testing.assert_array_equal(x.T if x.ndim == 2 else x.reshape(exp.shape), exp)
+        return
+    a, b = (np.asarray(v, np.float32) for v in rec["args"])
+    np.testing.assert_array_equal(oracle.port.binary(rec["op"], a, b), exp)
+    if oracle.ref.available:
+        np.testing.assert_array_equal(oracle.ref.binary(rec["op"], a, b), exp)
+
+
 def test_all_allclose_intended_semantics_where_the_reference_loops_are_broken():
     """oracle/port.c documents the two reference bugs; this pins what the port (and the kernels checked against it) do instead."""
     x = np.arange(1, 41, dtype=np.float32)
