@@ -1,9 +1,10 @@
 // Host-operand entry points: the step either side of the hot path (SURVEY.md §8 f, N3).  The reference moves whole
 // arrays with a pageable, blocking cudaMemcpy on the default stream (NDArray_ToGPU / NDArray_ToCPU,
 // src/ndarray.c:1037-1093) and only then computes.  nb200_sgemm_host pipelines instead:
-//   copy-in stream : B (once), then A row blocks            H2D
-//   compute stream : lo-split + tcgen05 GEMM per row block  (waits on the block's H2D event)
-//   copy-out stream: C row blocks                           D2H (overlaps the next blocks' H2D: PCIe is full duplex)
+//   copy-in stream     : B (once), then A row blocks                                   H2D
+//   two worker streams : per row block, in stream order: wait for the block's H2D event, lo-split, tcgen05 GEMM, D2H of its C rows
+//                        (the D2H overlaps the next blocks' H2D: PCIe is full duplex; why not a separate copy-out stream: see below)
+// nb200_sgemm_batched_host keeps copy-in / compute / copy-out streams (upload-bound: a chunk's download is half its upload).
 #include "common.cuh"
 #include <cstdlib>
 
@@ -138,7 +139,7 @@ extern "C" int nb200_sgemm_host(float *C_host, const float *A_host, const float 
         for (int64_t i = 0; i < nblk; i++) { cudaEventCreate(&trIn[i]); cudaEventCreate(&trDone[i]); cudaEventCreate(&trOut[i]); }
         cudaEventRecord(tr0, c.stream);
     }
-    // Stream structure (measured with scripts/probes/pcie_probe.cu, profiles/r2_pcie_probe.md): with the obvious three streams
+    // Stream structure (measured with scripts/probes/pcie_probe.cu: profiles/r2_pcie_probe.jsonl, profiles/r2_summary.md section 5d): with the obvious three streams
     // (copy-in, compute, copy-out, an event pair per block) the upload of A drops to ~36 GB/s as soon as C blocks go out, although
     // the same copies WITHOUT a kernel in the dependency chain keep 48-49 GB/s each way.  Giving every row block's split + GEMM +
     // D2H to one of two worker streams IN STREAM ORDER (the only cross-stream edge left per block is copy-in -> worker) keeps the
